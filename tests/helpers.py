@@ -1,0 +1,146 @@
+"""Shared test plumbing: load a model package against a chosen MinkowskiEngine implementation.
+
+The model files (ours under unscene3d_b200/models, the reference's under /root/reference/models)
+bind `MinkowskiEngine` at import time, so the same source can be imported twice under different
+package names — once over the CPU oracle, once over the CUDA shim — inside one process.
+"""
+import collections
+import collections.abc
+import contextlib
+import importlib
+import importlib.util
+import os
+import sys
+import types
+import zlib
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REFERENCE = "/root/reference"
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+_ME_KEYS = ["MinkowskiEngine", "MinkowskiEngine.MinkowskiOps", "MinkowskiEngine.MinkowskiPooling", "MinkowskiEngine.utils"]
+
+
+@contextlib.contextmanager
+def minkowski_as(modules: dict):
+    """Temporarily make `import MinkowskiEngine` resolve to `modules` (name -> module object)."""
+    saved = {k: sys.modules.get(k) for k in _ME_KEYS}
+    sys.modules.update(modules)
+    try:
+        yield
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+def oracle_me_modules():
+    from oracle import me_cpu
+
+    return me_cpu.as_module_tree()
+
+
+def load_package(pkg_dir: str, alias: str, me_modules: dict):
+    """Import the package at `pkg_dir` under the name `alias` with MinkowskiEngine := me_modules."""
+    if alias in sys.modules:
+        return sys.modules[alias]
+    with minkowski_as(me_modules):
+        spec = importlib.util.spec_from_file_location(alias, os.path.join(pkg_dir, "__init__.py"),
+                                                      submodule_search_locations=[pkg_dir])
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[alias] = mod
+        try:
+            spec.loader.exec_module(mod)
+        except Exception:
+            for k in [k for k in sys.modules if k == alias or k.startswith(alias + ".")]:
+                del sys.modules[k]
+            raise
+    return mod
+
+
+def our_models_on_oracle():
+    return load_package(os.path.join(REPO, "unscene3d_b200", "models"), "oracle_backed_models", oracle_me_modules())
+
+
+def have_reference() -> bool:
+    return os.path.isdir(os.path.join(REFERENCE, "models"))
+
+
+def reference_models_on_oracle():
+    """The UNMODIFIED reference `models` package over the oracle (build container only).
+    The reference uses absolute imports (`from models.resnet import ...`), so it has to be imported
+    under its own name with /root/reference on sys.path."""
+    assert have_reference()
+    collections.Set = collections.abc.Set  # py3.12 skew, utils/utils.py:340
+    if "models" in sys.modules and getattr(sys.modules["models"], "__file__", "").startswith(REFERENCE):
+        return sys.modules["models"]
+    with minkowski_as(oracle_me_modules()):
+        sys.path.insert(0, REFERENCE)
+        try:
+            for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
+                del sys.modules[k]
+            mod = importlib.import_module("models")
+            importlib.import_module("models.res16unet")
+        finally:
+            sys.path.remove(REFERENCE)
+    return mod
+
+
+class Cfg:
+    """Stand-in for the hydra node the backbones read (conf/model/mask3d.yaml:36-47)."""
+
+    def __init__(self, **kw):
+        self.bn_momentum = 0.02
+        self.conv1_kernel_size = 3
+        self.dilations = [1, 1, 1, 1]
+        self.__dict__.update(kw)
+
+
+def deterministic_state(module: torch.nn.Module, seed: int = 0):
+    """Name-keyed, construction-order-independent weights (same recipe as
+    unscene3d_b200.utils.seeded_init, restated here so tests do not depend on it)."""
+    out = {}
+    for name, t in module.state_dict().items():
+        g = torch.Generator().manual_seed((seed * 1000003 + zlib.crc32(name.encode())) & 0x7FFFFFFF)
+        if name.endswith("num_batches_tracked"):
+            out[name] = torch.zeros_like(t)
+        elif name.endswith("running_mean"):
+            out[name] = (torch.rand(t.shape, generator=g) - 0.5) * 0.2
+        elif name.endswith("running_var"):
+            out[name] = 0.5 + torch.rand(t.shape, generator=g)
+        elif ".bn.weight" in name or name.endswith("norm.weight"):
+            out[name] = 0.5 + torch.rand(t.shape, generator=g)
+        elif ".bn.bias" in name or name.endswith("norm.bias"):
+            out[name] = (torch.rand(t.shape, generator=g) - 0.5) * 0.4
+        else:
+            fan = t.shape[-2] * (t.shape[0] if t.ndim == 3 else 1) if t.ndim >= 2 else max(t.numel(), 1)
+            bound = (3.0 / fan) ** 0.5 * 1.4
+            out[name] = (torch.rand(t.shape, generator=g) * 2 - 1) * bound
+    return out
+
+
+def random_scene(n_target: int, seed: int, batch: int = 1, extent: int = 24, negative: bool = True):
+    """Small random voxel cloud on a few noisy sheets (surface-like, with negative coordinates)."""
+    rng = np.random.default_rng(seed)
+    coords = []
+    for b in range(batch):
+        pts = []
+        while sum(len(p) for p in pts) < n_target * 2:
+            u = rng.integers(0, extent, size=(n_target, 2))
+            axis = rng.integers(0, 3)
+            h = rng.integers(0, extent) + (rng.random(n_target) < 0.3).astype(np.int64)
+            p = np.insert(u, axis, h, axis=1)
+            pts.append(p)
+        p = np.concatenate(pts)
+        if negative:
+            p = p - extent // 2
+        _, first = np.unique(p, axis=0, return_index=True)
+        p = p[np.sort(first)][:n_target]
+        coords.append(np.concatenate([np.full((p.shape[0], 1), b), p], 1))
+    return np.concatenate(coords).astype(np.int32)

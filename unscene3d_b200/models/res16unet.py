@@ -1,0 +1,225 @@
+"""Res16UNet sparse-voxel backbones — host-side mirror of the reference's models/res16unet.py
+(Res16UNetBase :9-297, variants :300-425, Res16UNet34CMultiRes :428-505), models/resnet.py
+(ResNetBase ctor protocol :18-26, BN init :90-94, _make_layer :96-149) and models/model.py (:4-17).
+
+Topology (reference forward, models/res16unet.py:224-297):
+
+    stem   conv0p1s1 k3 -> bn0 -> relu                                   (stride 1)   = out_p1
+    enc i  conv{i}p{s}s2 k2s2 -> bn{i} -> relu -> block{i}               i=1..4       (strides 2,4,8,16)
+    dec j  convtr{j}p{s}s2 k2s2^T -> bntr{j} -> relu -> cat(skip) -> block{j+1}   j=4..7   (back to 8,4,2,1)
+    final  1x1 conv (+bias) — a parameter of every variant, applied only by the *MultiRes forward.
+
+The class below builds that from two small tables instead of spelling each layer out; attribute and
+therefore state-dict names are the reference's (conv0p1s1, bn0, block1.0.conv1, block2.0.downsample.0,
+convtr4p16s2, bntr4, final, ...), as are the quirks that affect numerics: blocks are created WITHOUT
+the configured bn_momentum (in-block BatchNorm keeps momentum 0.1 while stem/transition/downsample
+BatchNorm use config.bn_momentum, models/resnet.py:125-147), and BatchNorm affine parameters are
+reset to (1, 0) after construction.
+"""
+import torch.nn as nn
+import MinkowskiEngine as ME
+import MinkowskiEngine.MinkowskiOps as me
+from MinkowskiEngine import MinkowskiNetwork, MinkowskiReLU
+
+from .modules.common import ConvType, NormType, conv, conv_tr, get_norm
+from .modules.resnet_block import BasicBlock, Bottleneck
+
+
+class Model(MinkowskiNetwork):
+    """Base of every sparse network: remembers channel counts and the config object."""
+
+    OUT_PIXEL_DIST = -1
+
+    def __init__(self, in_channels, out_channels, config, D, **kwargs):
+        super().__init__(D)
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.config = config
+
+
+class ResNetBase(Model):
+    """Constructor protocol shared by the backbones: build layers, then reset BatchNorm affine."""
+
+    BLOCK = None
+    LAYERS = ()
+    INIT_DIM = 64
+    PLANES = (64, 128, 256, 512)
+    OUT_PIXEL_DIST = 32
+    CONV_TYPE = ConvType.HYPERCUBE
+
+    def __init__(self, in_channels, out_channels, config, D=3, **kwargs):
+        assert self.BLOCK is not None
+        assert self.OUT_PIXEL_DIST > 0
+        super().__init__(in_channels, out_channels, config, D, **kwargs)
+        self.network_initialization(in_channels, out_channels, config, D)
+        self.weight_initialization()
+
+    def network_initialization(self, in_channels, out_channels, config, D):
+        raise NotImplementedError
+
+    def weight_initialization(self):
+        for m in self.modules():
+            if isinstance(m, ME.MinkowskiBatchNorm):
+                nn.init.constant_(m.bn.weight, 1)
+                nn.init.constant_(m.bn.bias, 0)
+
+    def _make_layer(self, block, planes, blocks, stride=1, dilation=1, norm_type=NormType.BATCH_NORM, bn_momentum=0.1):
+        width = planes * block.expansion
+        shortcut = None
+        if stride != 1 or self.inplanes != width:
+            shortcut = nn.Sequential(
+                conv(self.inplanes, width, kernel_size=1, stride=stride, bias=False, D=self.D),
+                get_norm(norm_type, width, D=self.D, bn_momentum=bn_momentum),
+            )
+        stack = [block(self.inplanes, planes, stride=stride, dilation=dilation, downsample=shortcut,
+                       conv_type=self.CONV_TYPE, D=self.D)]
+        self.inplanes = width
+        stack += [block(width, planes, stride=1, dilation=dilation, conv_type=self.CONV_TYPE, D=self.D)
+                  for _ in range(1, blocks)]
+        return nn.Sequential(*stack)
+
+
+class Res16UNetBase(ResNetBase):
+    BLOCK = None
+    PLANES = (32, 64, 128, 256, 256, 256, 256, 256)
+    DILATIONS = (1, 1, 1, 1, 1, 1, 1, 1)
+    LAYERS = (2, 2, 2, 2, 2, 2, 2, 2)
+    INIT_DIM = 32
+    OUT_PIXEL_DIST = 1
+    NORM_TYPE = NormType.BATCH_NORM
+    NON_BLOCK_CONV_TYPE = ConvType.SPATIAL_HYPERCUBE
+    CONV_TYPE = ConvType.SPATIAL_HYPERCUBE_TEMPORAL_HYPERCROSS
+
+    # encoder stage i (1-based) consumes tensor stride 2**(i-1); decoder stage j consumes 2**(8-j)
+    _ENC = ((1, 1), (2, 2), (3, 4), (4, 8))          # (stage, incoming tensor stride)
+    _DEC = ((4, 16), (5, 8), (6, 4), (7, 2))
+
+    def __init__(self, in_channels, out_channels, config, D=3, out_fpn=False, **kwargs):
+        super().__init__(in_channels, out_channels, config, D)
+        self.out_fpn = out_fpn
+
+    def network_initialization(self, in_channels, out_channels, config, D):
+        mom = config.bn_momentum
+        X = self.BLOCK.expansion
+
+        def st(n, m):  # spatial n, temporal m
+            return n if D == 3 else [n, n, n, m]
+
+        if D == 4:
+            self.OUT_PIXEL_DIST = st(self.OUT_PIXEL_DIST, 1)
+
+        def stage(idx):
+            return self._make_layer(self.BLOCK, self.PLANES[idx], self.LAYERS[idx], dilation=self.DILATIONS[idx],
+                                    norm_type=self.NORM_TYPE, bn_momentum=mom)
+
+        self.inplanes = self.INIT_DIM
+        self.conv0p1s1 = conv(in_channels, self.inplanes, kernel_size=st(config.conv1_kernel_size, 1), stride=1,
+                              dilation=1, conv_type=self.NON_BLOCK_CONV_TYPE, D=D)
+        self.bn0 = get_norm(self.NORM_TYPE, self.inplanes, D, bn_momentum=mom)
+
+        for i, s in self._ENC:
+            setattr(self, f"conv{i}p{s}s2", conv(self.inplanes, self.inplanes, kernel_size=st(2, 1), stride=st(2, 1),
+                                                 dilation=1, conv_type=self.NON_BLOCK_CONV_TYPE, D=D))
+            setattr(self, f"bn{i}", get_norm(self.NORM_TYPE, self.inplanes, D, bn_momentum=mom))
+            setattr(self, f"block{i}", stage(i - 1))
+
+        # widths of the skip tensors, coarse to fine: block3, block2, block1 outputs, then the stem
+        skips = (self.PLANES[2] * X, self.PLANES[1] * X, self.PLANES[0] * X, self.INIT_DIM)
+        for (j, s), skip in zip(self._DEC, skips):
+            setattr(self, f"convtr{j}p{s}s2", conv_tr(self.inplanes, self.PLANES[j], kernel_size=st(2, 1),
+                                                      upsample_stride=st(2, 1), dilation=1, bias=False,
+                                                      conv_type=self.NON_BLOCK_CONV_TYPE, D=D))
+            setattr(self, f"bntr{j}", get_norm(self.NORM_TYPE, self.PLANES[j], D, bn_momentum=mom))
+            self.inplanes = self.PLANES[j] + skip
+            setattr(self, f"block{j + 1}", stage(j))
+
+        self.final = conv(self.PLANES[7], out_channels, kernel_size=1, stride=1, bias=True, D=D)
+        self.relu = MinkowskiReLU(inplace=True)
+
+    # ------------------------------------------------------------------------------------------
+    def _encode(self, x):
+        """Returns the five encoder outputs, fine to coarse: stem, block1..block4."""
+        outs = [self.relu(self.bn0(self.conv0p1s1(x)))]
+        for i, s in self._ENC:
+            t = getattr(self, f"conv{i}p{s}s2")(outs[-1])
+            t = self.relu(getattr(self, f"bn{i}")(t))
+            outs.append(getattr(self, f"block{i}")(t))
+        return outs
+
+    def _decode(self, enc):
+        """Returns the four decoder outputs, coarse to fine: block5..block8."""
+        out, ups = enc[-1], []
+        for (j, s), skip in zip(self._DEC, reversed(enc[:-1])):
+            t = getattr(self, f"convtr{j}p{s}s2")(out)
+            t = self.relu(getattr(self, f"bntr{j}")(t))
+            out = getattr(self, f"block{j + 1}")(me.cat(t, skip))
+            ups.append(out)
+        return ups
+
+    def forward(self, x):
+        enc = self._encode(x)
+        ups = self._decode(enc)
+        if not self.out_fpn:
+            return ups[-1]
+        return ups[-1], [enc[-1]] + ups
+
+
+class Res16UNet14(Res16UNetBase):
+    BLOCK = BasicBlock
+    LAYERS = (1, 1, 1, 1, 1, 1, 1, 1)
+
+
+class Res16UNet18(Res16UNetBase):
+    BLOCK = BasicBlock
+    LAYERS = (2, 2, 2, 2, 2, 2, 2, 2)
+
+
+class Res16UNet34(Res16UNetBase):
+    BLOCK = BasicBlock
+    LAYERS = (2, 3, 4, 6, 2, 2, 2, 2)
+
+
+class Res16UNet50(Res16UNetBase):
+    BLOCK = Bottleneck
+    LAYERS = (2, 3, 4, 6, 2, 2, 2, 2)
+
+
+class Res16UNet101(Res16UNetBase):
+    BLOCK = Bottleneck
+    LAYERS = (2, 3, 4, 23, 2, 2, 2, 2)
+
+
+def _variant(name, base, **attrs):
+    return type(name, (base,), dict(attrs, __module__=__name__, __doc__=f"{base.__name__} with {attrs}"))
+
+
+# decoder-width variants (reference models/res16unet.py:325-384)
+Res16UNet14A = _variant("Res16UNet14A", Res16UNet14, PLANES=(32, 64, 128, 256, 128, 128, 96, 96))
+Res16UNet14A2 = _variant("Res16UNet14A2", Res16UNet14A, LAYERS=(1, 1, 1, 1, 2, 2, 2, 2))
+Res16UNet14B = _variant("Res16UNet14B", Res16UNet14, PLANES=(32, 64, 128, 256, 128, 128, 128, 128))
+Res16UNet14B2 = _variant("Res16UNet14B2", Res16UNet14B, LAYERS=(1, 1, 1, 1, 2, 2, 2, 2))
+Res16UNet14B3 = _variant("Res16UNet14B3", Res16UNet14B, LAYERS=(2, 2, 2, 2, 1, 1, 1, 1))
+Res16UNet14C = _variant("Res16UNet14C", Res16UNet14, PLANES=(32, 64, 128, 256, 192, 192, 128, 128))
+Res16UNet14D = _variant("Res16UNet14D", Res16UNet14, PLANES=(32, 64, 128, 256, 384, 384, 384, 384))
+Res16UNet18A = _variant("Res16UNet18A", Res16UNet18, PLANES=(32, 64, 128, 256, 128, 128, 96, 96))
+Res16UNet18B = _variant("Res16UNet18B", Res16UNet18, PLANES=(32, 64, 128, 256, 128, 128, 128, 128))
+Res16UNet18D = _variant("Res16UNet18D", Res16UNet18, PLANES=(32, 64, 128, 256, 384, 384, 384, 384))
+Res16UNet34A = _variant("Res16UNet34A", Res16UNet34, PLANES=(32, 64, 128, 256, 256, 128, 64, 64))
+Res16UNet34B = _variant("Res16UNet34B", Res16UNet34, PLANES=(32, 64, 128, 256, 256, 128, 64, 32))
+Res16UNet34C = _variant("Res16UNet34C", Res16UNet34, PLANES=(32, 64, 128, 256, 256, 128, 96, 96))
+Custom30M = _variant("Custom30M", Res16UNet34, PLANES=(32, 64, 128, 256, 128, 64, 64, 32))
+Res16UNet34D = _variant("Res16UNet34D", Res16UNet34, PLANES=(32, 64, 128, 256, 256, 128, 96, 128))
+
+
+class Res16UNet34CMultiRes(Res16UNet34C):
+    """Pseudo-mask feature extractor (reference :428-505): applies `final` and returns every decoder
+    resolution by name."""
+
+    def forward(self, x):
+        enc = self._encode(x)
+        res_8, res_4, res_2, res_1 = self._decode(enc)
+        return self.final(res_1), {"res_1": res_1, "res_2": res_2, "res_4": res_4, "res_8": res_8, "res_16": enc[-1]}
+
+
+class Res16UNet34DMultiRes(Res16UNet34CMultiRes):
+    PLANES = (32, 64, 128, 256, 256, 256, 256, 512)
