@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""Headline benchmark: voxels/s for forward+backward of Res16UNet34C on synthetic 200k-voxel
+ScanNet-shaped scenes (BASELINE.json metric, configs[1]) on 1..8 B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one scene (batch 1) through the whole hot path: coordinate-manager construction from the
+[N,4] coordinate matrix (hash insert, 4 stride maps, 9 kernel maps), backbone forward, scalar loss,
+backward through every layer.  Scenes are independent, so N GPUs run N scenes per step with no
+data-path collective (weak scaling); the timed region is bracketed by barrier + synchronize, timed
+with CUDA events, and the maximum over ranks is reported by rank 0 as ONE JSON line.
+
+Legs:
+  value      inputs resident in HBM, device-timed, all ranks
+  e2e        same step fed from pinned HOST buffers (H2D inside the timed region) + D2H of the loss
+  roofline   per-launch CUDA-event timing of the dominant kernel (sparse-conv gather, fwd + dgrad)
+             against its algorithmic bytes and MEASURED_PEAKS.json
+  cpu_baseline  the CPU oracle (oracle/me_cpu.py, "port": same gather-GEMM-scatter algorithm as
+             MinkowskiEngine's CPU path, which is not installable here) on the host cores, rank 0, N=1
+  --impl reference   the same CPU oracle as the reference arm (MinkowskiEngine is absent)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "voxels/sec fwd+bwd Res16UNet34C @200k-voxel scenes"
+UNIT = "voxels/s"
+N_VOXELS = 200_000
+CPU_SAMPLE_VOXELS = 50_000
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+# ------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.samples, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for ts, line in self.samples:
+            if not (t0 - 0.05 <= ts <= t1 + 0.15):
+                continue
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                smax = float(p[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------- CPU arm
+def cpu_oracle_run(steps, warmup, n_voxels, seed=0):
+    """Times the CPU oracle (Res16UNet34C fwd+bwd incl. coordinate-manager construction) on all host threads."""
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import Cfg, our_models_on_oracle
+    from oracle import me_cpu
+    from unscene3d_b200_synthetic import make_scene
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    net = our_models_on_oracle().res16unet.Res16UNet34C(3, 20, Cfg(), D=3, out_fpn=True).train()
+    scene = make_scene(n_voxels, seed=seed, with_masks=False)
+    c4 = torch.from_numpy(np.concatenate([np.zeros((scene.n, 1), np.int32), scene.coords], 1))
+    feats = torch.from_numpy(scene.colors)
+    w = torch.linspace(-1, 1, 96)
+
+    def step():
+        x = me_cpu.SparseTensor(feats, c4)
+        out, _ = net(x)
+        (out.F * w).mean().backward()
+        net.zero_grad(set_to_none=True)
+
+    small = make_scene(5000, seed=seed + 1, with_masks=False)
+    c4s = torch.from_numpy(np.concatenate([np.zeros((small.n, 1), np.int32), small.coords], 1))
+    for _ in range(max(warmup, 1)):
+        out, _ = net(me_cpu.SparseTensor(torch.from_numpy(small.colors), c4s))
+        (out.F * w).mean().backward()
+        net.zero_grad(set_to_none=True)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return n_voxels * steps / dt, dt / steps * 1e3, torch.get_num_threads()
+
+
+def _load_synthetic_standalone():
+    """The scene generator is pure numpy; load it without importing the CUDA package (CPU arm)."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("unscene3d_b200_synthetic", os.path.join(ROOT, "unscene3d_b200", "synthetic.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["unscene3d_b200_synthetic"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def run_reference(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return 0
+    _load_synthetic_standalone()
+    v, ms, threads = cpu_oracle_run(args.steps, min(args.warmup, 2), CPU_SAMPLE_VOXELS)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "Res16UNet34C fwd+bwd, synthetic ScanNet-shaped scene, batch=1 (BASELINE configs[1])",
+                   "sample": f"{CPU_SAMPLE_VOXELS}-voxel scene per step (same generator; voxels/s is size-normalised)"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} steps of a {CPU_SAMPLE_VOXELS}-voxel scene, CPU oracle (gather-GEMM-scatter restatement; MinkowskiEngine not installable offline)"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = env_int("WORLD_SIZE", 1)
+    rank = env_int("RANK", 0)
+    local_rank = env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import unscene3d_b200
+    from unscene3d_b200 import _lib, engine, models
+    from unscene3d_b200.engine import functional as Fn
+    from unscene3d_b200.synthetic import level_sizes, make_scene
+    from unscene3d_b200.utils import BackboneConfig, conv_layer_bytes, seeded_state
+
+    scene = make_scene(args.voxels, seed=rank, with_masks=False)
+    c4_host = torch.from_numpy(np.concatenate([np.zeros((scene.n, 1), np.int32), scene.coords], 1)).pin_memory()
+    f_host = torch.from_numpy(scene.colors).pin_memory()
+    c4_dev, f_dev = c4_host.to(dev), f_host.to(dev)
+
+    net = models.Res16UNet34C(3, 20, BackboneConfig(), D=3, out_fpn=True)
+    net.load_state_dict(seeded_state(net, 0))
+    net = net.to(dev).train()
+    wvec = torch.linspace(-1, 1, 96, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    loss_host = torch.zeros(1).pin_memory()
+
+    def step(coords, feats):
+        x = engine.SparseTensor(feats, coords)
+        out, _ = net(x)
+        loss = (out.F * wvec).mean()
+        loss.backward()
+        net.zero_grad(set_to_none=True)
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        s.record()
+        for _ in range(steps):
+            flush.zero_()
+            fn()
+        e.record()
+        barrier()
+        t1 = time.time()
+        ms = torch.tensor([s.elapsed_time(e)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), t0, t1
+
+    def step_resident():
+        step(c4_dev, f_dev)
+
+    def step_e2e():
+        c = c4_host.to(dev, non_blocking=True)
+        f = f_host.to(dev, non_blocking=True)
+        loss = step(c, f)
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    _lib.reset_launch_count()
+    ms_total, t0, t1 = timed(step_resident, args.steps)
+    launches = _lib.launch_count()
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    ms_e2e, _, _ = timed(step_e2e, args.steps)
+
+    value = world * args.voxels * args.steps / (ms_total * 1e-3)
+    e2e_value = world * args.voxels * args.steps / (ms_e2e * 1e-3)
+
+    roofline = cpu_baseline = None
+    if rank == 0:
+        # ---- roofline leg: per-launch event timing of the conv kernels over a few extra steps
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peaks = json.load(open(peaks_path))
+            peak, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        prof_steps = 3
+        with Fn.KernelTimer() as kt:
+            for _ in range(prof_steps):
+                flush.zero_()
+                step_resident()
+        recs = kt.summary()
+        dom = [r for r in recs if r[0] in ("fwd", "dgrad")]
+        dom_bytes = sum(conv_layer_bytes(ni, no, kv, ci, co, k) for (k, ni, no, kv, ci, co, ms) in dom)
+        dom_ms = sum(r[6] for r in dom)
+        wg = [r for r in recs if r[0] == "wgrad"]
+        wg_ms = sum(r[6] for r in wg)
+        achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+        roofline = {"bound": "hbm", "kernel": "us3d::k_gather_conv (sparse-conv forward + input-gradient launches)",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "peak_source": peak_src, "launches_per_step": len(dom) // prof_steps,
+                    "alg_bytes_per_step": dom_bytes / prof_steps, "kernel_ms_per_step": dom_ms / prof_steps,
+                    "wgrad_ms_per_step": wg_ms / prof_steps, "step_ms": ms_total / args.steps,
+                    "level_sizes": level_sizes(c4_host.numpy())}
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "bench_layers.json"), "w") as fh:
+            json.dump([{"kind": k, "n_in": ni, "n_out": no, "kvol": kv, "cin": ci, "cout": co, "ms": ms,
+                        "alg_bytes": conv_layer_bytes(ni, no, kv, ci, co, k)} for (k, ni, no, kv, ci, co, ms) in recs[: len(recs) // prof_steps]], fh)
+        # ---- CPU baseline leg (bounded sample), N=1 only
+        if world == 1 and not args.no_cpu_baseline:
+            _load_synthetic_standalone()
+            v, ms, threads = cpu_oracle_run(1, 1, args.voxels)
+            cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                            "sample": f"1 step of the full {args.voxels}-voxel scene after a 5k-voxel warm-up ({ms:.0f} ms); CPU oracle = "
+                                      "gather-GEMM-scatter restatement of the MinkowskiEngine CPU path (ME itself is not installable offline)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"Res16UNet34C fwd+bwd, synthetic ScanNet-shaped {args.voxels}-voxel scene, batch=1 per GPU (BASELINE configs[1])",
+                       "parallelism": f"dp{world} (one scene per GPU, no data-path collective)",
+                       "l2": "256 MiB buffer written between timed iterations (L2 flush)",
+                       "step": "coordinate-manager build + forward + loss + backward"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(c4_host.numel() * 4 + f_host.numel() * 4),
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--voxels", type=int, default=N_VOXELS)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    world = env_int("WORLD_SIZE", 1)
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun when called directly with --gpus N
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,134 @@
+/* us3d.h — C ABI of the B200-native UnScene3D hot path (libus3d.so, sm_100a).
+ *
+ * This is the drop-in boundary: what the reference reaches through MinkowskiEngine's pybind layer
+ * (MinkowskiEngine is an un-vendored dependency, /root/reference/.devcontainer/Dockerfile:50-51;
+ * the reference-side call sites are listed per function) and through its own pybind extensions
+ * (third_party/pointnet2/_ext_src/src/bindings.cpp:9-22, utils/cuda_utils/cuda_utils.cpp:49-54).
+ *
+ * Conventions (mirroring the reference's native boundaries):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless its name ends in _h;
+ *   - the caller allocates every output and scratch buffer, kernels fill them in place;
+ *   - dtypes are fixed: float32 features/weights, int32 coordinates and row indices, (b,x,y,z) rows;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises
+ *     unless stated ("[sync]": the function returns a host value and waits for the stream);
+ *   - return value 0 = ok, negative = error (us3d_last_error() gives the text, thread local).
+ */
+#ifndef US3D_H
+#define US3D_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define US3D_ABI_VERSION 3
+#define US3D_MAX_KVOL 27
+
+int us3d_abi_version(void);
+const char *us3d_last_error(void);
+/* number of kernels launched by this library since load / since the last reset (bench.py gpu_launches) */
+long long us3d_launch_count(void);
+void us3d_reset_launch_count(void);
+
+/* ---------------------------------------------------------------- coordinates (SURVEY §8(a) A1–A3)
+ * Open-addressing hash table over packed 64-bit voxel keys (b:10|x:18|y:18|z:18, biased), stored in
+ * global memory (L2-resident on B200): keys[cap] uint64, vals[cap] int32, cap a power of two.     */
+
+/* power-of-two capacity for n keys (load factor <= 0.5) */
+int us3d_hash_capacity(int n);
+
+/* Quantise + de-duplicate coordinate rows; replaces ME's CoordinateMap insert / stride
+ * (ME.SparseTensor(...) trainer/trainer.py:115-117; conv(..., stride=2) models/res16unet.py:51-116)
+ * and ME.utils.sparse_quantize (datasets/utils.py:266-270, 403-408).
+ *   coords[n,4]  int32 rows (b,x,y,z);  each spatial axis is floored to a multiple of tstride[a]
+ *   out_coords[n,4] unique rows in order of FIRST OCCURRENCE; out_first[n] the input row of each
+ *   unique row (ascending); inverse[n] = unique row of every input row; *out_count_h = #unique.
+ *   keys/vals: hash table of capacity cap, left holding key -> unique row for later lookups.
+ *   scratch: int32[2*n + 4096].                                                             [sync] */
+int us3d_coords_unique(const int32_t *coords, int n, int tsx, int tsy, int tsz, uint64_t *keys, int32_t *vals,
+                       int cap, int32_t *out_coords, int32_t *out_first, int32_t *inverse, int32_t *scratch,
+                       int *out_count_h, void *stream);
+
+/* Neighbour table ("kernel map", ME KernelGenerator HYPER_CUBE, models/modules/common.py:137-144):
+ *   nbr[k*n_q + q] = row r of the hashed map with coords_r == query[q] + offsets_h[k]  (or -1).
+ *   offsets_h[kvol,3] is a HOST array of int32 (already scaled by tensor stride / negated by caller).
+ *   tile_mask (optional, may be NULL): uint32[ceil(n_q/tile_rows)], bit k set iff any row of that
+ *   tile has a neighbour at offset k.                                                             */
+int us3d_kernel_map(const int32_t *query, int n_q, const int32_t *offsets_h, int kvol, const uint64_t *keys,
+                    const int32_t *vals, int cap, int32_t *nbr, uint32_t *tile_mask, int tile_rows, void *stream);
+
+/* ---------------------------------------------------------------- sparse convolution (A4, A5)
+ * Output-stationary gather convolution over a neighbour table:
+ *     Y[orow(j)] (=|+=) sum_k  X[nbr[k*n_rows + j]] · Wk        j = 0..n_rows-1
+ * with Wk = W[k] ([cin,cout], row-major) or, when transpose_w, W[kk]^T with W stored [kvol,cout,cin]
+ * and kk = flip_k ? kvol-1-k : k   (that is the dX pass of the same map).  orow(j) = out_rows ?
+ * out_rows[j] : j.  X rows have leading dimension ldx, Y rows ldy (so halves of a concatenation can
+ * be read / written in place).  bias (optional, [cout]) is added once per output row.
+ * Replaces MinkowskiConvolution / MinkowskiConvolutionTranspose forward and input-gradient
+ * (models/modules/common.py:146-155, 179-188).                                                    */
+int us3d_spconv_gather(const float *x, int ldx, const int32_t *nbr, int n_rows, int kvol, const float *w, int cin,
+                       int cout, int transpose_w, int flip_k, const float *bias, const int32_t *out_rows, float *y,
+                       int ldy, int accumulate, const uint32_t *tile_mask, void *stream);
+
+/* Weight gradient of the same map:  dW[k] += sum_j X[nbr[k*n_rows+j]]^T · dY[orow(j)]   ([kvol,cin,cout]).
+ * dW must be zero-initialised (or hold the value to accumulate into) by the caller.             */
+int us3d_spconv_wgrad(const float *x, int ldx, const int32_t *nbr, int n_rows, int kvol, const float *dy, int ldy,
+                      const int32_t *out_rows, float *dw, int cin, int cout, void *stream);
+
+/* ---------------------------------------------------------------- normalisation / elementwise (A6)
+ * BatchNorm1d over all rows (ME.MinkowskiBatchNorm, models/modules/common.py:20-22), train mode:
+ *   stats: double sum[c], sumsq[c] (caller zeroes) ; finalize -> mean[c], invstd[c] float and the
+ *   running statistics update (momentum, unbiased variance) exactly like torch.nn.BatchNorm1d.   */
+int us3d_bn_stats(const float *x, int ldx, int n, int c, double *sum, double *sumsq, void *stream);
+int us3d_bn_finalize(const double *sum, const double *sumsq, int n, int c, float eps, float momentum, float *mean,
+                     float *invstd, float *running_mean, float *running_var, void *stream);
+/* y = [relu]( (x-mean)*invstd*gamma + beta [+ residual] ) */
+int us3d_bn_apply(const float *x, int ldx, int n, int c, const float *mean, const float *invstd, const float *gamma,
+                  const float *beta, const float *residual, int ldr, int relu, float *y, int ldy, void *stream);
+/* backward of the fused op above.  g = dy * (relu ? y>0 : 1):  red[0..c) = sum g, red[c..2c) = sum g*xhat
+ * (double, caller zeroes); then dx = gamma*invstd*(g - red0/n - xhat*red1/n), dres = g.            */
+int us3d_bn_bwd_reduce(const float *dy, int lddy, const float *x, int ldx, const float *y, int ldy, int n, int c,
+                       const float *mean, const float *invstd, int relu, double *red, void *stream);
+int us3d_bn_bwd_apply(const float *dy, int lddy, const float *x, int ldx, const float *y, int ldy, int n, int c,
+                      const float *mean, const float *invstd, const float *gamma, int relu, const double *red,
+                      float *dx, int lddx, float *dres, int lddres, float *dgamma, float *dbeta, void *stream);
+/* inference-mode BN is us3d_bn_apply with mean=running_mean, invstd=rsqrt(running_var+eps) (host computes) */
+
+/* y = relu(x) ; dx = dy * (y > 0) ; z = a + b ; concat along channels / its inverse */
+int us3d_relu(const float *x, float *y, long long numel, void *stream);
+int us3d_relu_bwd(const float *dy, const float *y, float *dx, long long numel, void *stream);
+int us3d_add(const float *a, const float *b, float *z, long long numel, void *stream);
+int us3d_copy2d(const float *src, int lds, float *dst, int ldd, int n, int c, void *stream);
+
+/* ---------------------------------------------------------------- pooling (A7)
+ * MinkowskiAvg/Sum/MaxPooling(k2,s2) (models/mask3d.py:131,213,432): y[o] = reduce over PRESENT
+ * children nbr[k*n_out+o]; mode 0 = avg, 1 = sum, 2 = max.  bwd scatters through the same table.   */
+int us3d_pool_fwd(const float *x, int c, const int32_t *nbr, int n_out, int kvol, int mode, float *y, void *stream);
+int us3d_pool_bwd(const float *dy, const float *x, const float *y, int c, const int32_t *nbr, int n_out, int kvol,
+                  int mode, float *dx, void *stream);
+
+/* ---------------------------------------------------------------- decoder helpers
+ * Furthest point sampling, bit-compatible with third_party/pointnet2/_ext_src/src/sampling_gpu.cu:72-176
+ * (start at row 0, rows with |p|^2 <= 1e-3 skipped, ties to the lowest thread slot then lowest row;
+ * thread count = min(2^floor(log2 n), 512), _ext_src/include/cuda_utils.h:15-21).
+ *   xyz[b,n,3] float, temp[b,n] float scratch (caller fills with 1e10), idx[b,m] int32.          */
+int us3d_furthest_point_sampling(const float *xyz, int b, int n, int m, float *temp, int32_t *idx, void *stream);
+
+/* torch_scatter.scatter_mean(src[n,c], index[n], dim=0) (models/mask3d.py:223): out[s,c] zeroed by
+ * caller, count[s] float zeroed by caller; fwd accumulates then divides; bwd gathers dy/count.     */
+int us3d_segment_mean_fwd(const float *src, const int64_t *index, int n, int c, int s, float *out, float *count,
+                          void *stream);
+int us3d_segment_mean_bwd(const float *dout, const int64_t *index, const float *count, int n, int c, float *dsrc,
+                          void *stream);
+
+/* Hungarian matcher cost (models/matcher.py:97-168):  C[q,t] = w_mask * BCE + w_class * (-p[q, label_t])
+ * + w_dice * dice,  logits[s,q] (pred_masks[b], row = segment/point), tgt[t,s] float {0,1},
+ * prob[q,ncls] softmaxed class probabilities, labels[t] int64 (253 = ignore -> class cost -1).     */
+int us3d_matcher_cost(const float *logits, int s, int q, const float *tgt, int t, const float *prob, int ncls,
+                      const int64_t *labels, float w_class, float w_mask, float w_dice, float *cost, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* US3D_H */

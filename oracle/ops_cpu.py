@@ -1,0 +1,84 @@
+"""CPU restatements of the non-MinkowskiEngine native operators on the hot path.
+TEST INFRASTRUCTURE (see oracle/__init__.py).
+
+  furthest_point_sampling   third_party/pointnet2/_ext_src/src/sampling_gpu.cu:72-176 (+ cuda_utils.h:15-21)
+  scatter_mean              torch_scatter.scatter_mean as used at models/mask3d.py:223 (un-vendored dep)
+  matcher_cost              models/matcher.py:12-59, 97-160 (the reference functions themselves run on CPU;
+                            this restatement is validated against them in tests/test_oracle_reference.py)
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+def opt_n_threads(work_size: int) -> int:
+    """cuda_utils.h:15-21: min(2^floor(log2 n), 512), at least 1."""
+    pow_2 = int(np.log(float(work_size)) / np.log(2.0))
+    return max(min(1 << pow_2, 512), 1)
+
+
+def furthest_point_sampling(xyz: np.ndarray, m: int) -> np.ndarray:
+    """xyz float32 [n, 3] -> int32 [m].  Simulates the kernel's thread slots and its shared-memory
+    reduction tree literally (slot s is merged with s+h for h = T/2..1, lower slot kept on ties)."""
+    xyz = np.asarray(xyz, dtype=np.float32)
+    n = xyz.shape[0]
+    T = opt_n_threads(n)
+    temp = np.full(n, 1e10, dtype=np.float32)
+    idxs = np.zeros(m, dtype=np.int32)
+    mag = (xyz[:, 0] * xyz[:, 0] + xyz[:, 1] * xyz[:, 1] + xyz[:, 2] * xyz[:, 2]).astype(np.float32)
+    valid = ~(mag.astype(np.float64) <= 1e-3)
+    slots = np.arange(n) % T
+    old = 0
+    for j in range(1, m):
+        diff = xyz - xyz[old]
+        d = (diff[:, 0] * diff[:, 0] + diff[:, 1] * diff[:, 1] + diff[:, 2] * diff[:, 2]).astype(np.float32)
+        d2 = np.minimum(d, temp)
+        temp = np.where(valid, d2, temp)
+        # per-slot best: first strict maximum in row order among the slot's valid rows
+        dists = np.full(T, -1.0, dtype=np.float32)
+        dists_i = np.zeros(T, dtype=np.int64)
+        cand = np.where(valid, d2, -np.inf)
+        order = np.lexsort((np.arange(n), -cand, slots))  # by slot, then larger d2, then lower row
+        first_of_slot = np.concatenate([[True], slots[order][1:] != slots[order][:-1]])
+        best_rows = order[first_of_slot]
+        ok = cand[best_rows] > -1.0
+        dists[slots[best_rows][ok]] = cand[best_rows][ok]
+        dists_i[slots[best_rows][ok]] = best_rows[ok]
+        h = T // 2
+        while h >= 1:
+            v1, v2 = dists[:h].copy(), dists[h:2 * h].copy()
+            i1, i2 = dists_i[:h].copy(), dists_i[h:2 * h].copy()
+            dists[:h] = np.maximum(v1, v2)
+            dists_i[:h] = np.where(v2 > v1, i2, i1)
+            h //= 2
+        old = int(dists_i[0])
+        idxs[j] = old
+    return idxs
+
+
+def scatter_mean(src: torch.Tensor, index: torch.Tensor, dim: int = 0) -> torch.Tensor:
+    assert dim == 0
+    s = int(index.max()) + 1 if index.numel() else 0
+    out = torch.zeros((s, src.shape[1]), dtype=src.dtype).index_add_(0, index, src)
+    cnt = torch.zeros(s, dtype=src.dtype).index_add_(0, index, torch.ones(index.shape[0], dtype=src.dtype))
+    return out / cnt.clamp(min=1)[:, None]
+
+
+def matcher_cost(pred_logits_q: torch.Tensor, pred_mask_sq: torch.Tensor, tgt_mask_ts: torch.Tensor, tgt_labels: torch.Tensor,
+                 cost_class: float, cost_mask: float, cost_dice: float) -> torch.Tensor:
+    """Cost matrix [Q, T] of one scene (models/matcher.py:107-160, num_points == -1)."""
+    out_prob = pred_logits_q.softmax(-1)
+    ids = tgt_labels.clone()
+    ignore = ids == 253
+    ids[ignore] = 0
+    c_class = -out_prob[:, ids]
+    c_class[:, ignore] = -1.0
+    x = pred_mask_sq.T.float()
+    t = tgt_mask_ts.float()
+    hw = x.shape[1]
+    pos = F.binary_cross_entropy_with_logits(x, torch.ones_like(x), reduction="none")
+    neg = F.binary_cross_entropy_with_logits(x, torch.zeros_like(x), reduction="none")
+    c_mask = (torch.einsum("nc,mc->nm", pos, t) + torch.einsum("nc,mc->nm", neg, 1 - t)) / hw
+    s = x.sigmoid()
+    c_dice = 1 - (2 * torch.einsum("nc,mc->nm", s, t) + 1) / (s.sum(-1)[:, None] + t.sum(-1)[None, :] + 1)
+    return cost_mask * c_mask + cost_class * c_class + cost_dice * c_dice

@@ -1,0 +1,72 @@
+"""No-GPU checks of the drop-in boundary: libus3d.so loads, exports every function include/us3d.h
+declares (and nothing the header does not), and argument validation fails loudly without touching a
+device."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "us3d.h")
+
+
+def header_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(us3d_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from unscene3d_b200 import _lib
+
+    declared = header_functions()
+    assert len(declared) >= 20
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(raw, name), f"{name} declared in include/us3d.h but not exported by libus3d.so"
+    assert sorted(_lib.PROTOTYPES) == declared, "ctypes prototypes and header disagree"
+
+
+def test_abi_version_matches_header():
+    from unscene3d_b200 import _lib
+
+    ver = int(re.search(r"#define US3D_ABI_VERSION (\d+)", open(HEADER).read()).group(1))
+    assert _lib.ABI_VERSION == ver
+
+
+def test_argument_validation_reports_errors_without_a_device():
+    from unscene3d_b200 import _lib
+
+    lib = _lib.lib
+    assert lib.us3d_hash_capacity(1000) == 2048
+    assert lib.us3d_hash_capacity(0) == 1024
+    rc = lib.us3d_spconv_gather(0, 4, 0, 10, 99, 0, 4, 4, 0, 0, 0, 0, 0, 4, 0, 0, 0)
+    assert rc != 0 and b"kvol" in lib.us3d_last_error()
+    with pytest.raises(_lib.Us3dError):
+        _lib.check(lib.us3d_kernel_map(0, 10, (ctypes.c_int32 * 3)(), 1, 0, 0, 1000, 0, 0, 128, 0))
+
+
+def test_shim_modules_import_under_reference_names():
+    import unscene3d_b200  # noqa: F401
+    import MinkowskiEngine as ME
+    import MinkowskiEngine.MinkowskiOps as me
+    from MinkowskiEngine import MinkowskiNetwork, MinkowskiReLU, SparseTensor  # noqa: F401
+    from MinkowskiEngine.MinkowskiPooling import MinkowskiAvgPooling  # noqa: F401
+
+    for name in ["SparseTensor", "MinkowskiConvolution", "MinkowskiConvolutionTranspose", "KernelGenerator", "RegionType",
+                 "MinkowskiBatchNorm", "MinkowskiInstanceNorm", "MinkowskiReLU", "MinkowskiAvgPooling", "MinkowskiSumPooling",
+                 "MinkowskiAvgUnpooling", "MinkowskiNetwork", "utils", "MinkowskiAlgorithm", "SparseTensorQuantizationMode", "TensorField"]:
+        assert hasattr(ME, name), name
+    assert [ME.RegionType(i) for i in range(3)]  # evaluated at import by models/modules/common.py:70
+    assert hasattr(me, "cat") and hasattr(me, "SparseTensor")
+    assert all(hasattr(ME.utils, n) for n in ("sparse_quantize", "sparse_collate", "batched_coordinates"))
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "unscene3d_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f"{f} imports the oracle"

@@ -1,0 +1,324 @@
+"""GPU parity tests, operator level: every libus3d kernel (through the C ABI) against the CPU oracle on
+the same seeded inputs.  Integer results (coordinate maps, kernel maps, FPS indices) must be
+bit-exact; floating point within the tolerance written next to each assert (north_star: 1e-3
+relative on features; the exact-fp32 SIMT path is held to 1e-5).
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import random_scene
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import unscene3d_b200  # noqa: F401  (loads libus3d.so, fails loudly if missing)
+    from unscene3d_b200 import engine
+
+    return engine
+
+
+@pytest.fixture(scope="module")
+def ora():
+    from oracle import me_cpu
+
+    return me_cpu
+
+
+def rel_err(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp(min=1e-30))
+
+
+# --------------------------------------------------------------------------------------------- coords
+@pytest.mark.parametrize("n,batch,seed", [(1, 1, 0), (37, 1, 1), (2000, 2, 2), (30000, 3, 3)])
+def test_coordinate_maps_and_strides_bit_exact(eng, ora, n, batch, seed):
+    c = random_scene(n, seed, batch=batch, extent=40)
+    x = eng.SparseTensor(torch.zeros(c.shape[0], 1, device="cuda"), torch.from_numpy(c).cuda())
+    y = ora.SparseTensor(torch.zeros(c.shape[0], 1), torch.from_numpy(c))
+    assert torch.equal(x.C.cpu(), y.C)
+    kx, ky = x.coordinate_map_key, y.coordinate_map_key
+    for _ in range(4):
+        kx = x.coordinate_manager.stride(kx, (2, 2, 2))
+        ky = y.coordinate_manager.stride(ky, (2, 2, 2))
+        assert kx.tensor_stride == ky.tensor_stride
+        # same rows in the same (first-occurrence) order
+        assert torch.equal(x.coordinate_manager.get_coordinates(kx).cpu(), y.coordinate_manager.get_coordinates(ky))
+
+
+def test_duplicate_rows_keep_first_occurrence(eng, ora):
+    rng = np.random.default_rng(7)
+    base = random_scene(500, 5, batch=2, extent=12)
+    dup = base[rng.integers(0, base.shape[0], size=1500)]
+    feats = torch.arange(dup.shape[0], dtype=torch.float32)[:, None]
+    x = eng.SparseTensor(feats.cuda(), torch.from_numpy(dup).cuda())
+    y = ora.SparseTensor(feats, torch.from_numpy(dup))
+    assert torch.equal(x.C.cpu(), y.C)
+    assert torch.equal(x.F.cpu(), y.F)
+
+
+def test_sparse_quantize_matches_oracle(eng, ora):
+    rng = np.random.default_rng(3)
+    pts = rng.uniform(-3, 3, size=(5000, 3))
+    labels = rng.integers(0, 4, size=5000)
+    got = eng.sparse_quantize(pts, labels=labels, return_index=True, return_inverse=True, quantization_size=0.25)
+    exp = ora.sparse_quantize(pts, labels=labels, return_index=True, return_inverse=True, quantization_size=0.25)
+    for g, e in zip(got, exp):
+        assert np.array_equal(np.asarray(g), np.asarray(e))
+
+
+def table_to_pairs(nbr):
+    nbr = nbr.cpu().numpy()
+    out = []
+    for k in range(nbr.shape[0]):
+        o = np.nonzero(nbr[k] >= 0)[0]
+        out.append(set(zip(nbr[k][o].tolist(), o.tolist())))
+    return out
+
+
+@pytest.mark.parametrize("ksize,stride", [((3, 3, 3), 1), ((2, 2, 2), 2), ((3, 3, 3), 2)])
+def test_kernel_maps_bit_exact(eng, ora, ksize, stride):
+    c = random_scene(6000, 11, batch=2, extent=30)
+    x = eng.SparseTensor(torch.zeros(c.shape[0], 1, device="cuda"), torch.from_numpy(c).cuda())
+    y = ora.SparseTensor(torch.zeros(c.shape[0], 1), torch.from_numpy(c))
+    for level in range(3):
+        kx_in, ky_in = x.coordinate_map_key, y.coordinate_map_key
+        for _ in range(level):
+            kx_in = x.coordinate_manager.stride(kx_in, (2, 2, 2))
+            ky_in = y.coordinate_manager.stride(ky_in, (2, 2, 2))
+        kx_out = x.coordinate_manager.stride(kx_in, (stride,) * 3)
+        ky_out = y.coordinate_manager.stride(ky_in, (stride,) * 3)
+        fwd = x.coordinate_manager.forward_table(kx_in, kx_out, ksize)
+        exp = y.coordinate_manager.kernel_map(ky_in, ky_out, ksize)
+        got = table_to_pairs(fwd.nbr)
+        assert len(got) == len(exp)
+        for k in range(len(exp)):
+            assert got[k] == set(zip(exp[k][0].tolist(), exp[k][1].tolist())), f"offset {k} differs at level {level}"
+        # transposed table = same pairs with roles swapped
+        bwd, flip = x.coordinate_manager.backward_table(kx_in, kx_out, ksize)
+        gotT = table_to_pairs(bwd.nbr)
+        K = len(exp)
+        for k in range(K):
+            kk = K - 1 - k if flip else k
+            assert gotT[kk] == {(o, i) for (i, o) in got[k]}
+        # tile mask: bit k set iff the 128-row tile has a neighbour at offset k
+        nbr = fwd.nbr.cpu().numpy()
+        mask = fwd.mask.cpu().numpy().astype(np.uint32)
+        for t in range(mask.shape[0]):
+            want = 0
+            for k in range(K):
+                if (nbr[k, t * 128:(t + 1) * 128] >= 0).any():
+                    want |= 1 << k
+            assert int(mask[t]) == want
+
+
+# --------------------------------------------------------------------------------------------- convs
+def _pair(eng, ora, c, cin, seed=0):
+    torch.manual_seed(seed)
+    f = torch.randn(c.shape[0], cin)
+    fx = f.clone().cuda().requires_grad_()
+    fy = f.clone().requires_grad_()
+    x = eng.SparseTensor(fx, torch.from_numpy(c).cuda())
+    y = ora.SparseTensor(fy, torch.from_numpy(c))
+    return x, y, fx, fy
+
+
+def _sync_params(mx, my):
+    my.load_state_dict({k: v.cpu() for k, v in mx.state_dict().items()})
+
+
+@pytest.mark.parametrize("cin,cout,ks,stride,bias", [
+    (3, 32, 3, 1, False), (32, 32, 2, 2, False), (32, 64, 3, 1, False), (64, 64, 3, 1, False), (128, 96, 3, 1, False),
+    (96, 96, 3, 1, False), (256, 256, 3, 1, False), (384, 256, 1, 1, False), (96, 20, 1, 1, True), (5, 7, 3, 1, True),
+    (16, 24, 3, 2, False),
+])
+def test_convolution_forward_backward(eng, ora, cin, cout, ks, stride, bias):
+    c = random_scene(3000, 21, batch=2, extent=26)
+    x, y, fx, fy = _pair(eng, ora, c, cin)
+    mx = eng.MinkowskiConvolution(cin, cout, kernel_size=ks, stride=stride, bias=bias, dimension=3).cuda()
+    my = ora.MinkowskiConvolution(cin, cout, kernel_size=ks, stride=stride, bias=bias, dimension=3)
+    _sync_params(mx, my)
+    ox, oy = mx(x), my(y)
+    assert torch.equal(ox.C.cpu(), oy.C)
+    assert rel_err(ox.F, oy.F) < 1e-5
+    g = torch.randn_like(oy.F)
+    ox.F.backward(g.cuda())
+    oy.F.backward(g)
+    assert rel_err(fx.grad, fy.grad) < 1e-5
+    assert rel_err(mx.kernel.grad, my.kernel.grad) < 1e-5
+    if bias:
+        assert rel_err(mx.bias.grad, my.bias.grad) < 1e-5
+
+
+@pytest.mark.parametrize("cin,cout", [(256, 256), (128, 96), (96, 96), (6, 10)])
+def test_transposed_convolution_forward_backward(eng, ora, cin, cout):
+    c = random_scene(3000, 23, batch=2, extent=26)
+    x, y, _, _ = _pair(eng, ora, c, 4)
+    dx = eng.MinkowskiConvolution(4, cin, kernel_size=2, stride=2, dimension=3).cuda()
+    dy = ora.MinkowskiConvolution(4, cin, kernel_size=2, stride=2, dimension=3)
+    _sync_params(dx, dy)
+    ux = eng.MinkowskiConvolutionTranspose(cin, cout, kernel_size=2, stride=2, dimension=3).cuda()
+    uy = ora.MinkowskiConvolutionTranspose(cin, cout, kernel_size=2, stride=2, dimension=3)
+    _sync_params(ux, uy)
+    hx, hy = dx(x), dy(y)
+    hx = eng.SparseTensor(hx.F.detach().requires_grad_(), coordinate_map_key=hx.coordinate_map_key, coordinate_manager=hx.coordinate_manager)
+    hy = ora.SparseTensor(hy.F.detach().requires_grad_(), coordinate_map_key=hy.coordinate_map_key, coordinate_manager=hy.coordinate_manager)
+    ox, oy = ux(hx), uy(hy)
+    assert ox.coordinate_map_key.tensor_stride == (1, 1, 1)
+    assert rel_err(ox.F, oy.F) < 1e-5
+    g = torch.randn_like(oy.F)
+    ox.F.backward(g.cuda())
+    oy.F.backward(g)
+    assert rel_err(hx.F.grad, hy.F.grad) < 1e-5
+    assert rel_err(ux.kernel.grad, uy.kernel.grad) < 1e-5
+
+
+def test_empty_and_single_voxel(eng, ora):
+    c = np.array([[0, 5, -3, 2]], dtype=np.int32)
+    x, y, fx, fy = _pair(eng, ora, c, 8)
+    mx = eng.MinkowskiConvolution(8, 8, kernel_size=3, dimension=3).cuda()
+    my = ora.MinkowskiConvolution(8, 8, kernel_size=3, dimension=3)
+    _sync_params(mx, my)
+    assert rel_err(mx(x).F, my(y).F) < 1e-6
+    px = eng.MinkowskiAvgPooling(kernel_size=2, stride=2, dimension=3)(x)
+    assert px.F.shape == (1, 8) and rel_err(px.F, fy) < 1e-6
+
+
+# --------------------------------------------------------------------------------------------- BN & friends
+@pytest.mark.parametrize("n,c,relu,res", [(5000, 32, False, False), (3001, 96, True, False), (777, 256, True, True), (64, 3, False, True)])
+def test_batchnorm_train_forward_backward(eng, n, c, relu, res):
+    from unscene3d_b200.engine import functional as Fn
+
+    torch.manual_seed(0)
+    x = (torch.randn(n, c) * 2 + 0.5)
+    r = torch.randn(n, c) if res else None
+    bn = torch.nn.BatchNorm1d(c, momentum=0.02)
+    bn.weight.data.uniform_(0.5, 1.5)
+    bn.bias.data.uniform_(-0.3, 0.3)
+    xr = x.clone().requires_grad_()
+    rr = r.clone().requires_grad_() if res else None
+    ref = bn(xr)
+    if res:
+        ref = ref + rr
+    if relu:
+        ref = torch.relu(ref)
+    g = torch.randn(n, c)
+    ref.backward(g)
+
+    xg = x.clone().cuda().requires_grad_()
+    rg = r.clone().cuda().requires_grad_() if res else None
+    w = bn.weight.detach().clone().cuda().requires_grad_()
+    b = bn.bias.detach().clone().cuda().requires_grad_()
+    rm, rv = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+    out = Fn.BatchNormFunction.apply(xg, w, b, rg, rm, rv, 0.02, 1e-5, True, relu)
+    out.backward(g.cuda())
+    assert rel_err(out, ref) < 1e-5
+    assert rel_err(xg.grad, xr.grad) < 1e-4
+    assert rel_err(w.grad, bn.weight.grad) < 1e-4
+    assert rel_err(b.grad, bn.bias.grad) < 1e-4
+    if res:
+        assert rel_err(rg.grad, rr.grad) < 1e-6
+    assert rel_err(rm, bn.running_mean) < 1e-5 and rel_err(rv, bn.running_var) < 1e-5
+
+
+def test_batchnorm_eval_mode(eng):
+    torch.manual_seed(1)
+    m = eng.MinkowskiBatchNorm(16, momentum=0.1).cuda()
+    m.bn.running_mean.uniform_(-1, 1)
+    m.bn.running_var.uniform_(0.5, 2)
+    m.eval()
+    c = random_scene(500, 3)
+    f = torch.randn(c.shape[0], 16)
+    x = eng.SparseTensor(f.cuda().requires_grad_(), torch.from_numpy(c).cuda())
+    ref_bn = torch.nn.BatchNorm1d(16).eval()
+    ref_bn.load_state_dict({k: v.cpu() for k, v in m.bn.state_dict().items()})
+    fr = f.clone().requires_grad_()
+    ref = ref_bn(fr)
+    out = m(x).F
+    g = torch.randn_like(ref)
+    out.backward(g.cuda())
+    ref.backward(g)
+    assert rel_err(out, ref) < 1e-5
+    assert rel_err(x.F.grad, fr.grad) < 1e-5
+
+
+def test_relu_add_cat_pool(eng, ora):
+    c = random_scene(4000, 31, batch=2, extent=20)
+    x, y, fx, fy = _pair(eng, ora, c, 12)
+    x2, y2 = x._like(fx * 0.5 + 1), y._like(fy * 0.5 + 1)
+    ox = eng.MinkowskiReLU(inplace=True)(eng.cat(x, x2) + eng.cat(x2, x))
+    oy = ora.MinkowskiReLU()(ora.cat(y, y2) + ora.cat(y2, y))
+    for mode in ("Avg", "Sum", "Max"):
+        px = getattr(eng, f"Minkowski{mode}Pooling")(kernel_size=2, stride=2, dimension=3)(ox)
+        py = getattr(ora, f"Minkowski{mode}Pooling")(kernel_size=2, stride=2, dimension=3)(oy)
+        assert torch.equal(px.C.cpu(), py.C)
+        assert rel_err(px.F, py.F) < 1e-6
+    px = eng.MinkowskiAvgPooling(kernel_size=2, stride=2, dimension=3)(ox)
+    py = ora.MinkowskiAvgPooling(kernel_size=2, stride=2, dimension=3)(oy)
+    g = torch.randn_like(py.F)
+    px.F.backward(g.cuda())
+    py.F.backward(g)
+    assert rel_err(fx.grad, fy.grad) < 1e-6
+    # decomposition by batch index keeps row order
+    for a, b in zip(px.decomposed_features, py.decomposed_features):
+        assert rel_err(a, b) < 1e-6
+    for a, b in zip(px.decomposed_coordinates, py.decomposed_coordinates):
+        assert torch.equal(a.cpu(), b)
+
+
+# --------------------------------------------------------------------------------------------- decoder helpers
+@pytest.mark.parametrize("n,m", [(5, 3), (31, 10), (100, 100), (777, 100), (5000, 100)])
+def test_fps_indices_bit_exact_on_integer_coords(eng, n, m):
+    from oracle import ops_cpu
+    from unscene3d_b200.engine import functional as Fn
+
+    rng = np.random.default_rng(n)
+    pts = rng.integers(-8, 9, size=(2, n, 3)).astype(np.float32)  # many exact distance ties, some |p|^2 = 0
+    got = Fn.furthest_point_sampling(torch.from_numpy(pts).cuda(), m).cpu().numpy()
+    for b in range(2):
+        assert np.array_equal(got[b], ops_cpu.furthest_point_sampling(pts[b], m))
+
+
+def test_segment_mean(eng):
+    from oracle import ops_cpu
+    from unscene3d_b200.engine import functional as Fn
+
+    torch.manual_seed(0)
+    src = torch.randn(20000, 128)
+    idx = torch.randint(0, 900, (20000,))
+    idx[0] = 899
+    ref_in = src.clone().requires_grad_()
+    ref = ops_cpu.scatter_mean(ref_in, idx)
+    s = src.clone().cuda().requires_grad_()
+    out = Fn.SegmentMeanFunction.apply(s, idx.cuda(), 900)
+    g = torch.randn_like(ref)
+    out.backward(g.cuda())
+    ref.backward(g)
+    assert rel_err(out, ref) < 1e-5
+    assert rel_err(s.grad, ref_in.grad) < 1e-6
+
+
+def test_matcher_cost(eng):
+    from oracle import ops_cpu
+    from unscene3d_b200.engine import functional as Fn
+
+    torch.manual_seed(0)
+    S, Q, T = 1500, 100, 20
+    logits = torch.randn(Q, 3)
+    masks = torch.randn(S, Q) * 4
+    tgt = torch.rand(T, S) < 0.1
+    labels = torch.ones(T, dtype=torch.long)
+    labels[3] = 253
+    ref = ops_cpu.matcher_cost(logits, masks, tgt, labels, 2.0, 5.0, 2.0)
+    got = Fn.matcher_cost(masks.cuda(), tgt.float().cuda(), logits.softmax(-1).cuda(), labels.cuda(), 2.0, 5.0, 2.0)
+    assert rel_err(got, ref) < 1e-5
+    from scipy.optimize import linear_sum_assignment
+
+    assert [a.tolist() for a in linear_sum_assignment(got.cpu())] == [a.tolist() for a in linear_sum_assignment(ref)]
+
+
+def test_cpu_tensor_is_rejected_loudly(eng):
+    with pytest.raises(RuntimeError):
+        eng.SparseTensor(torch.zeros(3, 1), torch.zeros(3, 4, dtype=torch.int32))

@@ -1,0 +1,126 @@
+"""Backbone parity.
+
+CPU (`-m "not gpu"`): our model definitions over the CPU oracle reproduce the golden vectors that
+the UNMODIFIED reference model files produced over the same oracle (tests/golden/make_golden.py) —
+this pins unscene3d_b200/models/*.py to /root/reference/models/*.py; when the reference tree is
+present the two are also compared live (state-dict names, shapes, BN momenta, outputs).
+
+GPU (`-m gpu`): the same model on the CUDA backend (libus3d through the C ABI) against the golden
+vectors and against the oracle run live — forward features, loss, parameter gradients, BN buffers.
+Tolerance: 1e-3 relative (north_star) for the model-level comparisons; the fp32 SIMT kernels land
+around 1e-6.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from golden.make_golden import CASES, GRAD_KEYS, case_inputs, run_case
+from helpers import (Cfg, deterministic_state, have_reference, our_models_on_oracle, random_scene,
+                     reference_models_on_oracle)
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_golden(name):
+    return dict(np.load(os.path.join(GOLDEN_DIR, f"{name}.npz")))
+
+
+def compare(res, gold, rtol):
+    for k, g in gold.items():
+        r = res[k]
+        if k.startswith(("shape", "idx")):
+            assert np.array_equal(r, g), k
+        else:
+            scale = max(float(np.abs(g).max()), 1e-12)
+            err = float(np.abs(np.asarray(r, dtype=np.float64) - g).max()) / scale
+            assert err < rtol, f"{k}: max error {err:.3e} (relative to max |golden|) exceeds {rtol}"
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_our_models_on_oracle_match_reference_golden(name):
+    from oracle import me_cpu
+
+    res = run_case(our_models_on_oracle(), me_cpu, name)
+    compare(res, load_golden(name), rtol=1e-6)
+
+
+@pytest.mark.skipif(not have_reference(), reason="reference tree only exists in the build container")
+@pytest.mark.parametrize("cls", ["Res16UNet14", "Res16UNet18", "Res16UNet34", "Res16UNet34C", "Res16UNet14A", "Res16UNet34CMultiRes"])
+def test_state_dict_and_outputs_identical_to_reference(cls):
+    from oracle import me_cpu
+
+    ref = reference_models_on_oracle()
+    import models.res16unet as R
+
+    ours = our_models_on_oracle().res16unet
+    a = getattr(R, cls)(3, 20, Cfg(), D=3, out_fpn=True)
+    b = getattr(ours, cls)(3, 20, Cfg(), D=3, out_fpn=True)
+    sa, sb = a.state_dict(), b.state_dict()
+    assert list(sa.keys()) == list(sb.keys())
+    assert all(sa[k].shape == sb[k].shape for k in sa)
+    mom = lambda m: {n: x.momentum for n, x in m.named_modules() if isinstance(x, torch.nn.BatchNorm1d)}
+    assert mom(a) == mom(b)
+    st = deterministic_state(a, 5)
+    a.load_state_dict(st)
+    b.load_state_dict(st)
+    c = random_scene(1500, 9, batch=2)
+    f = torch.randn(c.shape[0], 3)
+    oa = a(me_cpu.SparseTensor(f, torch.from_numpy(c)))
+    ob = b(me_cpu.SparseTensor(f, torch.from_numpy(c)))
+    assert torch.equal(oa[0].F, ob[0].F)
+    fa = list(oa[1].values()) if isinstance(oa[1], dict) else oa[1]
+    fb = list(ob[1].values()) if isinstance(ob[1], dict) else ob[1]
+    for u, v in zip(fa, fb):
+        assert torch.equal(u.F, v.F) and torch.equal(u.C, v.C)
+
+
+# ------------------------------------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(CASES))
+def test_cuda_backbone_matches_golden(name):
+    import unscene3d_b200
+    from unscene3d_b200 import engine, models
+
+    res = run_case(models, engine, name, device="cuda")
+    compare(res, load_golden(name), rtol=1e-3)
+
+
+@pytest.mark.gpu
+def test_cuda_backbone_matches_oracle_live_forward_backward():
+    import unscene3d_b200
+    from oracle import me_cpu
+    from unscene3d_b200 import engine, models
+
+    c = random_scene(6000, 77, batch=2, extent=36)
+    torch.manual_seed(3)
+    f = torch.randn(c.shape[0], 3)
+    cpu_net = our_models_on_oracle().res16unet.Res16UNet34C(3, 20, Cfg(), D=3, out_fpn=True)
+    st = deterministic_state(cpu_net, 11)
+    cpu_net.load_state_dict(st)
+    gpu_net = models.Res16UNet34C(3, 20, Cfg(), D=3, out_fpn=True)
+    gpu_net.load_state_dict(st)
+    gpu_net.cuda()
+    oc, fc = cpu_net(me_cpu.SparseTensor(f, torch.from_numpy(c)))
+    og, fg = gpu_net(engine.SparseTensor(f.cuda(), torch.from_numpy(c).cuda()))
+
+    def rel(a, b):
+        return float((a.double().cpu() - b.double()).norm() / b.double().norm())
+
+    # stride-1 rows keep input order; coarse maps share first-occurrence order with the oracle
+    for u, v in zip(fg, fc):
+        assert torch.equal(u.C.cpu(), v.C)
+        assert rel(u.F, v.F) < 1e-3
+    w = torch.linspace(-1, 1, oc.F.shape[1])
+    (oc.F * w).mean().backward()
+    (og.F * w.cuda()).mean().backward()
+    pc, pg = dict(cpu_net.named_parameters()), dict(gpu_net.named_parameters())
+    worst = max(rel(pg[k].grad, pc[k].grad) for k in pc if k != "final.kernel" and k != "final.bias")
+    assert worst < 1e-3, f"worst parameter-gradient relative error {worst:.3e}"
+    bc, bg = dict(cpu_net.named_buffers()), dict(gpu_net.named_buffers())
+    for k in bc:
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            assert rel(bg[k], bc[k]) < 1e-4, k
+        if k.endswith("num_batches_tracked"):
+            assert int(bg[k]) == int(bc[k])

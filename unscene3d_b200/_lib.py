@@ -1,0 +1,74 @@
+"""ctypes binding of libus3d.so (include/us3d.h).  The library is the product: if it is missing or
+does not export a declared symbol the import FAILS — there is no Python/CPU fallback."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libus3d.so")
+
+_i, _ll, _f = ctypes.c_int, ctypes.c_longlong, ctypes.c_float
+_p = ctypes.c_void_p
+
+# name -> argtypes (all functions return int unless listed in _RESTYPE)
+PROTOTYPES = {
+    "us3d_abi_version": [],
+    "us3d_last_error": [],
+    "us3d_launch_count": [],
+    "us3d_reset_launch_count": [],
+    "us3d_hash_capacity": [_i],
+    "us3d_coords_unique": [_p, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p, _p, ctypes.POINTER(_i), _p],
+    "us3d_kernel_map": [_p, _i, ctypes.POINTER(ctypes.c_int32), _i, _p, _p, _i, _p, _p, _i, _p],
+    "us3d_spconv_gather": [_p, _i, _p, _i, _i, _p, _i, _i, _i, _i, _p, _p, _p, _i, _i, _p, _p],
+    "us3d_spconv_wgrad": [_p, _i, _p, _i, _i, _p, _i, _p, _p, _i, _i, _p],
+    "us3d_bn_stats": [_p, _i, _i, _i, _p, _p, _p],
+    "us3d_bn_finalize": [_p, _p, _i, _i, _f, _f, _p, _p, _p, _p, _p],
+    "us3d_bn_apply": [_p, _i, _i, _i, _p, _p, _p, _p, _p, _i, _i, _p, _i, _p],
+    "us3d_bn_bwd_reduce": [_p, _i, _p, _i, _p, _i, _i, _i, _p, _p, _i, _p, _p],
+    "us3d_bn_bwd_apply": [_p, _i, _p, _i, _p, _i, _i, _i, _p, _p, _p, _i, _p, _p, _i, _p, _i, _p, _p, _p],
+    "us3d_relu": [_p, _p, _ll, _p],
+    "us3d_relu_bwd": [_p, _p, _p, _ll, _p],
+    "us3d_add": [_p, _p, _p, _ll, _p],
+    "us3d_copy2d": [_p, _i, _p, _i, _i, _i, _p],
+    "us3d_pool_fwd": [_p, _i, _p, _i, _i, _i, _p, _p],
+    "us3d_pool_bwd": [_p, _p, _p, _i, _p, _i, _i, _i, _p, _p],
+    "us3d_furthest_point_sampling": [_p, _i, _i, _i, _p, _p, _p],
+    "us3d_segment_mean_fwd": [_p, _p, _i, _i, _i, _p, _p, _p],
+    "us3d_segment_mean_bwd": [_p, _p, _p, _i, _i, _p, _p],
+    "us3d_matcher_cost": [_p, _i, _i, _p, _i, _p, _i, _p, _f, _f, _f, _p, _p],
+}
+_RESTYPE = {"us3d_last_error": ctypes.c_char_p, "us3d_launch_count": _ll, "us3d_reset_launch_count": None}
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m unscene3d_b200.csrc.build` "
+            "(or __graft_entry__.build()).  unscene3d_b200 has no fallback path."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError = stale library
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPE.get(name, _i)
+    return lib
+
+
+lib = _load()
+ABI_VERSION = lib.us3d_abi_version()
+
+
+class Us3dError(RuntimeError):
+    pass
+
+
+def check(rc: int):
+    if rc != 0:
+        raise Us3dError(lib.us3d_last_error().decode() or f"libus3d error {rc}")
+
+
+def launch_count() -> int:
+    return int(lib.us3d_launch_count())
+
+
+def reset_launch_count():
+    lib.us3d_reset_launch_count()

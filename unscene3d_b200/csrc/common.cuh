@@ -1,0 +1,100 @@
+// Shared helpers for libus3d (sm_100a).  Host code of the C ABI lives next to each kernel file.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+
+#include "../../include/us3d.h"
+
+namespace us3d {
+
+// ---- error plumbing ---------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+extern std::atomic<long long> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define US3D_CHECK_ARG(cond, ...)              \
+    do {                                       \
+        if (!(cond)) {                         \
+            ::us3d::set_error(__VA_ARGS__);    \
+            return -1;                         \
+        }                                      \
+    } while (0)
+
+#define US3D_CUDA(call)                                                                        \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            ::us3d::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return -2;                                                                         \
+        }                                                                                      \
+    } while (0)
+
+#define US3D_LAUNCH_CHECK()                                                                    \
+    do {                                                                                       \
+        ::us3d::count_launch();                                                                \
+        cudaError_t e__ = cudaGetLastError();                                                  \
+        if (e__ != cudaSuccess) {                                                              \
+            ::us3d::set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+            return -3;                                                                         \
+        }                                                                                      \
+    } while (0)
+
+inline int num_sms() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- voxel keys -------------------------------------------------------------------------------
+// b:10 | x:18 | y:18 | z:18, each spatial field biased by 2^17 so negative coordinates order correctly.
+constexpr int kAxisBits = 18;
+constexpr int kAxisBias = 1 << (kAxisBits - 1);
+constexpr uint64_t kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
+
+__host__ __device__ __forceinline__ uint64_t pack_key(int b, int x, int y, int z) {
+    return ((uint64_t)(uint32_t)b << (3 * kAxisBits)) | ((uint64_t)(uint32_t)(x + kAxisBias) << (2 * kAxisBits)) |
+           ((uint64_t)(uint32_t)(y + kAxisBias) << kAxisBits) | (uint64_t)(uint32_t)(z + kAxisBias);
+}
+
+__host__ __device__ __forceinline__ bool key_in_range(int b, int x, int y, int z) {
+    return b >= 0 && b < (1 << 10) && x >= -kAxisBias && x < kAxisBias && y >= -kAxisBias && y < kAxisBias &&
+           z >= -kAxisBias && z < kAxisBias;
+}
+
+__device__ __forceinline__ uint32_t hash_key(uint64_t k) {  // murmur3 finaliser
+    k ^= k >> 33;
+    k *= 0xff51afd7ed558ccdull;
+    k ^= k >> 33;
+    k *= 0xc4ceb9fe1a85ec53ull;
+    k ^= k >> 33;
+    return (uint32_t)k;
+}
+
+// floor(a / s) * s for s > 0, also for negative a
+__host__ __device__ __forceinline__ int floor_to(int a, int s) {
+    int q = a / s, r = a % s;
+    if (r < 0) --q;
+    return q * s;
+}
+
+__device__ __forceinline__ int hash_lookup(const uint64_t *__restrict__ keys, const int32_t *__restrict__ vals,
+                                           uint32_t mask, uint64_t key) {
+    uint32_t slot = hash_key(key) & mask;
+    while (true) {
+        uint64_t k = keys[slot];
+        if (k == key) return vals[slot];
+        if (k == kEmptyKey) return -1;
+        slot = (slot + 1) & mask;
+    }
+}
+
+}  // namespace us3d

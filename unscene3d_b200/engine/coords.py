@@ -1,0 +1,211 @@
+"""Device-side coordinate manager: coordinate maps (one per tensor stride) and neighbour tables.
+
+Host-side mirror of MinkowskiEngine's CoordinateManager as the reference uses it (SURVEY.md
+Appendix A.1–A.4, A.7): one manager per input SparseTensor, maps are created on first use and shared
+by every layer / pooling op / backward pass of that level (trainer/trainer.py:115-117,
+models/mask3d.py:206-215, 425-436).  All integer work runs in libus3d (csrc/coords.cu).
+
+Layout in HBM
+  coordinate map   int32 [N, 4] rows (b, x, y, z); hash table uint64 keys[cap] + int32 vals[cap]
+  neighbour table  int32 [K, N_out]  (nbr[k, o] = input row at coords_out[o] + off_k, or -1)
+                   + uint32 tile mask [ceil(N_out/128)] (bit k: any neighbour at offset k in the tile)
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .._lib import check, lib
+
+TILE_ROWS = 128
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _tuple(v, D=3) -> Tuple[int, ...]:
+    if isinstance(v, (list, tuple)):
+        assert len(v) == D, f"expected {D} entries, got {v}"
+        return tuple(int(a) for a in v)
+    if isinstance(v, (torch.Tensor, np.ndarray)):
+        return tuple(int(a) for a in v)
+    return (int(v),) * D
+
+
+class CoordinateMapKey:
+    __slots__ = ("tensor_stride", "string_id")
+
+    def __init__(self, tensor_stride: Sequence[int], string_id: str = ""):
+        self.tensor_stride = tuple(int(s) for s in tensor_stride)
+        self.string_id = string_id
+
+    def get_tensor_stride(self):
+        return list(self.tensor_stride)
+
+    def get_key(self):
+        return (list(self.tensor_stride), self.string_id)
+
+    def __hash__(self):
+        return hash((self.tensor_stride, self.string_id))
+
+    def __eq__(self, other):
+        return (isinstance(other, CoordinateMapKey) and self.tensor_stride == other.tensor_stride
+                and self.string_id == other.string_id)
+
+    def __repr__(self):
+        return f"CoordinateMapKey(stride={list(self.tensor_stride)}, id='{self.string_id}')"
+
+
+def kernel_offsets(kernel_size: Sequence[int], tensor_stride: Sequence[int], dilation: Sequence[int]) -> np.ndarray:
+    """HYPER_CUBE offsets, x fastest; odd k centred, even k starts at 0 (Appendix A.4)."""
+    ks = np.asarray(kernel_size)
+    vol = int(ks.prod())
+    idx = np.arange(vol)
+    out = np.zeros((vol, len(ks)), dtype=np.int32)
+    for a, k in enumerate(ks):
+        i = idx % k
+        idx = idx // k
+        out[:, a] = (i - k // 2 if k % 2 else i) * tensor_stride[a] * dilation[a]
+    return out
+
+
+class CoordinateMap:
+    """Unique coordinates of one tensor stride + the hash table that indexes them."""
+
+    def __init__(self, coords: torch.Tensor, keys: torch.Tensor, vals: torch.Tensor):
+        self.coords, self.keys, self.vals = coords, keys, vals
+        self.n = coords.shape[0]
+        self.cap = keys.shape[0]
+        self._batch_slices: Optional[List] = None
+
+
+class NeighbourTable:
+    __slots__ = ("nbr", "mask", "n_rows", "kvol")
+
+    def __init__(self, nbr: torch.Tensor, mask: torch.Tensor, n_rows: int, kvol: int):
+        self.nbr, self.mask, self.n_rows, self.kvol = nbr, mask, n_rows, kvol
+
+
+def unique_coords(coords: torch.Tensor, tensor_stride=(1, 1, 1)):
+    """libus3d us3d_coords_unique on a CUDA int32 [n,4] tensor.
+    Returns (CoordinateMap, first_rows int32 [m], inverse int32 [n])."""
+    assert coords.is_cuda and coords.dtype == torch.int32 and coords.ndim == 2 and coords.shape[1] == 4
+    coords = coords.contiguous()
+    n = coords.shape[0]
+    dev = coords.device
+    cap = lib.us3d_hash_capacity(n)
+    keys = torch.empty(cap, dtype=torch.int64, device=dev)
+    vals = torch.empty(cap, dtype=torch.int32, device=dev)
+    out = torch.empty((max(n, 1), 4), dtype=torch.int32, device=dev)
+    first = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    inverse = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    scratch = torch.empty(2 * n + 4200, dtype=torch.int32, device=dev)
+    count = ctypes.c_int(0)
+    check(lib.us3d_coords_unique(coords.data_ptr(), n, int(tensor_stride[0]), int(tensor_stride[1]), int(tensor_stride[2]),
+                                 keys.data_ptr(), vals.data_ptr(), cap, out.data_ptr(), first.data_ptr(),
+                                 inverse.data_ptr(), scratch.data_ptr(), ctypes.byref(count), _stream()))
+    m = count.value
+    return CoordinateMap(out[:m], keys, vals), first[:m], inverse[:n]
+
+
+class CoordinateManager:
+    def __init__(self, D: int = 3, device=None):
+        assert D == 3, "the hot path is 3-D (SURVEY §8(b))"
+        self.D = D
+        self.device = device
+        self._maps: Dict[CoordinateMapKey, CoordinateMap] = {}
+        self._parents: Dict[Tuple[CoordinateMapKey, CoordinateMapKey], torch.Tensor] = {}
+        self._tables: Dict[tuple, NeighbourTable] = {}
+        self._identity: Dict[CoordinateMapKey, NeighbourTable] = {}
+
+    # ---- coordinate maps --------------------------------------------------------------------
+    def insert(self, coords: torch.Tensor, tensor_stride=(1, 1, 1), string_id: str = ""):
+        key = CoordinateMapKey(tensor_stride, string_id)
+        cmap, first, inverse = unique_coords(coords, (1, 1, 1))
+        self._maps[key] = cmap
+        self.device = coords.device
+        return key, first, inverse
+
+    def exists(self, key: CoordinateMapKey) -> bool:
+        return key in self._maps
+
+    def size(self, key: CoordinateMapKey) -> int:
+        return self._maps[key].n
+
+    def get_coordinates(self, key: CoordinateMapKey) -> torch.Tensor:
+        return self._maps[key].coords
+
+    def stride(self, in_key: CoordinateMapKey, stride: Sequence[int]) -> CoordinateMapKey:
+        """c_out = floor(c_in / t_out) * t_out, unique in first-occurrence order (Appendix A.3)."""
+        if all(s == 1 for s in stride):
+            return in_key
+        t_out = tuple(a * b for a, b in zip(in_key.tensor_stride, stride))
+        out_key = CoordinateMapKey(t_out, "")
+        if out_key not in self._maps:
+            cmap, _, inverse = unique_coords(self._maps[in_key].coords, t_out)
+            self._maps[out_key] = cmap
+            self._parents[(in_key, out_key)] = inverse
+        return out_key
+
+    def batch_slices(self, key: CoordinateMapKey):
+        """Per-batch row selectors: slices when rows are batch-sorted (always true for collated input
+        and every map derived from it), index tensors otherwise."""
+        cmap = self._maps[key]
+        if cmap._batch_slices is None:
+            b = cmap.coords[:, 0]
+            if cmap.n == 0:
+                cmap._batch_slices = []
+            else:
+                counts = torch.bincount(b.long())
+                sorted_ok = bool((b[1:] >= b[:-1]).all()) if cmap.n > 1 else True
+                if sorted_ok:
+                    ends = torch.cumsum(counts, 0).tolist()
+                    starts = [0] + ends[:-1]
+                    cmap._batch_slices = [slice(s, e) for s, e in zip(starts, ends)]
+                else:
+                    cmap._batch_slices = [torch.nonzero(b == i).flatten() for i in range(counts.shape[0])]
+        return cmap._batch_slices
+
+    # ---- neighbour tables ------------------------------------------------------------------
+    def _build_table(self, query_key, table_key, offsets: np.ndarray) -> NeighbourTable:
+        q, t = self._maps[query_key], self._maps[table_key]
+        kvol = offsets.shape[0]
+        nbr = torch.empty((kvol, q.n), dtype=torch.int32, device=q.coords.device)
+        mask = torch.empty(max((q.n + TILE_ROWS - 1) // TILE_ROWS, 1), dtype=torch.int32, device=q.coords.device)
+        offs = np.ascontiguousarray(offsets, dtype=np.int32)
+        check(lib.us3d_kernel_map(q.coords.data_ptr(), q.n, offs.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), kvol,
+                                  t.keys.data_ptr(), t.vals.data_ptr(), t.cap, nbr.data_ptr(), mask.data_ptr(),
+                                  TILE_ROWS, _stream()))
+        return NeighbourTable(nbr, mask, q.n, kvol)
+
+    def forward_table(self, in_key, out_key, kernel_size, dilation=(1, 1, 1)) -> NeighbourTable:
+        """nbr[k, o] = in row at coords_out[o] + off_k  (offsets scaled by the INPUT stride)."""
+        ck = ("f", in_key, out_key, tuple(kernel_size), tuple(dilation))
+        if ck not in self._tables:
+            offs = kernel_offsets(kernel_size, in_key.tensor_stride, dilation)
+            self._tables[ck] = self._build_table(out_key, in_key, offs)
+        return self._tables[ck]
+
+    def backward_table(self, in_key, out_key, kernel_size, dilation=(1, 1, 1)) -> Tuple[NeighbourTable, bool]:
+        """Transposed map: nbrT[k, i] = out row at coords_in[i] - off_k.  Returns (table, flip_k): for an
+        odd kernel on one map the forward table read with k -> K-1-k IS the transposed map."""
+        same = in_key == out_key and all(k % 2 == 1 for k in kernel_size)
+        if same:
+            return self.forward_table(in_key, out_key, kernel_size, dilation), True
+        ck = ("b", in_key, out_key, tuple(kernel_size), tuple(dilation))
+        if ck not in self._tables:
+            offs = -kernel_offsets(kernel_size, in_key.tensor_stride, dilation)
+            self._tables[ck] = self._build_table(in_key, out_key, offs)
+        return self._tables[ck], False
+
+    def identity_table(self, key) -> NeighbourTable:
+        if key not in self._identity:
+            n = self._maps[key].n
+            nbr = torch.arange(n, dtype=torch.int32, device=self._maps[key].coords.device)[None]
+            mask = torch.ones(max((n + TILE_ROWS - 1) // TILE_ROWS, 1), dtype=torch.int32, device=nbr.device)
+            self._identity[key] = NeighbourTable(nbr, mask, n, 1)
+        return self._identity[key]

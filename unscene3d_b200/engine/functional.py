@@ -1,0 +1,314 @@
+"""torch.autograd.Function wrappers over the C ABI (include/us3d.h).  PyTorch supplies device
+memory, streams and the autograd graph; every arithmetic pass is a libus3d kernel.
+
+All functions take row-major fp32 CUDA tensors; a tensor whose last dimension is contiguous is passed
+with its row stride as leading dimension (so column slices of a concatenation need no copy).
+"""
+from __future__ import annotations
+
+import torch
+
+from .._lib import check, lib
+from .coords import NeighbourTable, _stream
+
+
+def _rows(t: torch.Tensor) -> torch.Tensor:
+    """2-D fp32 CUDA tensor with unit column stride (copy only if needed)."""
+    if not t.is_cuda:
+        raise RuntimeError("unscene3d_b200 operators run on CUDA tensors only (no CPU fallback)")
+    if t.dtype != torch.float32:
+        t = t.float()
+    if t.ndim != 2 or t.stride(1) != 1 or (t.shape[0] > 1 and t.stride(0) < t.shape[1]):
+        t = t.contiguous()
+    return t
+
+
+def _ld(t: torch.Tensor) -> int:
+    return t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0))
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+class KernelTimer:
+    """Optional per-launch CUDA-event timing of the convolution kernels (bench.py roofline leg).
+    `records` holds (kind, n_in_rows, n_out_rows, kvol, cin, cout, start_event, end_event)."""
+
+    def __init__(self):
+        self.records = []
+
+    def __enter__(self):
+        global _timer
+        _timer = self
+        return self
+
+    def __exit__(self, *exc):
+        global _timer
+        _timer = None
+
+    def summary(self):
+        torch.cuda.synchronize()
+        return [(k, ni, no, kv, ci, co, s.elapsed_time(e)) for (k, ni, no, kv, ci, co, s, e) in self.records]
+
+
+_timer = None
+
+
+def _timed(kind, n_in, n_out, kvol, cin, cout, launch):
+    if _timer is None:
+        return launch()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    r = launch()
+    e.record()
+    _timer.records.append((kind, n_in, n_out, kvol, cin, cout, s, e))
+    return r
+
+
+def spconv_gather(x, table: NeighbourTable, w3, cin, cout, transpose_w, flip_k, bias=None, out=None, accumulate=False):
+    x = _rows(x)
+    y = out if out is not None else torch.empty((table.n_rows, cout), dtype=torch.float32, device=x.device)
+    st = _stream()
+    _timed("dgrad" if transpose_w else "fwd", x.shape[0], table.n_rows, table.kvol, cin, cout, lambda: check(
+        lib.us3d_spconv_gather(x.data_ptr(), _ld(x), table.nbr.data_ptr(), table.n_rows, table.kvol, w3.data_ptr(), cin, cout,
+                               int(transpose_w), int(flip_k), _ptr(bias), 0, y.data_ptr(), _ld(y), int(accumulate),
+                               _ptr(table.mask), st)))
+    return y
+
+
+def spconv_wgrad(x, table: NeighbourTable, dy, cin, cout):
+    x, dy = _rows(x), _rows(dy)
+    dw = torch.zeros((table.kvol, cin, cout), dtype=torch.float32, device=x.device)
+    st = _stream()
+    _timed("wgrad", x.shape[0], table.n_rows, table.kvol, cin, cout, lambda: check(
+        lib.us3d_spconv_wgrad(x.data_ptr(), _ld(x), table.nbr.data_ptr(), table.n_rows, table.kvol, dy.data_ptr(), _ld(dy), 0,
+                              dw.data_ptr(), cin, cout, st)))
+    return dw
+
+
+class SparseConvFunction(torch.autograd.Function):
+    """Y = conv(X) over `fwd` ([K, n_out] neighbour table); backward uses `bwd` ([K, n_in], flip flag)."""
+
+    @staticmethod
+    def forward(ctx, x, kernel, bias, fwd: NeighbourTable, bwd_getter):
+        x = _rows(x)
+        w3 = kernel.detach().contiguous().view(fwd.kvol, kernel.shape[-2], kernel.shape[-1])
+        cin, cout = w3.shape[1], w3.shape[2]
+        assert x.shape[1] == cin, f"input has {x.shape[1]} channels, kernel expects {cin}"
+        y = spconv_gather(x, fwd, w3, cin, cout, False, False, None if bias is None else bias.detach().contiguous())
+        ctx.save_for_backward(x, kernel)
+        ctx.fwd, ctx.bwd_getter, ctx.has_bias = fwd, bwd_getter, bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, kernel = ctx.saved_tensors
+        dy = _rows(dy)
+        fwd = ctx.fwd
+        w3 = kernel.detach().contiguous().view(fwd.kvol, kernel.shape[-2], kernel.shape[-1])
+        cin, cout = w3.shape[1], w3.shape[2]
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            bwd, flip = ctx.bwd_getter()
+            dx = spconv_gather(dy, bwd, w3, cout, cin, True, flip)
+        if ctx.needs_input_grad[1]:
+            dw = spconv_wgrad(x, fwd, dy, cin, cout).view(kernel.shape)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy.sum(0, keepdim=True)
+        return dx, dw, db, None, None
+
+
+class BatchNormFunction(torch.autograd.Function):
+    """y = [relu]( BN_train(x) [+ residual] ), statistics over all rows, running stats updated in place."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, residual, running_mean, running_var, momentum, eps, training, relu):
+        x = _rows(x)
+        n, c = x.shape
+        dev = x.device
+        if residual is not None:
+            residual = _rows(residual)
+        st = _stream()
+        if training:
+            acc = torch.zeros((2, c), dtype=torch.float64, device=dev)
+            mean = torch.empty(c, dtype=torch.float32, device=dev)
+            invstd = torch.empty(c, dtype=torch.float32, device=dev)
+            check(lib.us3d_bn_stats(x.data_ptr(), _ld(x), n, c, acc[0].data_ptr(), acc[1].data_ptr(), st))
+            check(lib.us3d_bn_finalize(acc[0].data_ptr(), acc[1].data_ptr(), n, c, float(eps), float(momentum if momentum is not None else 0.0),
+                                       mean.data_ptr(), invstd.data_ptr(), _ptr(running_mean), _ptr(running_var), st))
+        else:
+            mean = running_mean.detach().float()
+            invstd = torch.rsqrt(running_var.detach().float() + eps)
+        g = gamma.detach().contiguous() if gamma is not None else torch.ones(c, device=dev)
+        b = beta.detach().contiguous() if beta is not None else torch.zeros(c, device=dev)
+        y = torch.empty((n, c), dtype=torch.float32, device=dev)
+        check(lib.us3d_bn_apply(x.data_ptr(), _ld(x), n, c, mean.data_ptr(), invstd.data_ptr(), g.data_ptr(), b.data_ptr(),
+                                _ptr(residual), 0 if residual is None else _ld(residual), int(relu), y.data_ptr(), _ld(y), st))
+        ctx.save_for_backward(x, y if relu else None, mean, invstd, g)
+        ctx.relu, ctx.training, ctx.has_res = bool(relu), bool(training), residual is not None
+        ctx.affine = gamma is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, mean, invstd, g = ctx.saved_tensors
+        dy = _rows(dy)
+        n, c = x.shape
+        dev = x.device
+        st = _stream()
+        red = torch.zeros((2, c), dtype=torch.float64, device=dev)
+        yy = y if y is not None else x
+        check(lib.us3d_bn_bwd_reduce(dy.data_ptr(), _ld(dy), x.data_ptr(), _ld(x), yy.data_ptr(), _ld(yy), n, c, mean.data_ptr(),
+                                     invstd.data_ptr(), int(ctx.relu), red.data_ptr(), st))
+        if not ctx.training:
+            # inference statistics are constants: dx = g * invstd * gamma (zero the two batch terms)
+            dgamma_src = red.clone()
+            red.zero_()
+        dx = torch.empty((n, c), dtype=torch.float32, device=dev)
+        dres = torch.empty((n, c), dtype=torch.float32, device=dev) if ctx.has_res else None
+        dgamma = torch.empty(c, dtype=torch.float32, device=dev)
+        dbeta = torch.empty(c, dtype=torch.float32, device=dev)
+        check(lib.us3d_bn_bwd_apply(dy.data_ptr(), _ld(dy), x.data_ptr(), _ld(x), yy.data_ptr(), _ld(yy), n, c, mean.data_ptr(),
+                                    invstd.data_ptr(), g.data_ptr(), int(ctx.relu), red.data_ptr(), dx.data_ptr(), _ld(dx),
+                                    _ptr(dres), 0 if dres is None else _ld(dres), dgamma.data_ptr(), dbeta.data_ptr(), st))
+        if not ctx.training:
+            dgamma, dbeta = dgamma_src[1].float(), dgamma_src[0].float()
+        if not ctx.affine:
+            dgamma = dbeta = None
+        return dx, dgamma, dbeta, dres, None, None, None, None, None, None
+
+
+class ReLUFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, inplace):
+        xc = x if (x.is_contiguous() and x.dtype == torch.float32) else x.float().contiguous()
+        if not xc.is_cuda:
+            raise RuntimeError("unscene3d_b200 operators run on CUDA tensors only (no CPU fallback)")
+        y = xc if (inplace and xc is x) else torch.empty_like(xc)
+        check(lib.us3d_relu(xc.data_ptr(), y.data_ptr(), xc.numel(), _stream()))
+        if y is x:
+            ctx.mark_dirty(x)
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = torch.empty_like(dy)
+        check(lib.us3d_relu_bwd(dy.data_ptr(), y.data_ptr(), dx.data_ptr(), dy.numel(), _stream()))
+        return dx, None
+
+
+class AddFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = _rows(a).contiguous(), _rows(b).contiguous()
+        assert a.shape == b.shape
+        z = torch.empty_like(a)
+        check(lib.us3d_add(a.data_ptr(), b.data_ptr(), z.data_ptr(), a.numel(), _stream()))
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        return dz, dz
+
+
+class CatFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, *feats):
+        feats = [_rows(f) for f in feats]
+        n = feats[0].shape[0]
+        widths = [f.shape[1] for f in feats]
+        out = torch.empty((n, sum(widths)), dtype=torch.float32, device=feats[0].device)
+        st, c0 = _stream(), 0
+        for f, w in zip(feats, widths):
+            assert f.shape[0] == n
+            dst = out[:, c0:c0 + w]
+            check(lib.us3d_copy2d(f.data_ptr(), _ld(f), dst.data_ptr(), out.shape[1], n, w, st))
+            c0 += w
+        ctx.widths = widths
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        grads, c0 = [], 0
+        for w in ctx.widths:
+            grads.append(dout[:, c0:c0 + w])  # consumers accept a leading dimension: no copy
+            c0 += w
+        return tuple(grads)
+
+
+class PoolFunction(torch.autograd.Function):
+    MODES = {"avg": 0, "sum": 1, "max": 2}
+
+    @staticmethod
+    def forward(ctx, x, table: NeighbourTable, n_in, mode):
+        x = _rows(x).contiguous()
+        c = x.shape[1]
+        y = torch.empty((table.n_rows, c), dtype=torch.float32, device=x.device)
+        check(lib.us3d_pool_fwd(x.data_ptr(), c, table.nbr.data_ptr(), table.n_rows, table.kvol, mode, y.data_ptr(), _stream()))
+        ctx.table, ctx.mode, ctx.n_in = table, mode, n_in
+        ctx.save_for_backward(x, y) if mode == 2 else ctx.save_for_backward()
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _rows(dy).contiguous()
+        c = dy.shape[1]
+        x, y = ctx.saved_tensors if ctx.mode == 2 else (None, None)
+        dx = torch.zeros((ctx.n_in, c), dtype=torch.float32, device=dy.device)
+        t = ctx.table
+        check(lib.us3d_pool_bwd(dy.data_ptr(), _ptr(x), _ptr(y), c, t.nbr.data_ptr(), t.n_rows, t.kvol, ctx.mode, dx.data_ptr(), _stream()))
+        return dx, None, None, None
+
+
+class SegmentMeanFunction(torch.autograd.Function):
+    """torch_scatter.scatter_mean(src, index, dim=0) (models/mask3d.py:223)."""
+
+    @staticmethod
+    def forward(ctx, src, index, num_segments):
+        src = _rows(src).contiguous()
+        index = index.contiguous().long()
+        n, c = src.shape
+        out = torch.zeros((num_segments, c), dtype=torch.float32, device=src.device)
+        count = torch.zeros(num_segments, dtype=torch.float32, device=src.device)
+        check(lib.us3d_segment_mean_fwd(src.data_ptr(), index.data_ptr(), n, c, num_segments, out.data_ptr(), count.data_ptr(), _stream()))
+        ctx.save_for_backward(index, count)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        index, count = ctx.saved_tensors
+        dout = _rows(dout).contiguous()
+        n, c = index.shape[0], dout.shape[1]
+        dsrc = torch.empty((n, c), dtype=torch.float32, device=dout.device)
+        check(lib.us3d_segment_mean_bwd(dout.data_ptr(), index.data_ptr(), count.data_ptr(), n, c, dsrc.data_ptr(), _stream()))
+        return dsrc, None, None
+
+
+def furthest_point_sampling(xyz: torch.Tensor, nsamples: int) -> torch.Tensor:
+    """pointnet2._ext.furthest_point_sampling(points[B,N,3] float cuda contiguous, nsamples) -> int32 [B, nsamples]."""
+    if not xyz.is_cuda:
+        raise RuntimeError("CPU not supported")  # same contract as _ext_src/src/sampling.cpp:83-85
+    xyz = xyz.float().contiguous()
+    B, N, _ = xyz.shape
+    idx = torch.zeros((B, nsamples), dtype=torch.int32, device=xyz.device)
+    temp = torch.full((B, N), 1e10, dtype=torch.float32, device=xyz.device)
+    check(lib.us3d_furthest_point_sampling(xyz.data_ptr(), B, N, nsamples, temp.data_ptr(), idx.data_ptr(), _stream()))
+    return idx
+
+
+def matcher_cost(logits_sq, tgt_ts, prob_qc, labels_t, w_class, w_mask, w_dice):
+    """Cost matrix [Q, T] of models/matcher.py:97-168 for one scene."""
+    logits_sq = _rows(logits_sq).contiguous()
+    tgt_ts = _rows(tgt_ts).contiguous()
+    prob_qc = _rows(prob_qc).contiguous()
+    labels_t = labels_t.contiguous().long()
+    S, Q = logits_sq.shape
+    T = tgt_ts.shape[0]
+    cost = torch.empty((Q, T), dtype=torch.float32, device=logits_sq.device)
+    check(lib.us3d_matcher_cost(logits_sq.data_ptr(), S, Q, tgt_ts.data_ptr(), T, prob_qc.data_ptr(), prob_qc.shape[1],
+                                labels_t.data_ptr(), float(w_class), float(w_mask), float(w_dice), cost.data_ptr(), _stream()))
+    return cost
