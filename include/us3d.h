@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define US3D_ABI_VERSION 3
+#define US3D_ABI_VERSION 4
 #define US3D_MAX_KVOL 27
 
 int us3d_abi_version(void);
@@ -71,10 +71,32 @@ int us3d_spconv_gather(const float *x, int ldx, const int32_t *nbr, int n_rows, 
                        int cout, int transpose_w, int flip_k, const float *bias, const int32_t *out_rows, float *y,
                        int ldy, int accumulate, const uint32_t *tile_mask, void *stream);
 
+/* Tensor-core (tcgen05 + TMEM) variant of us3d_spconv_gather for cin, cout multiples of 16, cout <= 256.
+ *   passes = 1: bf16 x bf16 -> fp32;  passes = 3: three-term bf16 split (hi·hi + lo·hi + hi·lo), fp32-faithful.
+ *   wpack: weights pre-packed by us3d_spconv_pack_weights into bf16 planes laid out as the swizzled
+ *   shared-memory image of every (offset, 64-channel chunk) slab; us3d_spconv_packed_bytes gives its size.
+ *   pack_weights(transpose=1, flip_k) produces the slabs of the input-gradient pass (W[kk]^T), in which case
+ *   the GEMM runs with cin' = cout, cout' = cin.                                                    */
+int us3d_spconv_tc_supported(int cin, int cout);
+long long us3d_spconv_packed_bytes(int kvol, int kdim, int ndim, int passes);
+int us3d_spconv_pack_weights(const float *w, int kvol, int cin, int cout, int transpose, int flip_k, int passes,
+                             void *out, void *stream);
+int us3d_spconv_gather_tc(const float *x, int ldx, const int32_t *nbr, int n_rows, int kvol, const void *wpack, int cin,
+                          int cout, int passes, const float *bias, const int32_t *out_rows, float *y, int ldy,
+                          int accumulate, const uint32_t *tile_mask, void *stream);
+
 /* Weight gradient of the same map:  dW[k] += sum_j X[nbr[k*n_rows+j]]^T · dY[orow(j)]   ([kvol,cin,cout]).
  * dW must be zero-initialised (or hold the value to accumulate into) by the caller.             */
 int us3d_spconv_wgrad(const float *x, int ldx, const int32_t *nbr, int n_rows, int kvol, const float *dy, int ldy,
                       const int32_t *out_rows, float *dw, int cin, int cout, void *stream);
+
+/* Tensor-core weight gradient (cin, cout multiples of 8, cout <= 256): D[ci, co] accumulates in TMEM over the rows
+ * of one (offset, 128-input-channel block, row split); both operands are MN-major SWIZZLE_128B tiles built from
+ * the fp32 rows with the same bf16 split as the forward kernel; partial tiles are reduced into dW with atomics. */
+int us3d_spconv_wgrad_tc_supported(int cin, int cout);
+int us3d_spconv_wgrad_tc(const float *x, int ldx, const int32_t *nbr, int n_rows, int kvol, const float *dy, int ldy,
+                         const int32_t *out_rows, float *dw, int cin, int cout, int passes, const uint32_t *tile_mask,
+                         void *stream);
 
 /* ---------------------------------------------------------------- normalisation / elementwise (A6)
  * BatchNorm1d over all rows (ME.MinkowskiBatchNorm, models/modules/common.py:20-22), train mode:

@@ -19,6 +19,12 @@ PROTOTYPES = {
     "us3d_coords_unique": [_p, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p, _p, ctypes.POINTER(_i), _p],
     "us3d_kernel_map": [_p, _i, ctypes.POINTER(ctypes.c_int32), _i, _p, _p, _i, _p, _p, _i, _p],
     "us3d_spconv_gather": [_p, _i, _p, _i, _i, _p, _i, _i, _i, _i, _p, _p, _p, _i, _i, _p, _p],
+    "us3d_spconv_tc_supported": [_i, _i],
+    "us3d_spconv_packed_bytes": [_i, _i, _i, _i],
+    "us3d_spconv_pack_weights": [_p, _i, _i, _i, _i, _i, _i, _p, _p],
+    "us3d_spconv_gather_tc": [_p, _i, _p, _i, _i, _p, _i, _i, _i, _p, _p, _p, _i, _i, _p, _p],
+    "us3d_spconv_wgrad_tc_supported": [_i, _i],
+    "us3d_spconv_wgrad_tc": [_p, _i, _p, _i, _i, _p, _i, _p, _p, _i, _i, _i, _p, _p],
     "us3d_spconv_wgrad": [_p, _i, _p, _i, _i, _p, _i, _p, _p, _i, _i, _p],
     "us3d_bn_stats": [_p, _i, _i, _i, _p, _p, _p],
     "us3d_bn_finalize": [_p, _p, _i, _i, _f, _f, _p, _p, _p, _p, _p],
@@ -36,7 +42,8 @@ PROTOTYPES = {
     "us3d_segment_mean_bwd": [_p, _p, _p, _i, _i, _p, _p],
     "us3d_matcher_cost": [_p, _i, _i, _p, _i, _p, _i, _p, _f, _f, _f, _p, _p],
 }
-_RESTYPE = {"us3d_last_error": ctypes.c_char_p, "us3d_launch_count": _ll, "us3d_reset_launch_count": None}
+_RESTYPE = {"us3d_last_error": ctypes.c_char_p, "us3d_launch_count": _ll, "us3d_reset_launch_count": None,
+            "us3d_spconv_packed_bytes": _ll}
 
 
 def _load():

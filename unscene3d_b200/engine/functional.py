@@ -66,10 +66,44 @@ def _timed(kind, n_in, n_out, kvol, cin, cout, launch):
     return r
 
 
+# Arithmetic of the sparse-conv forward / input-gradient GEMMs:
+#   0  exact fp32 FMA (SIMT kernel)          1  bf16 x bf16 -> fp32 on tcgen05 (one pass)
+#   3  three-term bf16 split on tcgen05 (hi*hi + lo*hi + hi*lo): fp32-faithful products, fp32 accumulation
+_precision = {"mode": 3}
+
+
+def set_precision(mode: int):
+    assert mode in (0, 1, 3)
+    _precision["mode"] = mode
+
+
+def get_precision() -> int:
+    return _precision["mode"]
+
+
+def pack_weights(w3: torch.Tensor, transpose: bool, flip_k: bool, passes: int) -> torch.Tensor:
+    """fp32 [kvol, cin, cout] -> bf16 slabs in the swizzled shared-memory image the tcgen05 kernel streams."""
+    kvol, w_cin, w_cout = w3.shape
+    kdim, ndim = (w_cout, w_cin) if transpose else (w_cin, w_cout)
+    nbytes = lib.us3d_spconv_packed_bytes(kvol, kdim, ndim, passes)
+    out = torch.empty(nbytes, dtype=torch.uint8, device=w3.device)
+    check(lib.us3d_spconv_pack_weights(w3.data_ptr(), kvol, w_cin, w_cout, int(transpose), int(flip_k), passes,
+                                       out.data_ptr(), _stream()))
+    return out
+
+
 def spconv_gather(x, table: NeighbourTable, w3, cin, cout, transpose_w, flip_k, bias=None, out=None, accumulate=False):
     x = _rows(x)
     y = out if out is not None else torch.empty((table.n_rows, cout), dtype=torch.float32, device=x.device)
     st = _stream()
+    mode = _precision["mode"]
+    if (mode != 0 and lib.us3d_spconv_tc_supported(cin, cout) and x.data_ptr() % 16 == 0 and _ld(x) % 4 == 0):
+        wpack = pack_weights(w3, transpose_w, flip_k, mode)
+        _timed("dgrad" if transpose_w else "fwd", x.shape[0], table.n_rows, table.kvol, cin, cout, lambda: check(
+            lib.us3d_spconv_gather_tc(x.data_ptr(), _ld(x), table.nbr.data_ptr(), table.n_rows, table.kvol, wpack.data_ptr(),
+                                      cin, cout, mode, _ptr(bias), 0, y.data_ptr(), _ld(y), int(accumulate),
+                                      _ptr(table.mask), st)))
+        return y
     _timed("dgrad" if transpose_w else "fwd", x.shape[0], table.n_rows, table.kvol, cin, cout, lambda: check(
         lib.us3d_spconv_gather(x.data_ptr(), _ld(x), table.nbr.data_ptr(), table.n_rows, table.kvol, w3.data_ptr(), cin, cout,
                                int(transpose_w), int(flip_k), _ptr(bias), 0, y.data_ptr(), _ld(y), int(accumulate),
@@ -81,6 +115,13 @@ def spconv_wgrad(x, table: NeighbourTable, dy, cin, cout):
     x, dy = _rows(x), _rows(dy)
     dw = torch.zeros((table.kvol, cin, cout), dtype=torch.float32, device=x.device)
     st = _stream()
+    mode = _precision["mode"]
+    if (mode != 0 and lib.us3d_spconv_wgrad_tc_supported(cin, cout) and x.data_ptr() % 16 == 0 and dy.data_ptr() % 16 == 0
+            and _ld(x) % 4 == 0 and _ld(dy) % 4 == 0):
+        _timed("wgrad", x.shape[0], table.n_rows, table.kvol, cin, cout, lambda: check(
+            lib.us3d_spconv_wgrad_tc(x.data_ptr(), _ld(x), table.nbr.data_ptr(), table.n_rows, table.kvol, dy.data_ptr(), _ld(dy),
+                                     0, dw.data_ptr(), cin, cout, mode, _ptr(table.mask), st)))
+        return dw
     _timed("wgrad", x.shape[0], table.n_rows, table.kvol, cin, cout, lambda: check(
         lib.us3d_spconv_wgrad(x.data_ptr(), _ld(x), table.nbr.data_ptr(), table.n_rows, table.kvol, dy.data_ptr(), _ld(dy), 0,
                               dw.data_ptr(), cin, cout, st)))
