@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define US3D_ABI_VERSION 4
+#define US3D_ABI_VERSION 5
 #define US3D_MAX_KVOL 27
 
 int us3d_abi_version(void);
@@ -89,6 +89,27 @@ int us3d_spconv_gather_tc(const float *x, int ldx, const int32_t *nbr, int n_row
  * dW must be zero-initialised (or hold the value to accumulate into) by the caller.             */
 int us3d_spconv_wgrad(const float *x, int ldx, const int32_t *nbr, int n_rows, int kvol, const float *dy, int ldy,
                       const int32_t *out_rows, float *dw, int cin, int cout, void *stream);
+
+/* TMA-fed variant (the default data path): the activation rows are consumed as bf16 planes — hi, and
+ * lo = x - hi for passes == 3 — row-major [n_in, cin], produced by us3d_split_bf16.  One producer warp gathers
+ * the neighbour rows with cp.async.bulk.tensor ... tile::gather4 (absent neighbours = row -1 = hardware zero
+ * fill) straight into the swizzled operand buffers; persistent CTAs, two TMEM accumulators so a tile's
+ * epilogue overlaps the next tile's main loop.  Same contract as us3d_spconv_gather_tc otherwise.           */
+int us3d_split_bf16(const float *x, int ldx, int n, int c, void *hi, void *lo, void *stream);
+int us3d_spconv_gather_tma(const void *x_hi, const void *x_lo, int n_in, const int32_t *nbr, int n_rows, int kvol,
+                           const void *wpack, int cin, int cout, int passes, const float *bias, const int32_t *out_rows,
+                           float *y, int ldy, int accumulate, const uint32_t *tile_mask, void *stream);
+/* Same pipeline with the row gather done by 16-byte cp.async (LDGSTS) from four producer warps; measured an
+ * order of magnitude faster than tile::gather4 for 128-byte rows, hence the default.                      */
+int us3d_spconv_gather_cp(const void *x_hi, const void *x_lo, int n_in, const int32_t *nbr, int n_rows, int kvol,
+                          const void *wpack, int cin, int cout, int passes, const float *bias, const int32_t *out_rows,
+                          float *y, int ldy, int accumulate, const uint32_t *tile_mask, void *stream);
+
+/* Production kernel: as us3d_spconv_gather_cp, but T = 512 / acc_cols (<= 4) output tiles share every weight
+ * slab (one TMEM accumulator each), which removes the dominant L2 -> SM stream (weights re-read per tile).    */
+int us3d_spconv_gather_mt(const void *x_hi, const void *x_lo, int n_in, const int32_t *nbr, int n_rows, int kvol,
+                          const void *wpack, int cin, int cout, int passes, const float *bias, const int32_t *out_rows,
+                          float *y, int ldy, int accumulate, const uint32_t *tile_mask, void *stream);
 
 /* Tensor-core weight gradient (cin, cout multiples of 8, cout <= 256): D[ci, co] accumulates in TMEM over the rows
  * of one (offset, 128-input-channel block, row split); both operands are MN-major SWIZZLE_128B tiles built from

@@ -18,6 +18,8 @@ from unscene3d_b200.engine import functional as Fn
 from unscene3d_b200.engine.coords import NeighbourTable
 
 dev = torch.device("cuda")
+Fn._tc_kernel["fwd"] = os.environ.get("US3D_TC_KERNEL", "mt")
+print("tensor-core forward kernel:", Fn._tc_kernel["fwd"], flush=True)
 
 
 def run(x, table, w3, cin, cout, mode, transpose=False, flip=False):

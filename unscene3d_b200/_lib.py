@@ -23,6 +23,10 @@ PROTOTYPES = {
     "us3d_spconv_packed_bytes": [_i, _i, _i, _i],
     "us3d_spconv_pack_weights": [_p, _i, _i, _i, _i, _i, _i, _p, _p],
     "us3d_spconv_gather_tc": [_p, _i, _p, _i, _i, _p, _i, _i, _i, _p, _p, _p, _i, _i, _p, _p],
+    "us3d_split_bf16": [_p, _i, _i, _i, _p, _p, _p],
+    "us3d_spconv_gather_tma": [_p, _p, _i, _p, _i, _i, _p, _i, _i, _i, _p, _p, _p, _i, _i, _p, _p],
+    "us3d_spconv_gather_cp": [_p, _p, _i, _p, _i, _i, _p, _i, _i, _i, _p, _p, _p, _i, _i, _p, _p],
+    "us3d_spconv_gather_mt": [_p, _p, _i, _p, _i, _i, _p, _i, _i, _i, _p, _p, _p, _i, _i, _p, _p],
     "us3d_spconv_wgrad_tc_supported": [_i, _i],
     "us3d_spconv_wgrad_tc": [_p, _i, _p, _i, _i, _p, _i, _p, _p, _i, _i, _i, _p, _p],
     "us3d_spconv_wgrad": [_p, _i, _p, _i, _i, _p, _i, _p, _p, _i, _i, _p],

@@ -1,0 +1,417 @@
+// Sparse convolution forward / input-gradient — the production tcgen05 kernel ("multi-tile").
+//
+//     Y[orow(j)] = sum_k X[nbr[k, j]] · W'[k]
+//
+// Every tcgen05 variant measured on B200 (register-staged, cp.async, TMA gather4) ran into the same wall: the
+// L2 -> SM fabric tops out near 6-7 TB/s, and with one 128-row tile per CTA the weight slabs re-streamed by
+// every tile are 60 % of that traffic.  This kernel therefore keeps T = 512 / acc_cols (up to 4) output tiles
+// in flight per CTA: one weight slab (offset k, 64-channel chunk) is loaded ONCE into a B ring slot and
+// multiplied against the gathered A tiles of all T tiles, each accumulating into its own TMEM accumulator.
+//
+//   warps 0-3  A producers: 16-byte cp.async (LDGSTS) from the bf16 planes (hi, + lo for the three-term
+//              split) straight into K-major SWIZZLE_128B slots, zero-fill for absent neighbours;
+//              cp.async.wait_group (lag) -> fence.proxy.async -> mbarrier arrive
+//   warp 4     B loader: cp.async.bulk of the pre-packed, pre-swizzled weight slab
+//   warp 5     MMA issuer: tcgen05.mma M=128, N=Cout, K=16 (x3 for the split); tcgen05.commit frees slots
+//   warps 6-9  epilogue: tcgen05.ld -> (+bias, +=) -> fp32 rows
+//
+// Replaces MinkowskiConvolution / MinkowskiConvolutionTranspose forward and input gradient
+// (/root/reference/models/modules/common.py:146-155, 179-188).
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace us3d {
+namespace mt {
+
+using namespace tcx;
+
+constexpr int M = 128;
+constexpr int KC = 64;
+constexpr int A_PLANE = M * 128;  // bytes of one plane of one A slot
+constexpr int PROD_WARPS = 4;
+constexpr int B_WARP = PROD_WARPS, MMA_WARP = PROD_WARPS + 1, EPI_WARP0 = PROD_WARPS + 2;
+constexpr int THREADS = (PROD_WARPS + 2 + 4) * 32;
+constexpr int MAX_A = 8, MAX_B = 3, MAX_T = 4;
+
+struct Params {
+    const __nv_bfloat16 *x_hi, *x_lo;  // [n_in, cin] planes
+    const int32_t *nbr;
+    int n_rows, kvol, n_tiles, n_super, T;
+    const uint8_t *wpack;
+    int cin, cout, nchunks;
+    const float *bias;
+    const int32_t *out_rows;
+    float *y;
+    int ldy, accumulate;
+    const uint32_t *tile_mask;
+    int a_slots, b_slots, b_plane, acc_cols;
+    long long *prof;  // optional per-CTA wait-cycle counters of the MMA thread (debug)
+};
+
+template <int PASSES, int LAG>
+__global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t a_full[MAX_A], a_empty[MAX_A], b_full[MAX_B], b_empty[MAX_B], acc_full, acc_empty;
+    __shared__ uint32_t tmem_base_s;
+    constexpr int NPL = PASSES == 3 ? 2 : 1;
+    constexpr int A_SLOT = NPL * A_PLANE;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t a_base = smem_u32(smem);
+    const uint32_t b_base = a_base + (uint32_t)p.a_slots * A_SLOT;
+    const int b_slot_bytes = NPL * p.b_plane;
+    const uint32_t all_k = p.kvol >= 32 ? 0xFFFFFFFFu : ((1u << p.kvol) - 1u);
+    const int T = p.T;
+
+    if (tid == 0) {
+        for (int s = 0; s < p.a_slots; ++s) {
+            mbar_init(smem_u32(&a_full[s]), PROD_WARPS);
+            mbar_init(smem_u32(&a_empty[s]), 1);
+        }
+        for (int s = 0; s < p.b_slots; ++s) {
+            mbar_init(smem_u32(&b_full[s]), 1);
+            mbar_init(smem_u32(&b_empty[s]), 1);
+        }
+        mbar_init(smem_u32(&acc_full), 1);
+        mbar_init(smem_u32(&acc_empty), 4);
+        mbar_fence_init();
+    }
+    if (warp == MMA_WARP) tmem_alloc(&tmem_base_s, (uint32_t)(T * p.acc_cols));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    auto tile_kmask = [&](int tile) -> uint32_t {
+        if (tile >= p.n_tiles) return 0u;
+        return p.tile_mask ? (p.tile_mask[tile] & all_k) : all_k;
+    };
+
+    if (warp < PROD_WARPS) {
+        // ------------------------------------------------------------------ A producers
+        constexpr int RPT = 8;       // rows per thread: rbase + 16 i
+        const int grp = tid & 7;     // 16-byte chunk within the 128-byte row
+        const int rbase = tid >> 3;
+        int item = 0, signalled = 0;
+        int ps = 0, ss = 0;  // ring positions of `item` and `signalled`
+        uint32_t ppar = 0;
+        for (int st = blockIdx.x; st < p.n_super; st += gridDim.x) {
+            uint32_t m[MAX_T], U = 0;
+#pragma unroll
+            for (int t = 0; t < MAX_T; ++t) {
+                m[t] = t < T ? tile_kmask(st * T + t) : 0u;
+                U |= m[t];
+            }
+            for (int k = 0; k < p.kvol; ++k) {
+                if (!((U >> k) & 1u)) continue;
+                int idx[MAX_T][RPT];
+#pragma unroll
+                for (int t = 0; t < MAX_T; ++t) {
+                    if (!((m[t] >> k) & 1u)) continue;
+                    const int tile0 = (st * T + t) * M;
+#pragma unroll
+                    for (int i = 0; i < RPT; ++i) {
+                        const int j = tile0 + rbase + 16 * i;
+                        idx[t][i] = j < p.n_rows ? __ldg(p.nbr + (size_t)k * p.n_rows + j) : -1;
+                    }
+                }
+                for (int c = 0; c < p.nchunks; ++c) {
+                    const int c0 = c * KC + grp * 8;
+                    const bool col_ok = c0 < p.cin;
+#pragma unroll
+                    for (int t = 0; t < MAX_T; ++t) {
+                        if (!((m[t] >> k) & 1u)) continue;
+                        mbar_wait(smem_u32(&a_empty[ps]), ppar ^ 1, 0);
+                        const uint32_t slot = a_base + (uint32_t)ps * A_SLOT;
+#pragma unroll
+                        for (int i = 0; i < RPT; ++i) {
+                            const int r = rbase + 16 * i;
+                            const uint32_t dst = slot + (uint32_t)r * 128u + (uint32_t)((grp ^ (r & 7)) << 4);
+                            const bool ok = idx[t][i] >= 0 && col_ok;
+                            const size_t off = ok ? (size_t)idx[t][i] * p.cin + c0 : 0;
+                            cp_async16(dst, p.x_hi + off, ok ? 16u : 0u);
+                            if (PASSES == 3) cp_async16(dst + A_PLANE, p.x_lo + off, ok ? 16u : 0u);
+                        }
+                        cp_async_commit();
+                        if (item - signalled >= LAG) {
+                            cp_async_wait<LAG>();
+                            fence_proxy_async();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(smem_u32(&a_full[ss]));
+                            ++signalled;
+                            if (++ss == p.a_slots) ss = 0;
+                        }
+                        ++item;
+                        if (++ps == p.a_slots) {
+                            ps = 0;
+                            ppar ^= 1u;
+                        }
+                    }
+                }
+            }
+        }
+        cp_async_wait<0>();
+        fence_proxy_async();
+        __syncwarp();
+        for (; signalled < item; ++signalled) {
+            if (lane == 0) mbar_arrive(smem_u32(&a_full[ss]));
+            if (++ss == p.a_slots) ss = 0;
+        }
+    } else if (warp == B_WARP) {
+        // ------------------------------------------------------------------ weight slabs
+        if (lane == 0) {
+            int bitem = 0;
+            for (int st = blockIdx.x; st < p.n_super; st += gridDim.x) {
+                uint32_t U = 0;
+                for (int t = 0; t < T; ++t) U |= tile_kmask(st * T + t);
+                for (int k = 0; k < p.kvol; ++k) {
+                    if (!((U >> k) & 1u)) continue;
+                    for (int c = 0; c < p.nchunks; ++c, ++bitem) {
+                        const int s = bitem % p.b_slots;
+                        const uint32_t par = (bitem / p.b_slots) & 1;
+                        mbar_wait(smem_u32(&b_empty[s]), par ^ 1, 1);
+                        const uint32_t bar = smem_u32(&b_full[s]);
+                        const uint32_t dst = b_base + (uint32_t)s * b_slot_bytes;
+                        const uint8_t *src = p.wpack + ((size_t)k * p.nchunks + c) * (size_t)b_slot_bytes;
+                        mbar_arrive_expect_tx(bar, (uint32_t)b_slot_bytes);
+                        bulk_g2s(dst, src, (uint32_t)p.b_plane, bar);
+                        if (PASSES == 3) bulk_g2s(dst + p.b_plane, src + p.b_plane, (uint32_t)p.b_plane, bar);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == MMA_WARP) {
+        // ------------------------------------------------------------------ MMA issuer
+        // The whole warp runs the (warp-uniform) control flow so that descriptors and ring positions live in
+        // uniform registers; one elected lane issues tcgen05.mma / tcgen05.commit.  (A single-lane branch makes
+        // ptxas wrap every UTCHMMA in an elect + R2UR.BROADCAST loop: ~80 issue cycles per MMA, measured.)
+        const uint32_t idesc = idesc_bf16(p.cout);
+        const uint64_t a_desc0 = desc_k_sw128(a_base), b_desc0 = desc_k_sw128(b_base);
+        int as = 0, bs = 0, siter = 0, item = 0, bitem = 0;
+        uint32_t apar = 0, bpar = 0;
+        long long w_acc = 0, w_b = 0, w_a = 0;
+        const long long t_begin = clock64();
+        for (int st = blockIdx.x; st < p.n_super; st += gridDim.x, ++siter) {
+            uint32_t m[MAX_T], U = 0;
+#pragma unroll
+            for (int t = 0; t < MAX_T; ++t) {
+                m[t] = t < T ? tile_kmask(st * T + t) : 0u;
+                U |= m[t];
+            }
+            long long tw0 = clock64();
+            mbar_wait(smem_u32(&acc_empty), (siter & 1) ^ 1, 2);
+            w_acc += clock64() - tw0;
+            tc_fence_after();
+            uint32_t started = 0;
+            for (int k = 0; k < p.kvol; ++k) {
+                if (!((U >> k) & 1u)) continue;
+                for (int c = 0; c < p.nchunks; ++c) {
+                    long long tw1 = clock64();
+                    mbar_wait(smem_u32(&b_full[bs]), bpar, 3);
+                    w_b += clock64() - tw1;
+                    const int ksteps = min(KC, p.cin - c * KC) / 16;
+                    const uint64_t db_hi = b_desc0 + (uint64_t)((uint32_t)(bs * b_slot_bytes) >> 4);
+                    const uint64_t db_lo = db_hi + (uint64_t)((uint32_t)p.b_plane >> 4);
+#pragma unroll
+                    for (int t = 0; t < MAX_T; ++t) {
+                        if (!((m[t] >> k) & 1u)) continue;
+                        long long tw2 = clock64();
+                        mbar_wait(smem_u32(&a_full[as]), apar, 4);
+                        w_a += clock64() - tw2;
+                        tc_fence_after();
+                        const uint64_t da_hi = a_desc0 + (uint64_t)((uint32_t)(as * A_SLOT) >> 4);
+                        const uint64_t da_lo = da_hi + (uint64_t)(A_PLANE >> 4);
+                        const uint32_t acc = tmem_base + (uint32_t)(t * p.acc_cols);
+                        const uint32_t first = (started >> t) & 1u;
+                        if (elect_one()) {
+                            for (int kk = 0; kk < ksteps; ++kk) {
+                                const uint64_t adv = (uint64_t)(kk * 2);
+                                umma(acc, da_hi + adv, db_hi + adv, idesc, first | (kk != 0));
+                                if (PASSES == 3) {
+                                    umma(acc, da_lo + adv, db_hi + adv, idesc, 1);
+                                    umma(acc, da_hi + adv, db_lo + adv, idesc, 1);
+                                }
+                            }
+                            umma_commit(smem_u32(&a_empty[as]));
+                        }
+                        __syncwarp();
+                        started |= 1u << t;
+                        ++item;
+                        if (++as == p.a_slots) {
+                            as = 0;
+                            apar ^= 1u;
+                        }
+                    }
+                    if (elect_one()) umma_commit(smem_u32(&b_empty[bs]));
+                    __syncwarp();
+                    ++bitem;
+                    if (++bs == p.b_slots) {
+                        bs = 0;
+                        bpar ^= 1u;
+                    }
+                }
+            }
+            if (elect_one()) {
+                if (started)
+                    umma_commit(smem_u32(&acc_full));
+                else
+                    mbar_arrive(smem_u32(&acc_full));
+            }
+            __syncwarp();
+        }
+        if (p.prof != nullptr && lane == 0) {
+            long long *o = p.prof + (size_t)blockIdx.x * 8;
+            o[0] = clock64() - t_begin;
+            o[1] = w_acc;
+            o[2] = w_b;
+            o[3] = w_a;
+            o[4] = item;
+            o[5] = bitem;
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue
+        const int quarter = warp & 3;
+        const bool vec = (p.ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
+        int siter = 0;
+        for (int st = blockIdx.x; st < p.n_super; st += gridDim.x, ++siter) {
+            mbar_wait(smem_u32(&acc_full), siter & 1, 5);
+            tc_fence_after();
+            for (int t = 0; t < T; ++t) {
+                const int tile = st * T + t;
+                if (tile >= p.n_tiles) break;
+                const bool has_acc = tile_kmask(tile) != 0;
+                const int j = tile * M + quarter * 32 + lane;
+                const bool row_ok = j < p.n_rows;
+                float *yrow = nullptr;
+                if (row_ok) yrow = p.y + (size_t)(p.out_rows ? p.out_rows[j] : j) * p.ldy;
+                const uint32_t acc_addr = tmem_base + (uint32_t)(t * p.acc_cols) + ((uint32_t)(quarter * 32) << 16);
+                for (int col = 0; col < p.cout; col += 16) {
+                    float acc[16];
+                    if (has_acc) {
+                        tmem_ld16(acc_addr + (uint32_t)col, acc);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+                    }
+                    if (!row_ok) continue;
+                    if (p.bias)
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) acc[e] += __ldg(p.bias + col + e);
+                    if (vec) {
+#pragma unroll
+                        for (int e = 0; e < 16; e += 4) {
+                            float4 o = make_float4(acc[e], acc[e + 1], acc[e + 2], acc[e + 3]);
+                            float4 *dst = reinterpret_cast<float4 *>(yrow + col + e);
+                            if (p.accumulate) {
+                                float4 old = *dst;
+                                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                            }
+                            *dst = o;
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) yrow[col + e] = p.accumulate ? yrow[col + e] + acc[e] : acc[e];
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&acc_empty));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) tmem_dealloc(tmem_base, (uint32_t)(T * p.acc_cols));
+}
+
+template <int PASSES>
+static void launch(int lag, int grid, size_t smem, cudaStream_t st, const Params &p) {
+    if (lag >= 3)
+        k_spconv_mt<PASSES, 3><<<grid, THREADS, smem, st>>>(p);
+    else if (lag == 2)
+        k_spconv_mt<PASSES, 2><<<grid, THREADS, smem, st>>>(p);
+    else
+        k_spconv_mt<PASSES, 1><<<grid, THREADS, smem, st>>>(p);
+}
+
+}  // namespace mt
+}  // namespace us3d
+
+using namespace us3d;
+
+static long long *g_prof = nullptr;
+static int g_tune_a_slots = 0, g_tune_lag = 0, g_tune_T = 0;
+
+extern "C" {
+
+/* debug / tuning hooks (not part of the drop-in surface): per-CTA wait counters of the MMA thread, ring overrides */
+void us3d_debug_set_prof(void *buf) { g_prof = (long long *)buf; }
+void us3d_debug_set_tuning(int a_slots, int lag, int T) {
+    g_tune_a_slots = a_slots;
+    g_tune_lag = lag;
+    g_tune_T = T;
+}
+
+int us3d_spconv_gather_mt(const void *x_hi, const void *x_lo, int n_in, const int32_t *nbr, int n_rows, int kvol,
+                          const void *wpack, int cin, int cout, int passes, const float *bias, const int32_t *out_rows,
+                          float *y, int ldy, int accumulate, const uint32_t *tile_mask, void *stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    US3D_CHECK_ARG(kvol >= 1 && kvol <= US3D_MAX_KVOL, "spconv_gather_mt: kvol %d out of range", kvol);
+    US3D_CHECK_ARG(passes == 1 || passes == 3, "spconv_gather_mt: passes must be 1 or 3");
+    US3D_CHECK_ARG(us3d_spconv_tc_supported(cin, cout), "spconv_gather_mt: unsupported channel counts %d -> %d", cin, cout);
+    US3D_CHECK_ARG(x_hi != nullptr && (passes == 1 || x_lo != nullptr), "spconv_gather_mt: missing activation plane");
+    US3D_CHECK_ARG((reinterpret_cast<uintptr_t>(x_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(x_lo) & 15) == 0,
+                   "spconv_gather_mt: planes must be 16-byte aligned");
+    US3D_CHECK_ARG(ldy >= cout && n_in > 0, "spconv_gather_mt: bad sizes");
+    if (n_rows == 0) return 0;
+    mt::Params p;
+    p.x_hi = (const __nv_bfloat16 *)x_hi; p.x_lo = (const __nv_bfloat16 *)x_lo;
+    p.nbr = nbr; p.n_rows = n_rows; p.kvol = kvol; p.n_tiles = ceil_div(n_rows, mt::M);
+    p.wpack = (const uint8_t *)wpack; p.cin = cin; p.cout = cout; p.nchunks = ceil_div(cin, mt::KC);
+    p.bias = bias; p.out_rows = out_rows; p.y = y; p.ldy = ldy; p.accumulate = accumulate; p.tile_mask = tile_mask;
+    const int npl = passes == 3 ? 2 : 1;
+    int cols = 32;
+    while (cols < cout) cols <<= 1;
+    p.acc_cols = cols;
+    int T = 512 / cols;
+    if (T > mt::MAX_T) T = mt::MAX_T;
+    // small maps: do not starve SMs of work for the sake of weight reuse
+    while (T > 1 && ceil_div(p.n_tiles, T) < num_sms()) T >>= 1;
+    if (g_tune_T > 0 && g_tune_T <= T) T = g_tune_T;
+    p.T = T;
+    p.prof = g_prof;
+    p.n_super = ceil_div(p.n_tiles, T);
+    p.b_plane = cout * 128;
+    const int a_slot = npl * mt::A_PLANE, b_slot = npl * p.b_plane;
+    const int budget = 208 * 1024;
+    p.b_slots = 2;
+    p.a_slots = (budget - p.b_slots * b_slot) / a_slot;
+    if (p.a_slots > mt::MAX_A) p.a_slots = mt::MAX_A;
+    US3D_CHECK_ARG(p.a_slots >= 2, "spconv_gather_mt: operand slots do not fit in shared memory (cout %d)", cout);
+    if (p.a_slots == mt::MAX_A && budget - p.a_slots * a_slot - 3 * b_slot >= 0) p.b_slots = 3;
+    if (g_tune_a_slots >= 2 && g_tune_a_slots <= p.a_slots) p.a_slots = g_tune_a_slots;
+    const size_t smem = (size_t)p.a_slots * a_slot + (size_t)p.b_slots * b_slot + 1024;
+    static bool attr_done = false;
+    if (!attr_done) {
+        US3D_CUDA(cudaFuncSetAttribute(mt::k_spconv_mt<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+        US3D_CUDA(cudaFuncSetAttribute(mt::k_spconv_mt<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+        US3D_CUDA(cudaFuncSetAttribute(mt::k_spconv_mt<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+        US3D_CUDA(cudaFuncSetAttribute(mt::k_spconv_mt<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+        US3D_CUDA(cudaFuncSetAttribute(mt::k_spconv_mt<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+        US3D_CUDA(cudaFuncSetAttribute(mt::k_spconv_mt<3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+        attr_done = true;
+    }
+    const int grid = p.n_super < num_sms() ? p.n_super : num_sms();
+    int lag = p.a_slots - 1;
+    if (g_tune_lag >= 1 && g_tune_lag < lag) lag = g_tune_lag;
+    if (passes == 3)
+        mt::launch<3>(lag, grid, smem, st, p);
+    else
+        mt::launch<1>(lag, grid, smem, st, p);
+    US3D_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

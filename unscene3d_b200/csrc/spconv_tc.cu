@@ -666,7 +666,7 @@ int us3d_spconv_wgrad_tc(const float *x, int ldx, const int32_t *nbr, int n_rows
     p.x = x; p.ldx = ldx; p.nbr = nbr; p.n_rows = n_rows; p.kvol = kvol; p.dy = dy; p.ldy = ldy; p.out_rows = out_rows;
     p.dw = dw; p.cin = cin; p.cout = cout; p.tile_mask = tile_mask;
     p.mblks = ceil_div(cin, 128);
-    int splits = ceil_div(2 * num_sms(), kvol * p.mblks);
+    int splits = (2 * num_sms()) / (kvol * p.mblks);  // whole waves of one CTA per SM: never spill into a third wave
     int max_splits = ceil_div(n_rows, 1024);
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;

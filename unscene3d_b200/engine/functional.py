@@ -92,6 +92,28 @@ def pack_weights(w3: torch.Tensor, transpose: bool, flip_k: bool, passes: int) -
     return out
 
 
+# forward / input-gradient tensor-core kernel: "cp" = cp.async row gather, persistent, double-buffered TMEM (default);
+# "tma" = same pipeline with TMA tile::gather4 (slower: ~80 cycles per gather4); "ldg" = register-staged gather
+_tc_kernel = {"fwd": "mt"}  # "mt" = "cp" + up to 4 output tiles sharing each weight slab (production)
+
+
+def bf16_planes(x: torch.Tensor, need_lo: bool):
+    """bf16 hi plane (+ lo = x - hi) of a row-major fp32 tensor, cached on the tensor object while its
+    version counter is unchanged (an activation feeds the forward conv, a shortcut conv and the weight gradient)."""
+    cached = getattr(x, "_us3d_planes", None)
+    if cached is not None and cached[2] == x._version and (cached[1] is not None or not need_lo):
+        return cached[0], cached[1]
+    n, c = x.shape
+    hi = torch.empty((n, c), dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty((n, c), dtype=torch.bfloat16, device=x.device) if need_lo else None
+    check(lib.us3d_split_bf16(x.data_ptr(), _ld(x), n, c, hi.data_ptr(), _ptr(lo), _stream()))
+    try:
+        x._us3d_planes = (hi, lo, x._version)
+    except Exception:  # pragma: no cover - tensors normally accept attributes
+        pass
+    return hi, lo
+
+
 def spconv_gather(x, table: NeighbourTable, w3, cin, cout, transpose_w, flip_k, bias=None, out=None, accumulate=False):
     x = _rows(x)
     y = out if out is not None else torch.empty((table.n_rows, cout), dtype=torch.float32, device=x.device)
@@ -99,7 +121,16 @@ def spconv_gather(x, table: NeighbourTable, w3, cin, cout, transpose_w, flip_k, 
     mode = _precision["mode"]
     if (mode != 0 and lib.us3d_spconv_tc_supported(cin, cout) and x.data_ptr() % 16 == 0 and _ld(x) % 4 == 0):
         wpack = pack_weights(w3, transpose_w, flip_k, mode)
-        _timed("dgrad" if transpose_w else "fwd", x.shape[0], table.n_rows, table.kvol, cin, cout, lambda: check(
+        kind = "dgrad" if transpose_w else "fwd"
+        if _tc_kernel["fwd"] in ("tma", "cp", "mt"):
+            hi, lo = bf16_planes(x, mode == 3)
+            fn = {"tma": lib.us3d_spconv_gather_tma, "cp": lib.us3d_spconv_gather_cp, "mt": lib.us3d_spconv_gather_mt}[_tc_kernel["fwd"]]
+            _timed(kind, x.shape[0], table.n_rows, table.kvol, cin, cout, lambda: check(
+                fn(hi.data_ptr(), _ptr(lo), x.shape[0], table.nbr.data_ptr(), table.n_rows, table.kvol,
+                                           wpack.data_ptr(), cin, cout, mode, _ptr(bias), 0, y.data_ptr(), _ld(y),
+                                           int(accumulate), _ptr(table.mask), st)))
+            return y
+        _timed(kind, x.shape[0], table.n_rows, table.kvol, cin, cout, lambda: check(
             lib.us3d_spconv_gather_tc(x.data_ptr(), _ld(x), table.nbr.data_ptr(), table.n_rows, table.kvol, wpack.data_ptr(),
                                       cin, cout, mode, _ptr(bias), 0, y.data_ptr(), _ld(y), int(accumulate),
                                       _ptr(table.mask), st)))
