@@ -119,6 +119,12 @@ int us3d_spconv_wgrad_tc(const float *x, int ldx, const int32_t *nbr, int n_rows
                          const int32_t *out_rows, float *dw, int cin, int cout, int passes, const uint32_t *tile_mask,
                          void *stream);
 
+/* Production weight-gradient kernel: operands from the bf16 planes of X and dY via cp.async; one CTA handles up
+ * to 4 kernel offsets per dY tile (one TMEM accumulator each), so dY is streamed ceil(kvol/4) times, not kvol. */
+int us3d_spconv_wgrad_planes(const void *x_hi, const void *x_lo, const void *dy_hi, const void *dy_lo, const int32_t *nbr,
+                             int n_rows, int kvol, float *dw, int cin, int cout, int passes, const uint32_t *tile_mask,
+                             void *stream);
+
 /* ---------------------------------------------------------------- normalisation / elementwise (A6)
  * BatchNorm1d over all rows (ME.MinkowskiBatchNorm, models/modules/common.py:20-22), train mode:
  *   stats: double sum[c], sumsq[c] (caller zeroes) ; finalize -> mean[c], invstd[c] float and the

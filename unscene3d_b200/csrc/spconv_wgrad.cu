@@ -1,0 +1,334 @@
+// Sparse-convolution weight gradient on tcgen05 — production kernel.
+//
+//     dW[k][ci][co] += sum_j X[nbr[k, j]][ci] * dY[j][co]
+//
+// D[M = ci (128 TMEM lanes)][N = co] accumulates over K = rows j.  Operands are read from the bf16 planes
+// (hi, + lo for the three-term split) exactly as they lie in HBM — rows j, channels contiguous — which makes
+// them MN-major UMMA operands: every 64-channel block of a 64-row stage is a [64 rows][128 B] slab in the
+// SWIZZLE_128B MN-major canonical layout (8-row groups 1024 B apart = SBO, blocks one slab apart = LBO); one
+// K = 16 step is two 8-row groups (2048 B).
+//
+// One CTA = (group of KG = 512 / npad (<= 4) kernel offsets, 128-input-channel block, row split).  For every
+// 64-row block of its split the dY tile is fetched ONCE (B ring) and multiplied against the gathered X tile of
+// each offset of the group (A ring), each offset accumulating into its own TMEM accumulator — the dY stream,
+// which a one-offset-per-CTA layout re-reads 27 times, is read ceil(27 / KG) times.
+//
+//   warps 0-3  producers: 16-byte cp.async into the swizzled slabs (zero-fill for absent neighbours / rows past
+//              the split), cp.async.wait_group (lag) -> fence.proxy.async -> mbarrier arrive
+//   warp 4     MMA issuer (warp-uniform control flow, one elected lane issues)
+//   warps 0-3  epilogue at the end: tcgen05.ld -> red.global.add into dW
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace us3d {
+namespace wg {
+
+using namespace tcx;
+
+constexpr int R = 64;             // rows (GEMM-K) per stage
+constexpr int SLAB = R * 128;     // one 64-channel block of one plane
+constexpr int PROD_WARPS = 4;
+constexpr int MMA_WARP = PROD_WARPS;
+constexpr int THREADS = (PROD_WARPS + 1) * 32;
+constexpr int MAX_A = 6, MAX_B = 3, MAX_KG = 4, MAX_LAG = 3;
+
+struct Params {
+    const __nv_bfloat16 *x_hi, *x_lo;    // [n_in, cin]
+    const __nv_bfloat16 *dy_hi, *dy_lo;  // [n_rows, cout]
+    const int32_t *nbr;
+    int n_rows, kvol;
+    float *dw;
+    int cin, cout, npad, mblks, splits, rows_per_split, kg, ngroups;
+    const uint32_t *tile_mask;
+    int a_slots, b_slots, acc_cols;
+};
+
+template <int PASSES, int LAG>
+__global__ void __launch_bounds__(THREADS, 1) k_wgrad(Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t a_full[MAX_A], a_empty[MAX_A], b_full[MAX_B], b_empty[MAX_B], acc_full;
+    __shared__ uint32_t tmem_base_s;
+    constexpr int NPL = PASSES == 3 ? 2 : 1;
+    constexpr int A_PLANE = 2 * SLAB;  // 128 input channels
+    constexpr int A_SLOT = NPL * A_PLANE;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int b_plane = (p.npad / 64) * SLAB;
+    const int b_slot_bytes = NPL * b_plane;
+    const uint32_t a_base = smem_u32(smem);
+    const uint32_t b_base = a_base + (uint32_t)p.a_slots * A_SLOT;
+
+    int b = blockIdx.x;
+    const int split = b % p.splits;
+    b /= p.splits;
+    const int mblk = b % p.mblks;
+    const int grp = b / p.mblks;
+    const int k0 = grp * p.kg;
+    const int nk = min(p.kg, p.kvol - k0);
+    const int r_begin = split * p.rows_per_split;
+    const int r_end = min(p.n_rows, r_begin + p.rows_per_split);
+    const int ci0 = mblk * 128;
+    const uint32_t gmask = ((nk >= 32 ? 0xFFFFFFFFu : ((1u << nk) - 1u)) << k0);
+
+    // offsets of this group with a neighbour somewhere in the 128-row tile holding row r0
+    auto active = [&](int r0) -> uint32_t {
+        return (p.tile_mask ? p.tile_mask[r0 >> 7] : 0xFFFFFFFFu) & gmask;
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < p.a_slots; ++s) {
+            mbar_init(smem_u32(&a_full[s]), PROD_WARPS);
+            mbar_init(smem_u32(&a_empty[s]), 1);
+        }
+        for (int s = 0; s < p.b_slots; ++s) {
+            mbar_init(smem_u32(&b_full[s]), PROD_WARPS);
+            mbar_init(smem_u32(&b_empty[s]), 1);
+        }
+        mbar_init(smem_u32(&acc_full), 1);
+        mbar_fence_init();
+    }
+    if (warp == MMA_WARP) tmem_alloc(&tmem_base_s, (uint32_t)p.acc_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    uint32_t touched = 0;  // offsets (relative to k0) that received at least one MMA — same in every role
+
+    if (warp < PROD_WARPS) {
+        // ------------------------------------------------------------------ producers
+        const int GB = p.cout / 8;  // 16-byte chunks per dY row
+        uint32_t pending[MAX_LAG];  // mbarriers of the committed, not yet signalled groups (oldest first)
+        int n_pending = 0;
+        int as = 0, bs = 0;
+        uint32_t apar = 0, bpar = 0;
+        auto commit_and_signal = [&](uint32_t bar) {
+            cp_async_commit();
+            if (n_pending == LAG) {
+                cp_async_wait<LAG>();
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(pending[0]);
+#pragma unroll
+                for (int i = 0; i + 1 < MAX_LAG; ++i) pending[i] = pending[i + 1];
+                --n_pending;
+            }
+#pragma unroll
+            for (int i = 0; i < MAX_LAG; ++i)
+                if (i == n_pending) pending[i] = bar;
+            ++n_pending;
+        };
+        for (int r0 = r_begin; r0 < r_end; r0 += R) {
+            const uint32_t act = active(r0);
+            if (!act) continue;
+            touched |= act;
+            // ---- B item: 64 rows of dY
+            mbar_wait(smem_u32(&b_empty[bs]), bpar ^ 1, 0);
+            {
+                const uint32_t slot = b_base + (uint32_t)bs * b_slot_bytes;
+                for (int it = tid; it < R * GB; it += PROD_WARPS * 32) {
+                    const int row = it / GB, g = it - row * GB;
+                    const int j = r0 + row;
+                    const bool ok = j < r_end;
+                    const uint32_t dst = slot + (uint32_t)(g >> 3) * SLAB + (uint32_t)row * 128u + (uint32_t)(((g & 7) ^ (row & 7)) << 4);
+                    const size_t off = ok ? (size_t)j * p.cout + g * 8 : 0;
+                    cp_async16(dst, p.dy_hi + off, ok ? 16u : 0u);
+                    if (PASSES == 3) cp_async16(dst + b_plane, p.dy_lo + off, ok ? 16u : 0u);
+                }
+                commit_and_signal(smem_u32(&b_full[bs]));
+                if (++bs == p.b_slots) {
+                    bs = 0;
+                    bpar ^= 1u;
+                }
+            }
+            // ---- A items: gathered X rows for every active offset of the group
+            for (int kq = 0; kq < nk; ++kq) {
+                const int k = k0 + kq;
+                if (!((act >> k) & 1u)) continue;
+                mbar_wait(smem_u32(&a_empty[as]), apar ^ 1, 1);
+                const uint32_t slot = a_base + (uint32_t)as * A_SLOT;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int it = i * (PROD_WARPS * 32) + tid;
+                    const int row = it >> 4, g = it & 15;
+                    const int j = r0 + row;
+                    int src = -1;
+                    if (j < r_end) src = __ldg(p.nbr + (size_t)k * p.n_rows + j);
+                    const int c = ci0 + g * 8;
+                    const bool ok = src >= 0 && c < p.cin;
+                    const uint32_t dst = slot + (uint32_t)(g >> 3) * SLAB + (uint32_t)row * 128u + (uint32_t)(((g & 7) ^ (row & 7)) << 4);
+                    const size_t off = ok ? (size_t)src * p.cin + c : 0;
+                    cp_async16(dst, p.x_hi + off, ok ? 16u : 0u);
+                    if (PASSES == 3) cp_async16(dst + A_PLANE, p.x_lo + off, ok ? 16u : 0u);
+                }
+                commit_and_signal(smem_u32(&a_full[as]));
+                if (++as == p.a_slots) {
+                    as = 0;
+                    apar ^= 1u;
+                }
+            }
+        }
+        cp_async_wait<0>();
+        fence_proxy_async();
+        __syncwarp();
+        for (int i = 0; i < n_pending; ++i)
+            if (lane == 0) mbar_arrive(pending[i]);
+
+        // ------------------------------------------------------------------ epilogue: lanes = ci, columns = co
+        if (touched) {
+            mbar_wait(smem_u32(&acc_full), 0, 2);
+            tc_fence_after();
+            const int ci = warp * 32 + lane;  // warp w owns TMEM lanes 32 w .. 32 w + 31
+            const bool ci_ok = ci0 + ci < p.cin;
+            for (int kq = 0; kq < nk; ++kq) {
+                if (!((touched >> (k0 + kq)) & 1u)) continue;
+                float *drow = p.dw + ((size_t)(k0 + kq) * p.cin + ci0 + ci) * p.cout;
+                const uint32_t taddr = tmem_base + (uint32_t)(kq * p.npad) + ((uint32_t)(warp * 32) << 16);
+                for (int col = 0; col < p.cout; col += 16) {
+                    float acc[16];
+                    tmem_ld16(taddr + (uint32_t)col, acc);
+                    if (ci_ok) {
+#pragma unroll
+                        for (int e = 0; e < 16; e += 4) atomicAdd(reinterpret_cast<float4 *>(drow + col + e), make_float4(acc[e], acc[e + 1], acc[e + 2], acc[e + 3]));
+                    }
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ MMA issuer (uniform warp, elected lane)
+        const uint32_t idesc = idesc_bf16(p.npad, true, true);
+        const uint64_t a_desc0 = desc_mn_sw128(a_base, SLAB), b_desc0 = desc_mn_sw128(b_base, SLAB);
+        int as = 0, bs = 0;
+        uint32_t apar = 0, bpar = 0;
+        for (int r0 = r_begin; r0 < r_end; r0 += R) {
+            const uint32_t act = active(r0);
+            if (!act) continue;
+            mbar_wait(smem_u32(&b_full[bs]), bpar, 3);
+            const uint64_t db_hi = b_desc0 + (uint64_t)((uint32_t)(bs * b_slot_bytes) >> 4);
+            const uint64_t db_lo = db_hi + (uint64_t)((uint32_t)b_plane >> 4);
+            for (int kq = 0; kq < nk; ++kq) {
+                const int k = k0 + kq;
+                if (!((act >> k) & 1u)) continue;
+                mbar_wait(smem_u32(&a_full[as]), apar, 4);
+                tc_fence_after();
+                const uint64_t da_hi = a_desc0 + (uint64_t)((uint32_t)(as * A_SLOT) >> 4);
+                const uint64_t da_lo = da_hi + (uint64_t)(A_PLANE >> 4);
+                const uint32_t acc = tmem_base + (uint32_t)(kq * p.npad);
+                const uint32_t first = (touched >> k) & 1u;
+                if (elect_one()) {
+#pragma unroll
+                    for (int kk = 0; kk < R / 16; ++kk) {
+                        const uint64_t adv = (uint64_t)(kk * (2048 >> 4));  // two 8-row groups
+                        umma(acc, da_hi + adv, db_hi + adv, idesc, first | (kk != 0));
+                        if (PASSES == 3) {
+                            umma(acc, da_lo + adv, db_hi + adv, idesc, 1);
+                            umma(acc, da_hi + adv, db_lo + adv, idesc, 1);
+                        }
+                    }
+                    umma_commit(smem_u32(&a_empty[as]));
+                }
+                __syncwarp();
+                touched |= 1u << k;
+                if (++as == p.a_slots) {
+                    as = 0;
+                    apar ^= 1u;
+                }
+            }
+            if (elect_one()) umma_commit(smem_u32(&b_empty[bs]));
+            __syncwarp();
+            if (++bs == p.b_slots) {
+                bs = 0;
+                bpar ^= 1u;
+            }
+        }
+        if (touched && elect_one()) umma_commit(smem_u32(&acc_full));
+        __syncwarp();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) tmem_dealloc(tmem_base, (uint32_t)p.acc_cols);
+}
+
+template <int PASSES>
+static void launch(int lag, int grid, size_t smem, cudaStream_t st, const Params &p) {
+    if (lag >= 3)
+        k_wgrad<PASSES, 3><<<grid, THREADS, smem, st>>>(p);
+    else if (lag == 2)
+        k_wgrad<PASSES, 2><<<grid, THREADS, smem, st>>>(p);
+    else
+        k_wgrad<PASSES, 1><<<grid, THREADS, smem, st>>>(p);
+}
+
+}  // namespace wg
+}  // namespace us3d
+
+using namespace us3d;
+
+extern "C" {
+
+int us3d_spconv_wgrad_planes(const void *x_hi, const void *x_lo, const void *dy_hi, const void *dy_lo, const int32_t *nbr,
+                             int n_rows, int kvol, float *dw, int cin, int cout, int passes, const uint32_t *tile_mask,
+                             void *stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    US3D_CHECK_ARG(kvol >= 1 && kvol <= US3D_MAX_KVOL, "spconv_wgrad_planes: kvol %d out of range", kvol);
+    US3D_CHECK_ARG(passes == 1 || passes == 3, "spconv_wgrad_planes: passes must be 1 or 3");
+    US3D_CHECK_ARG(us3d_spconv_wgrad_tc_supported(cin, cout), "spconv_wgrad_planes: unsupported channel counts %d -> %d", cin, cout);
+    US3D_CHECK_ARG(x_hi && dy_hi && (passes == 1 || (x_lo && dy_lo)), "spconv_wgrad_planes: missing plane");
+    if (n_rows == 0) return 0;
+    wg::Params p;
+    p.x_hi = (const __nv_bfloat16 *)x_hi; p.x_lo = (const __nv_bfloat16 *)x_lo;
+    p.dy_hi = (const __nv_bfloat16 *)dy_hi; p.dy_lo = (const __nv_bfloat16 *)dy_lo;
+    p.nbr = nbr; p.n_rows = n_rows; p.kvol = kvol; p.dw = dw; p.cin = cin; p.cout = cout; p.tile_mask = tile_mask;
+    p.npad = ceil_div(cout, 64) * 64;
+    p.mblks = ceil_div(cin, 128);
+    int kg = 512 / p.npad;
+    if (kg > wg::MAX_KG) kg = wg::MAX_KG;
+    if (kg > kvol) kg = kvol;
+    p.kg = kg;
+    p.ngroups = ceil_div(kvol, kg);
+    int acc = 32;
+    while (acc < kg * p.npad) acc <<= 1;
+    p.acc_cols = acc;
+    // one CTA per SM, whole waves
+    int units = p.ngroups * p.mblks;
+    int splits = num_sms() / units;
+    if (splits < 1) splits = 1;
+    int max_splits = ceil_div(n_rows, 512);
+    if (splits > max_splits) splits = max_splits;
+    p.rows_per_split = ceil_div(ceil_div(n_rows, splits), 128) * 128;
+    p.splits = ceil_div(n_rows, p.rows_per_split);
+    const int npl = passes == 3 ? 2 : 1;
+    const int a_slot = npl * 2 * wg::SLAB, b_slot = npl * (p.npad / 64) * wg::SLAB;
+    const int budget = 208 * 1024;
+    p.b_slots = 2;
+    p.a_slots = (budget - p.b_slots * b_slot) / a_slot;
+    if (p.a_slots > wg::MAX_A) p.a_slots = wg::MAX_A;
+    US3D_CHECK_ARG(p.a_slots >= 2, "spconv_wgrad_planes: operand slots do not fit in shared memory (cout %d)", cout);
+    const size_t smem = (size_t)p.a_slots * a_slot + (size_t)p.b_slots * b_slot + 1024;
+    static bool attr_done = false;
+    if (!attr_done) {
+        US3D_CUDA(cudaFuncSetAttribute(wg::k_wgrad<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+        US3D_CUDA(cudaFuncSetAttribute(wg::k_wgrad<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+        US3D_CUDA(cudaFuncSetAttribute(wg::k_wgrad<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+        US3D_CUDA(cudaFuncSetAttribute(wg::k_wgrad<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+        US3D_CUDA(cudaFuncSetAttribute(wg::k_wgrad<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+        US3D_CUDA(cudaFuncSetAttribute(wg::k_wgrad<3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+        attr_done = true;
+    }
+    const int grid = p.ngroups * p.mblks * p.splits;
+    // Unsignalled cp.async groups: at most a_slots - 1 (an A slot is re-used a_slots items later) and at most
+    // 2 (b_slots - 1): a row block issues >= 2 groups (dY + one offset), and the dY slot of block n + 1 may only be
+    // claimed once every group of block n + 1 - b_slots has been signalled and consumed.
+    int lag = p.a_slots - 1;
+    if (lag > 2 * (p.b_slots - 1)) lag = 2 * (p.b_slots - 1);
+    if (lag > wg::MAX_LAG) lag = wg::MAX_LAG;
+    if (lag < 1) lag = 1;
+    if (passes == 3)
+        wg::launch<3>(lag, grid, smem, st, p);
+    else
+        wg::launch<1>(lag, grid, smem, st, p);
+    US3D_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

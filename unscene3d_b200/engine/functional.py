@@ -94,7 +94,9 @@ def pack_weights(w3: torch.Tensor, transpose: bool, flip_k: bool, passes: int) -
 
 # forward / input-gradient tensor-core kernel: "cp" = cp.async row gather, persistent, double-buffered TMEM (default);
 # "tma" = same pipeline with TMA tile::gather4 (slower: ~80 cycles per gather4); "ldg" = register-staged gather
-_tc_kernel = {"fwd": "mt"}  # "mt" = "cp" + up to 4 output tiles sharing each weight slab (production)
+# "mt" = "cp" + up to 4 output tiles sharing each weight slab (production).  Weight gradient: "planes" = cp.async
+# from the bf16 planes, up to 4 offsets per dY tile (production); "ldg" = register-staged, one offset per CTA
+_tc_kernel = {"fwd": "mt", "wgrad": "planes"}
 
 
 def bf16_planes(x: torch.Tensor, need_lo: bool):
@@ -149,6 +151,13 @@ def spconv_wgrad(x, table: NeighbourTable, dy, cin, cout):
     mode = _precision["mode"]
     if (mode != 0 and lib.us3d_spconv_wgrad_tc_supported(cin, cout) and x.data_ptr() % 16 == 0 and dy.data_ptr() % 16 == 0
             and _ld(x) % 4 == 0 and _ld(dy) % 4 == 0):
+        if _tc_kernel["wgrad"] == "planes":
+            xh, xl = bf16_planes(x, mode == 3)
+            dh, dl = bf16_planes(dy, mode == 3)
+            _timed("wgrad", x.shape[0], table.n_rows, table.kvol, cin, cout, lambda: check(
+                lib.us3d_spconv_wgrad_planes(xh.data_ptr(), _ptr(xl), dh.data_ptr(), _ptr(dl), table.nbr.data_ptr(), table.n_rows,
+                                             table.kvol, dw.data_ptr(), cin, cout, mode, _ptr(table.mask), st)))
+            return dw
         _timed("wgrad", x.shape[0], table.n_rows, table.kvol, cin, cout, lambda: check(
             lib.us3d_spconv_wgrad_tc(x.data_ptr(), _ld(x), table.nbr.data_ptr(), table.n_rows, table.kvol, dy.data_ptr(), _ld(dy),
                                      0, dw.data_ptr(), cin, cout, mode, _ptr(table.mask), st)))
@@ -171,6 +180,7 @@ class SparseConvFunction(torch.autograd.Function):
         y = spconv_gather(x, fwd, w3, cin, cout, False, False, None if bias is None else bias.detach().contiguous())
         ctx.save_for_backward(x, kernel)
         ctx.fwd, ctx.bwd_getter, ctx.has_bias = fwd, bwd_getter, bias is not None
+        ctx.x_planes = getattr(x, "_us3d_planes", None)  # the weight gradient re-uses the forward's bf16 planes
         return y
 
     @staticmethod
@@ -178,6 +188,8 @@ class SparseConvFunction(torch.autograd.Function):
         x, kernel = ctx.saved_tensors
         dy = _rows(dy)
         fwd = ctx.fwd
+        if ctx.x_planes is not None and ctx.x_planes[2] == x._version:
+            x._us3d_planes = ctx.x_planes
         w3 = kernel.detach().contiguous().view(fwd.kvol, kernel.shape[-2], kernel.shape[-1])
         cin, cout = w3.shape[1], w3.shape[2]
         dx = dw = db = None
