@@ -45,6 +45,8 @@ struct Params {
     int ldy, accumulate;
     const uint32_t *tile_mask;
     int a_slots, b_slots, b_plane, acc_cols;
+    int ksplit, n_units;                  // small maps: the offsets of a super-tile are dealt to `ksplit` CTAs
+    uint32_t part_mask[US3D_MAX_KVOL];    // offsets handled by part q (k % ksplit == q)
     long long *prof;  // optional per-CTA wait-cycle counters of the MMA thread (debug)
 };
 
@@ -82,9 +84,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
 
-    auto tile_kmask = [&](int tile) -> uint32_t {
+    auto tile_kmask = [&](int tile, uint32_t pm) -> uint32_t {
         if (tile >= p.n_tiles) return 0u;
-        return p.tile_mask ? (p.tile_mask[tile] & all_k) : all_k;
+        return (p.tile_mask ? (p.tile_mask[tile] & all_k) : all_k) & pm;
     };
 
     if (warp < PROD_WARPS) {
@@ -95,11 +97,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
         int item = 0, signalled = 0;
         int ps = 0, ss = 0;  // ring positions of `item` and `signalled`
         uint32_t ppar = 0;
-        for (int st = blockIdx.x; st < p.n_super; st += gridDim.x) {
+        for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+            const int st = u / p.ksplit;
+            const uint32_t pm = p.part_mask[u - st * p.ksplit];
             uint32_t m[MAX_T], U = 0;
 #pragma unroll
             for (int t = 0; t < MAX_T; ++t) {
-                m[t] = t < T ? tile_kmask(st * T + t) : 0u;
+                m[t] = t < T ? tile_kmask(st * T + t, pm) : 0u;
                 U |= m[t];
             }
             for (int k = 0; k < p.kvol; ++k) {
@@ -161,9 +165,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
         // ------------------------------------------------------------------ weight slabs
         if (lane == 0) {
             int bitem = 0;
-            for (int st = blockIdx.x; st < p.n_super; st += gridDim.x) {
+            for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+                const int st = u / p.ksplit;
+                const uint32_t pm = p.part_mask[u - st * p.ksplit];
                 uint32_t U = 0;
-                for (int t = 0; t < T; ++t) U |= tile_kmask(st * T + t);
+                for (int t = 0; t < T; ++t) U |= tile_kmask(st * T + t, pm);
                 for (int k = 0; k < p.kvol; ++k) {
                     if (!((U >> k) & 1u)) continue;
                     for (int c = 0; c < p.nchunks; ++c, ++bitem) {
@@ -192,11 +198,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
         uint32_t apar = 0, bpar = 0;
         long long w_acc = 0, w_b = 0, w_a = 0;
         const long long t_begin = clock64();
-        for (int st = blockIdx.x; st < p.n_super; st += gridDim.x, ++siter) {
+        for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++siter) {
+            const int st = u / p.ksplit;
+            const uint32_t pm = p.part_mask[u - st * p.ksplit];
             uint32_t m[MAX_T], U = 0;
 #pragma unroll
             for (int t = 0; t < MAX_T; ++t) {
-                m[t] = t < T ? tile_kmask(st * T + t) : 0u;
+                m[t] = t < T ? tile_kmask(st * T + t, pm) : 0u;
                 U |= m[t];
             }
             long long tw0 = clock64();
@@ -274,13 +282,18 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
         const int quarter = warp & 3;
         const bool vec = (p.ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
         int siter = 0;
-        for (int st = blockIdx.x; st < p.n_super; st += gridDim.x, ++siter) {
+        const bool split = p.ksplit > 1;  // partial sums of the offset parts meet in y through vector reds (y pre-zeroed)
+        for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++siter) {
+            const int st = u / p.ksplit;
+            const int part = u - st * p.ksplit;
+            const uint32_t pm = p.part_mask[part];
             mbar_wait(smem_u32(&acc_full), siter & 1, 5);
             tc_fence_after();
             for (int t = 0; t < T; ++t) {
                 const int tile = st * T + t;
                 if (tile >= p.n_tiles) break;
-                const bool has_acc = tile_kmask(tile) != 0;
+                const bool has_acc = tile_kmask(tile, pm) != 0;
+                if (split && !has_acc && !(p.bias && part == 0)) continue;
                 const int j = tile * M + quarter * 32 + lane;
                 const bool row_ok = j < p.n_rows;
                 float *yrow = nullptr;
@@ -295,10 +308,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
                         for (int e = 0; e < 16; ++e) acc[e] = 0.f;
                     }
                     if (!row_ok) continue;
-                    if (p.bias)
+                    if (p.bias && part == 0)
 #pragma unroll
                         for (int e = 0; e < 16; ++e) acc[e] += __ldg(p.bias + col + e);
-                    if (vec) {
+                    if (split) {
+                        if (vec) {
+#pragma unroll
+                            for (int e = 0; e < 16; e += 4)
+                                atomicAdd(reinterpret_cast<float4 *>(yrow + col + e), make_float4(acc[e], acc[e + 1], acc[e + 2], acc[e + 3]));
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) atomicAdd(yrow + col + e, acc[e]);
+                        }
+                    } else if (vec) {
 #pragma unroll
                         for (int e = 0; e < 16; e += 4) {
                             float4 o = make_float4(acc[e], acc[e + 1], acc[e + 2], acc[e + 3]);
@@ -383,6 +405,21 @@ int us3d_spconv_gather_mt(const void *x_hi, const void *x_lo, int n_in, const in
     p.T = T;
     p.prof = g_prof;
     p.n_super = ceil_div(p.n_tiles, T);
+    // small maps (coarse levels): deal the kernel offsets of a super-tile to several CTAs; partial sums meet in y
+    int ksplit = 1;
+    if (out_rows == nullptr && kvol > 1 && p.n_super * 2 <= num_sms()) {
+        ksplit = num_sms() / p.n_super;
+        if (ksplit > kvol) ksplit = kvol;
+    }
+    p.ksplit = ksplit;
+    p.n_units = p.n_super * ksplit;
+    for (int q = 0; q < US3D_MAX_KVOL; ++q) {
+        uint32_t pmask = 0;
+        for (int k = q; k < kvol && q < ksplit; k += ksplit) pmask |= 1u << k;
+        p.part_mask[q] = ksplit == 1 ? 0xFFFFFFFFu : pmask;
+    }
+    if (ksplit > 1 && !accumulate)
+        US3D_CUDA(cudaMemset2DAsync(y, (size_t)ldy * sizeof(float), 0, (size_t)cout * sizeof(float), (size_t)n_rows, st));
     p.b_plane = cout * 128;
     const int a_slot = npl * mt::A_PLANE, b_slot = npl * p.b_plane;
     const int budget = 208 * 1024;
@@ -403,7 +440,7 @@ int us3d_spconv_gather_mt(const void *x_hi, const void *x_lo, int n_in, const in
         US3D_CUDA(cudaFuncSetAttribute(mt::k_spconv_mt<3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
         attr_done = true;
     }
-    const int grid = p.n_super < num_sms() ? p.n_super : num_sms();
+    const int grid = p.n_units < num_sms() ? p.n_units : num_sms();
     int lag = p.a_slots - 1;
     if (g_tune_lag >= 1 && g_tune_lag < lag) lag = g_tune_lag;
     if (passes == 3)
