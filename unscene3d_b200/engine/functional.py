@@ -203,34 +203,40 @@ class SparseConvFunction(torch.autograd.Function):
         return dx, dw, db, None, None
 
 
-class BatchNormFunction(torch.autograd.Function):
-    """y = [relu]( BN_train(x) [+ residual] ), statistics over all rows, running stats updated in place."""
+def bn_batch_stats(x, running_mean, running_var, momentum, eps):
+    """Batch statistics of all rows (no autograd: the apply function's backward carries the dependence on them).
+    Returns (mean, invstd) fp32 [c]; updates the running statistics in place like nn.BatchNorm1d."""
+    x = _rows(x)
+    n, c = x.shape
+    dev = x.device
+    st = _stream()
+    acc = torch.zeros((2, c), dtype=torch.float64, device=dev)
+    mean = torch.empty(c, dtype=torch.float32, device=dev)
+    invstd = torch.empty(c, dtype=torch.float32, device=dev)
+    check(lib.us3d_bn_stats(x.data_ptr(), _ld(x), n, c, acc[0].data_ptr(), acc[1].data_ptr(), st))
+    check(lib.us3d_bn_finalize(acc[0].data_ptr(), acc[1].data_ptr(), n, c, float(eps), float(momentum if momentum is not None else 0.0),
+                               mean.data_ptr(), invstd.data_ptr(), _ptr(running_mean), _ptr(running_var), st))
+    return mean, invstd
+
+
+class BatchNormApplyFunction(torch.autograd.Function):
+    """y = [relu]( (x - mean) * invstd * gamma + beta [+ residual] ) with (mean, invstd) given.  `batch_stats`
+    says whether they are this batch's statistics (training: backward includes the two batch terms) or constants."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, residual, running_mean, running_var, momentum, eps, training, relu):
+    def forward(ctx, x, gamma, beta, residual, mean, invstd, batch_stats, relu):
         x = _rows(x)
         n, c = x.shape
         dev = x.device
         if residual is not None:
             residual = _rows(residual)
-        st = _stream()
-        if training:
-            acc = torch.zeros((2, c), dtype=torch.float64, device=dev)
-            mean = torch.empty(c, dtype=torch.float32, device=dev)
-            invstd = torch.empty(c, dtype=torch.float32, device=dev)
-            check(lib.us3d_bn_stats(x.data_ptr(), _ld(x), n, c, acc[0].data_ptr(), acc[1].data_ptr(), st))
-            check(lib.us3d_bn_finalize(acc[0].data_ptr(), acc[1].data_ptr(), n, c, float(eps), float(momentum if momentum is not None else 0.0),
-                                       mean.data_ptr(), invstd.data_ptr(), _ptr(running_mean), _ptr(running_var), st))
-        else:
-            mean = running_mean.detach().float()
-            invstd = torch.rsqrt(running_var.detach().float() + eps)
         g = gamma.detach().contiguous() if gamma is not None else torch.ones(c, device=dev)
         b = beta.detach().contiguous() if beta is not None else torch.zeros(c, device=dev)
         y = torch.empty((n, c), dtype=torch.float32, device=dev)
         check(lib.us3d_bn_apply(x.data_ptr(), _ld(x), n, c, mean.data_ptr(), invstd.data_ptr(), g.data_ptr(), b.data_ptr(),
-                                _ptr(residual), 0 if residual is None else _ld(residual), int(relu), y.data_ptr(), _ld(y), st))
+                                _ptr(residual), 0 if residual is None else _ld(residual), int(relu), y.data_ptr(), _ld(y), _stream()))
         ctx.save_for_backward(x, y if relu else None, mean, invstd, g)
-        ctx.relu, ctx.training, ctx.has_res = bool(relu), bool(training), residual is not None
+        ctx.relu, ctx.training, ctx.has_res = bool(relu), bool(batch_stats), residual is not None
         ctx.affine = gamma is not None
         return y
 
@@ -260,7 +266,20 @@ class BatchNormFunction(torch.autograd.Function):
             dgamma, dbeta = dgamma_src[1].float(), dgamma_src[0].float()
         if not ctx.affine:
             dgamma = dbeta = None
-        return dx, dgamma, dbeta, dres, None, None, None, None, None, None
+        return dx, dgamma, dbeta, dres, None, None, None, None
+
+
+class BatchNormFunction:
+    """Statistics + apply in one call (kept for callers that do not need the deferred form)."""
+
+    @staticmethod
+    def apply(x, gamma, beta, residual, running_mean, running_var, momentum, eps, training, relu):
+        if training:
+            mean, invstd = bn_batch_stats(x.detach(), running_mean, running_var, momentum, eps)
+        else:
+            mean = running_mean.detach().float()
+            invstd = torch.rsqrt(running_var.detach().float() + eps)
+        return BatchNormApplyFunction.apply(x, gamma, beta, residual, mean, invstd, training, relu)
 
 
 class ReLUFunction(torch.autograd.Function):

@@ -72,9 +72,36 @@ class SparseTensor:
                 f"feature rows {features.shape[0]} != coordinate map size {coordinate_manager.size(coordinate_map_key)}")
         if requires_grad is not None:
             features.requires_grad_(requires_grad)
-        self._F = features
+        self._feats = features
+        self._lazy = None
         self.coordinate_map_key = coordinate_map_key
         self.coordinate_manager = coordinate_manager
+
+    # ---- deferred BatchNorm epilogue -----------------------------------------------------------
+    # MinkowskiBatchNorm computes the batch statistics at once but defers the normalisation; a following
+    # `+= residual` and MinkowskiReLU are folded into ONE apply pass (y = relu(bn(x) + residual)) — the
+    # reference's conv-bn-relu and block-tail patterns (models/modules/resnet_block.py:48-64) become a single
+    # read of the conv output.  Touching the features any other way materialises the plain result.
+    @classmethod
+    def _deferred(cls, lazy, coordinate_map_key, coordinate_manager):
+        self = cls.__new__(cls)
+        self._feats = None
+        self._lazy = lazy
+        self.coordinate_map_key = coordinate_map_key
+        self.coordinate_manager = coordinate_manager
+        return self
+
+    @property
+    def _F(self):
+        if self._feats is None:
+            self._feats = self._lazy.materialize()
+            self._lazy = None
+        return self._feats
+
+    @_F.setter
+    def _F(self, value):
+        self._feats = value
+        self._lazy = None
 
     # ---- accessors ---------------------------------------------------------------------------
     @property
@@ -164,16 +191,25 @@ class SparseTensor:
     def _add(self, other):
         if isinstance(other, SparseTensor):
             self._check(other)
+            if self._feats is None and self._lazy.residual is None and not self._lazy.relu and other._F.dtype == torch.float32:
+                return self._lazy.with_residual(other._F)  # stays deferred: bn(x) + residual
             other = other._F
         if isinstance(other, torch.Tensor) and other.shape == self._F.shape and self._F.dtype == torch.float32:
             return Fn.AddFunction.apply(self._F, other)
         return self._F + other
 
     def __add__(self, other):
-        return self._like(self._add(other))
+        r = self._add(other)
+        if isinstance(r, _DeferredBN):
+            return SparseTensor._deferred(r, self.coordinate_map_key, self.coordinate_manager)
+        return self._like(r)
 
     def __iadd__(self, other):
-        self._F = self._add(other)
+        r = self._add(other)
+        if isinstance(r, _DeferredBN):
+            self._feats, self._lazy = None, r
+        else:
+            self._F = r
         return self
 
     def __sub__(self, other):
@@ -193,6 +229,26 @@ class SparseTensor:
 
 
 TensorField = SparseTensor
+
+
+class _DeferredBN:
+    """BatchNorm whose statistics are known and whose apply pass has not run yet."""
+
+    __slots__ = ("x", "weight", "bias", "mean", "invstd", "batch_stats", "residual", "relu")
+
+    def __init__(self, x, weight, bias, mean, invstd, batch_stats, residual=None, relu=False):
+        self.x, self.weight, self.bias, self.mean, self.invstd = x, weight, bias, mean, invstd
+        self.batch_stats, self.residual, self.relu = batch_stats, residual, relu
+
+    def with_residual(self, residual):
+        return _DeferredBN(self.x, self.weight, self.bias, self.mean, self.invstd, self.batch_stats, residual, self.relu)
+
+    def with_relu(self):
+        return _DeferredBN(self.x, self.weight, self.bias, self.mean, self.invstd, self.batch_stats, self.residual, True)
+
+    def materialize(self):
+        return Fn.BatchNormApplyFunction.apply(self.x, self.weight, self.bias, self.residual, self.mean, self.invstd,
+                                               self.batch_stats, self.relu)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -342,9 +398,14 @@ class MinkowskiBatchNorm(nn.Module):
                 momentum = 1.0 / float(bn.num_batches_tracked)
         rm = bn.running_mean if (bn.track_running_stats and (bn.training or not use_batch)) else None
         rv = bn.running_var if rm is not None else None
-        y = Fn.BatchNormFunction.apply(x.F, bn.weight, bn.bias, None if residual is None else residual.F, rm, rv,
-                                       momentum, bn.eps, use_batch, relu)
-        return x._like(y)
+        f = x.F
+        if use_batch:
+            mean, invstd = Fn.bn_batch_stats(f.detach(), rm, rv, momentum, bn.eps)
+        else:
+            mean = bn.running_mean.detach().float()
+            invstd = torch.rsqrt(bn.running_var.detach().float() + bn.eps)
+        lazy = _DeferredBN(f, bn.weight, bn.bias, mean, invstd, use_batch, None if residual is None else residual.F, relu)
+        return SparseTensor._deferred(lazy, x.coordinate_map_key, x.coordinate_manager)
 
 
 class MinkowskiInstanceNorm(nn.Module):
@@ -369,6 +430,8 @@ class MinkowskiReLU(nn.Module):
         self.inplace = inplace
 
     def forward(self, x: SparseTensor) -> SparseTensor:
+        if x._feats is None and not x._lazy.relu:  # fold into the deferred BatchNorm apply
+            return SparseTensor._deferred(x._lazy.with_relu(), x.coordinate_map_key, x.coordinate_manager)
         f = x.F
         inplace = self.inplace and f.is_contiguous() and f.dtype == torch.float32 and not (f.requires_grad and f.is_leaf) \
             and f._base is None
