@@ -142,6 +142,13 @@ int us3d_bn_bwd_reduce(const float *dy, int lddy, const float *x, int ldx, const
 int us3d_bn_bwd_apply(const float *dy, int lddy, const float *x, int ldx, const float *y, int ldy, int n, int c,
                       const float *mean, const float *invstd, const float *gamma, int relu, const double *red,
                       float *dx, int lddx, float *dres, int lddres, float *dgamma, float *dbeta, void *stream);
+/* one-call forms of the two pairs above (ws: 2*c doubles of scratch, zeroed inside); batch_terms = 0 treats the
+ * statistics as constants (inference): dx = g * invstd * gamma                                          */
+int us3d_bn_batch_stats(const float *x, int ldx, int n, int c, float eps, float momentum, float *mean, float *invstd,
+                        float *running_mean, float *running_var, double *ws, void *stream);
+int us3d_bn_backward(const float *dy, int lddy, const float *x, int ldx, const float *y, int ldy, int n, int c,
+                     const float *mean, const float *invstd, const float *gamma, int relu, int batch_terms, double *ws,
+                     float *dx, int lddx, float *dres, int lddres, float *dgamma, float *dbeta, void *stream);
 /* inference-mode BN is us3d_bn_apply with mean=running_mean, invstd=rsqrt(running_var+eps) (host computes) */
 
 /* y = relu(x) ; dx = dy * (y > 0) ; z = a + b ; concat along channels / its inverse */

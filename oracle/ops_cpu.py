@@ -82,3 +82,36 @@ def matcher_cost(pred_logits_q: torch.Tensor, pred_mask_sq: torch.Tensor, tgt_ma
     s = x.sigmoid()
     c_dice = 1 - (2 * torch.einsum("nc,mc->nm", s, t) + 1) / (s.sum(-1)[:, None] + t.sum(-1)[None, :] + 1)
     return cost_mask * c_mask + cost_class * c_class + cost_dice * c_dice
+
+
+# --------------------------------------------------------------------------------------------
+# registration under the reference's import names (tests / fixture scripts only)
+# --------------------------------------------------------------------------------------------
+def _fps_tensor(xyz: torch.Tensor, npoint: int) -> torch.Tensor:
+    """pointnet2._ext.furthest_point_sampling(points[B,N,3], nsamples) -> int32 [B, nsamples]."""
+    pts = xyz.detach().cpu().float().numpy()
+    return torch.from_numpy(np.stack([furthest_point_sampling(pts[b], npoint) for b in range(pts.shape[0])])).to(torch.int32)
+
+
+def _scatter_minmax(src, index, dim, reduce):
+    assert dim == 0
+    s = int(index.max()) + 1 if index.numel() else 0
+    idx = index.long()[:, None].expand_as(src)
+    out = torch.zeros((s, src.shape[1]), dtype=src.dtype).scatter_reduce(0, idx, src, reduce=reduce, include_self=False)
+    return out, None
+
+
+def as_module_tree():
+    """Module objects `torch_scatter`, `pointnet2`, `pointnet2._ext` exporting the CPU restatements."""
+    import types
+
+    ts = types.ModuleType("torch_scatter")
+    ts.scatter_mean = lambda src, index, dim=-1, out=None, dim_size=None: scatter_mean(src, index, dim)
+    ts.scatter_max = lambda src, index, dim=-1, out=None, dim_size=None: _scatter_minmax(src, index, dim, "amax")
+    ts.scatter_min = lambda src, index, dim=-1, out=None, dim_size=None: _scatter_minmax(src, index, dim, "amin")
+    pn = types.ModuleType("pointnet2")
+    pn.__path__ = []
+    ext = types.ModuleType("pointnet2._ext")
+    ext.furthest_point_sampling = _fps_tensor
+    pn._ext = ext
+    return {"torch_scatter": ts, "pointnet2": pn, "pointnet2._ext": ext}

@@ -95,5 +95,87 @@ def main():
               os.path.getsize(path), "bytes")
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--mask3d" not in sys.argv:
     main()
+
+
+# ------------------------------------------------------------------------------------------------- Mask3D step
+MASK3D_KW = dict(hidden_dim=128, num_queries=100, num_heads=8, dim_feedforward=1024, sample_sizes=[200, 800, 3200, 12800, 51200],
+                 shared_decoder=True, num_classes=3, num_decoders=3, dropout=0.0, pre_norm=False,
+                 positional_encoding_type="fourier", non_parametric_queries=True, train_on_segments=True,
+                 normalize_pos_enc=True, use_level_embed=False, scatter_type="mean", hlevels=[0, 1, 2, 3],
+                 use_np_features=False, voxel_size=0.02, max_sample_size=False, random_queries=False, gauss_scale=1.0,
+                 random_query_both=False, random_normal=False)  # conf/model/mask3d.yaml:5-34
+LOSS_WEIGHTS = {"loss_ce": 2.0, "loss_mask": 5.0, "loss_dice": 2.0, "loss_noise_robust": 0.0}  # trainer/trainer.py:68-79
+
+
+def mask3d_inputs(n=1500, batch=2, seed=404, n_seg=40, n_tgt=6):
+    coords = random_scene(n, seed, batch=batch, extent=24)
+    g = torch.Generator().manual_seed(seed)
+    feats = torch.randn(coords.shape[0], 3, generator=g)
+    raw = torch.from_numpy(coords[:, 1:]).float() * 0.02 + torch.rand(coords.shape[0], 3, generator=g) * 0.01
+    bidx = torch.from_numpy(coords[:, 0])
+    p2s, targets = [], []
+    for b in range(batch):
+        nb = int((bidx == b).sum())
+        seg = torch.randint(0, n_seg, (nb,), generator=g)
+        seg[:n_seg] = torch.arange(n_seg)
+        owner = torch.randint(0, n_tgt + 2, (n_seg,), generator=g)  # segments owned by target t (>= n_tgt: background)
+        owner[:n_tgt] = torch.arange(n_tgt)
+        seg_mask = torch.stack([owner == t for t in range(n_tgt)])
+        targets.append({"labels": torch.ones(n_tgt, dtype=torch.long), "segment_mask": seg_mask,
+                        "masks": seg_mask[:, seg], "point2segment": seg})
+        p2s.append(seg)
+    return coords, feats, raw, p2s, targets
+
+
+def run_mask3d_case(models_pkg, me, matcher, device="cpu", criterion_cls=None):
+    """Full self-training step (Mask3D forward, Hungarian matching, set criterion, backward)."""
+    coords, feats, raw, p2s, targets = mask3d_inputs()
+    backbone = models_pkg.res16unet.Res16UNet34C(3, 20, Cfg(), D=3, out_fpn=True)
+    net = models_pkg.mask3d.Mask3D(type("C", (), {"backbone": backbone})(), **MASK3D_KW)
+    net.load_state_dict(deterministic_state(net, 7))
+    net = net.to(device).train()
+    weight_dict = dict(LOSS_WEIGHTS)
+    for i in range(len(MASK3D_KW["hlevels"]) * MASK3D_KW["num_decoders"]):
+        weight_dict.update({f"{k}_{i}": v for k, v in LOSS_WEIGHTS.items()})
+    criterion_cls = criterion_cls or models_pkg.criterion.SetCriterion
+    crit = criterion_cls(num_classes=3, matcher=matcher, weight_dict=weight_dict, eos_coef=0.1, losses=["labels", "masks"],
+                         num_points=-1, oversample_ratio=3.0, importance_sample_ratio=0.75, class_weights=-1).to(device)
+    tg = [{k: v.to(device) for k, v in t.items()} for t in targets]
+    x = me.SparseTensor(feats.to(device), torch.from_numpy(coords).to(device))
+    out = net(x, point2segment=[p.to(device) for p in p2s], raw_coordinates=raw.to(device))
+    losses = crit(out, tg, mask_type="segment_mask")
+    total = sum(losses[k] * weight_dict[k] for k in losses if k in weight_dict)
+    total.backward()
+    res = {"pred_logits": out["pred_logits"].detach().double().cpu().numpy(), "sampled_coords": np.asarray(out["sampled_coords"], dtype=np.float64),
+           "total_loss": np.asarray(float(total))}
+    for b, m in enumerate(out["pred_masks"]):
+        res[f"pred_masks{b}"] = m.detach().double().cpu().numpy()
+    for k in ("loss_ce", "loss_mask", "loss_dice", "loss_ce_5", "loss_mask_11", "loss_dice_0"):
+        res["L:" + k] = np.asarray(float(losses[k]))
+    idx = matcher({k: v for k, v in out.items() if k != "aux_outputs"}, tg, "segment_mask")
+    for b, (i, j) in enumerate(idx):
+        res[f"match{b}"] = np.stack([i.numpy(), j.numpy()])
+    params = dict(net.named_parameters())
+    for k in ("mask_features_head.kernel", "class_embed_head.weight", "cross_attention.0.2.multihead_attn.in_proj_weight",
+              "query_projection.layers.0.weight", "backbone.block8.1.conv2.kernel", "backbone.conv0p1s1.kernel"):
+        gr = params[k].grad.detach().double().cpu().reshape(-1)
+        res["gnorm:" + k] = np.asarray(gr.norm().item())
+    return res
+
+
+def main_mask3d():
+    from oracle import me_cpu
+
+    ref = reference_models_on_oracle()
+    matcher = ref.matcher.HungarianMatcher(cost_class=2.0, cost_mask=5.0, cost_dice=2.0, cost_noise_robust=0.0, num_points=-1)
+    res = run_mask3d_case(ref, me_cpu, matcher)
+    path = os.path.join(HERE, "mask3d_step.npz")
+    np.savez_compressed(path, **res)
+    print("mask3d_step", "loss", float(res["total_loss"]), {k: float(v) for k, v in res.items() if k.startswith("L:")},
+          os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__" and "--mask3d" in sys.argv:
+    main_mask3d()

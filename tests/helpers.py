@@ -28,7 +28,8 @@ _ME_KEYS = ["MinkowskiEngine", "MinkowskiEngine.MinkowskiOps", "MinkowskiEngine.
 @contextlib.contextmanager
 def minkowski_as(modules: dict):
     """Temporarily make `import MinkowskiEngine` resolve to `modules` (name -> module object)."""
-    saved = {k: sys.modules.get(k) for k in _ME_KEYS}
+    keys = list(dict.fromkeys(_ME_KEYS + list(modules)))
+    saved = {k: sys.modules.get(k) for k in keys}
     sys.modules.update(modules)
     try:
         yield
@@ -41,9 +42,21 @@ def minkowski_as(modules: dict):
 
 
 def oracle_me_modules():
-    from oracle import me_cpu
+    """Every operator module the model files import, backed by the CPU oracle."""
+    from oracle import me_cpu, ops_cpu
 
-    return me_cpu.as_module_tree()
+    mods = me_cpu.as_module_tree()
+    mods.update(ops_cpu.as_module_tree())
+    return mods
+
+
+def _stub_modules():
+    """Import-only dependencies of the reference's model files that are absent here."""
+    import types
+
+    hydra = types.ModuleType("hydra")
+    hydra.main = lambda *a, **k: (lambda fn: fn)
+    return {"hydra": hydra}
 
 
 def load_package(pkg_dir: str, alias: str, me_modules: dict):
@@ -80,13 +93,20 @@ def reference_models_on_oracle():
     collections.Set = collections.abc.Set  # py3.12 skew, utils/utils.py:340
     if "models" in sys.modules and getattr(sys.modules["models"], "__file__", "").startswith(REFERENCE):
         return sys.modules["models"]
-    with minkowski_as(oracle_me_modules()):
+    import unscene3d_b200  # noqa: F401  puts the pure-Python detectron2 / custom_cuda_utils shims on sys.path
+
+    mods = oracle_me_modules()
+    mods.update(_stub_modules())
+    with minkowski_as(mods):
         sys.path.insert(0, REFERENCE)
         try:
-            for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
+            for k in [k for k in sys.modules if k == "models" or k.startswith("models.") or k.startswith("third_party")]:
                 del sys.modules[k]
             mod = importlib.import_module("models")
             importlib.import_module("models.res16unet")
+            importlib.import_module("models.mask3d")
+            importlib.import_module("models.matcher")
+            importlib.import_module("models.criterion")
         finally:
             sys.path.remove(REFERENCE)
     return mod

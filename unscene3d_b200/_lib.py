@@ -36,6 +36,8 @@ PROTOTYPES = {
     "us3d_bn_apply": [_p, _i, _i, _i, _p, _p, _p, _p, _p, _i, _i, _p, _i, _p],
     "us3d_bn_bwd_reduce": [_p, _i, _p, _i, _p, _i, _i, _i, _p, _p, _i, _p, _p],
     "us3d_bn_bwd_apply": [_p, _i, _p, _i, _p, _i, _i, _i, _p, _p, _p, _i, _p, _p, _i, _p, _i, _p, _p, _p],
+    "us3d_bn_batch_stats": [_p, _i, _i, _i, _f, _f, _p, _p, _p, _p, _p, _p],
+    "us3d_bn_backward": [_p, _i, _p, _i, _p, _i, _i, _i, _p, _p, _p, _i, _i, _p, _p, _i, _p, _i, _p, _p, _p],
     "us3d_relu": [_p, _p, _ll, _p],
     "us3d_relu_bwd": [_p, _p, _p, _ll, _p],
     "us3d_add": [_p, _p, _p, _ll, _p],

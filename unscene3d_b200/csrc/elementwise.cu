@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(256)
 k_bn_bwd_apply(const float *__restrict__ dy, int lddy, const float *__restrict__ x, int ldx, const float *__restrict__ y,
                int ldy, int n, int c, const float *__restrict__ mean, const float *__restrict__ invstd,
                const float *__restrict__ gamma, int relu, const double *__restrict__ red, float *__restrict__ dx, int lddx,
-               float *__restrict__ dres, int lddres, float *dgamma, float *dbeta) {
+               float *__restrict__ dres, int lddres, float *dgamma, float *dbeta, int batch_terms) {
     long long total = (long long)n * c;
     const float inv_n = 1.f / (float)n;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -132,7 +132,8 @@ k_bn_bwd_apply(const float *__restrict__ dy, int lddy, const float *__restrict__
         if (dres) dres[(size_t)r * lddres + ch] = g;
         float is = invstd[ch];
         float xh = (x[(size_t)r * ldx + ch] - mean[ch]) * is;
-        float s0 = (float)red[ch], s1 = (float)red[c + ch];
+        // batch_terms = 0: the statistics were constants (inference), dx = g * invstd * gamma
+        float s0 = batch_terms ? (float)red[ch] : 0.f, s1 = batch_terms ? (float)red[c + ch] : 0.f;
         dx[(size_t)r * lddx + ch] = (g - s0 * inv_n - xh * s1 * inv_n) * is * gamma[ch];
     }
     if (blockIdx.x == 0)
@@ -290,7 +291,36 @@ int us3d_bn_bwd_apply(const float *dy, int lddy, const float *x, int ldx, const 
     cudaStream_t st = (cudaStream_t)stream_;
     US3D_CHECK_ARG(n > 0 && c > 0, "bn_bwd_apply: bad shape");
     k_bn_bwd_apply<<<flat_grid((long long)n * c), 256, 0, st>>>(dy, lddy, x, ldx, y, ldy, n, c, mean, invstd, gamma, relu, red, dx,
-                                                              lddx, dres, lddres, dgamma, dbeta);
+                                                              lddx, dres, lddres, dgamma, dbeta, 1);
+    US3D_LAUNCH_CHECK();
+    return 0;
+}
+
+/* one-call forms (fewer host round trips): workspace ws = 2*c doubles, zeroed here */
+int us3d_bn_batch_stats(const float *x, int ldx, int n, int c, float eps, float momentum, float *mean, float *invstd,
+                        float *running_mean, float *running_var, double *ws, void *stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    US3D_CHECK_ARG(n > 0 && c > 0 && ldx >= c, "bn_batch_stats: bad shape");
+    US3D_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * c, st));
+    dim3 grid(ceil_div(n, kRedRows), ceil_div(c, 32)), block(32, 8);
+    k_bn_stats<<<grid, block, 0, st>>>(x, ldx, n, c, ws, ws + c);
+    US3D_LAUNCH_CHECK();
+    k_bn_finalize<<<ceil_div(c, 128), 128, 0, st>>>(ws, ws + c, n, c, eps, momentum, mean, invstd, running_mean, running_var);
+    US3D_LAUNCH_CHECK();
+    return 0;
+}
+
+int us3d_bn_backward(const float *dy, int lddy, const float *x, int ldx, const float *y, int ldy, int n, int c,
+                     const float *mean, const float *invstd, const float *gamma, int relu, int batch_terms, double *ws,
+                     float *dx, int lddx, float *dres, int lddres, float *dgamma, float *dbeta, void *stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    US3D_CHECK_ARG(n > 0 && c > 0, "bn_backward: bad shape");
+    US3D_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * c, st));
+    dim3 grid(ceil_div(n, kRedRows), ceil_div(c, 32)), block(32, 8);
+    k_bn_bwd_reduce<<<grid, block, 0, st>>>(dy, lddy, x, ldx, y, ldy, n, c, mean, invstd, relu, ws);
+    US3D_LAUNCH_CHECK();
+    k_bn_bwd_apply<<<flat_grid((long long)n * c), 256, 0, st>>>(dy, lddy, x, ldx, y, ldy, n, c, mean, invstd, gamma, relu, ws, dx,
+                                                              lddx, dres, lddres, dgamma, dbeta, batch_terms);
     US3D_LAUNCH_CHECK();
     return 0;
 }

@@ -23,7 +23,13 @@ from .._lib import check, lib
 TILE_ROWS = 128
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream() -> int:
+    """cudaStream_t of torch's current stream (the raw getter is ~50x cheaper than torch.cuda.current_stream())."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 

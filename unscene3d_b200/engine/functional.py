@@ -116,14 +116,24 @@ def bf16_planes(x: torch.Tensor, need_lo: bool):
     return hi, lo
 
 
+def _tc_ok(cin, cout):  # == us3d_spconv_tc_supported, without the FFI round trip
+    return cin >= 16 and cin % 16 == 0 and cout >= 16 and cout % 16 == 0 and cout <= 256
+
+
 def spconv_gather(x, table: NeighbourTable, w3, cin, cout, transpose_w, flip_k, bias=None, out=None, accumulate=False):
     x = _rows(x)
     y = out if out is not None else torch.empty((table.n_rows, cout), dtype=torch.float32, device=x.device)
     st = _stream()
     mode = _precision["mode"]
-    if (mode != 0 and lib.us3d_spconv_tc_supported(cin, cout) and x.data_ptr() % 16 == 0 and _ld(x) % 4 == 0):
+    if (mode != 0 and _tc_ok(cin, cout) and x.data_ptr() % 16 == 0 and _ld(x) % 4 == 0):
         wpack = pack_weights(w3, transpose_w, flip_k, mode)
         kind = "dgrad" if transpose_w else "fwd"
+        if _tc_kernel["fwd"] == "mt" and _timer is None:  # production path, no per-launch timing
+            hi, lo = bf16_planes(x, mode == 3)
+            check(lib.us3d_spconv_gather_mt(hi.data_ptr(), _ptr(lo), x.shape[0], table.nbr.data_ptr(), table.n_rows, table.kvol,
+                                            wpack.data_ptr(), cin, cout, mode, _ptr(bias), 0, y.data_ptr(), _ld(y),
+                                            int(accumulate), _ptr(table.mask), st))
+            return y
         if _tc_kernel["fwd"] in ("tma", "cp", "mt"):
             hi, lo = bf16_planes(x, mode == 3)
             fn = {"tma": lib.us3d_spconv_gather_tma, "cp": lib.us3d_spconv_gather_cp, "mt": lib.us3d_spconv_gather_mt}[_tc_kernel["fwd"]]
@@ -203,20 +213,30 @@ class SparseConvFunction(torch.autograd.Function):
         return dx, dw, db, None, None
 
 
+_bn_ws = {}
+
+
+def _bn_workspace(dev, c):
+    """Per-device scratch for the BatchNorm column reductions (2*c doubles).  Kernels on one stream are ordered,
+    so one buffer per device is enough for the single-stream execution the module surface uses."""
+    ws = _bn_ws.get(dev.index)
+    if ws is None or ws.numel() < 2 * c:
+        ws = torch.empty(max(2 * c, 2048), dtype=torch.float64, device=dev)
+        _bn_ws[dev.index] = ws
+    return ws
+
+
 def bn_batch_stats(x, running_mean, running_var, momentum, eps):
     """Batch statistics of all rows (no autograd: the apply function's backward carries the dependence on them).
     Returns (mean, invstd) fp32 [c]; updates the running statistics in place like nn.BatchNorm1d."""
     x = _rows(x)
     n, c = x.shape
     dev = x.device
-    st = _stream()
-    acc = torch.zeros((2, c), dtype=torch.float64, device=dev)
-    mean = torch.empty(c, dtype=torch.float32, device=dev)
-    invstd = torch.empty(c, dtype=torch.float32, device=dev)
-    check(lib.us3d_bn_stats(x.data_ptr(), _ld(x), n, c, acc[0].data_ptr(), acc[1].data_ptr(), st))
-    check(lib.us3d_bn_finalize(acc[0].data_ptr(), acc[1].data_ptr(), n, c, float(eps), float(momentum if momentum is not None else 0.0),
-                               mean.data_ptr(), invstd.data_ptr(), _ptr(running_mean), _ptr(running_var), st))
-    return mean, invstd
+    stats = torch.empty((2, c), dtype=torch.float32, device=dev)
+    check(lib.us3d_bn_batch_stats(x.data_ptr(), _ld(x), n, c, float(eps), float(momentum if momentum is not None else 0.0),
+                                  stats[0].data_ptr(), stats[1].data_ptr(), _ptr(running_mean), _ptr(running_var),
+                                  _bn_workspace(dev, c).data_ptr(), _stream()))
+    return stats[0], stats[1]
 
 
 class BatchNormApplyFunction(torch.autograd.Function):
@@ -246,24 +266,15 @@ class BatchNormApplyFunction(torch.autograd.Function):
         dy = _rows(dy)
         n, c = x.shape
         dev = x.device
-        st = _stream()
-        red = torch.zeros((2, c), dtype=torch.float64, device=dev)
         yy = y if y is not None else x
-        check(lib.us3d_bn_bwd_reduce(dy.data_ptr(), _ld(dy), x.data_ptr(), _ld(x), yy.data_ptr(), _ld(yy), n, c, mean.data_ptr(),
-                                     invstd.data_ptr(), int(ctx.relu), red.data_ptr(), st))
-        if not ctx.training:
-            # inference statistics are constants: dx = g * invstd * gamma (zero the two batch terms)
-            dgamma_src = red.clone()
-            red.zero_()
         dx = torch.empty((n, c), dtype=torch.float32, device=dev)
         dres = torch.empty((n, c), dtype=torch.float32, device=dev) if ctx.has_res else None
-        dgamma = torch.empty(c, dtype=torch.float32, device=dev)
-        dbeta = torch.empty(c, dtype=torch.float32, device=dev)
-        check(lib.us3d_bn_bwd_apply(dy.data_ptr(), _ld(dy), x.data_ptr(), _ld(x), yy.data_ptr(), _ld(yy), n, c, mean.data_ptr(),
-                                    invstd.data_ptr(), g.data_ptr(), int(ctx.relu), red.data_ptr(), dx.data_ptr(), _ld(dx),
-                                    _ptr(dres), 0 if dres is None else _ld(dres), dgamma.data_ptr(), dbeta.data_ptr(), st))
-        if not ctx.training:
-            dgamma, dbeta = dgamma_src[1].float(), dgamma_src[0].float()
+        dgb = torch.empty((2, c), dtype=torch.float32, device=dev)
+        dgamma, dbeta = dgb[0], dgb[1]
+        check(lib.us3d_bn_backward(dy.data_ptr(), _ld(dy), x.data_ptr(), _ld(x), yy.data_ptr(), _ld(yy), n, c, mean.data_ptr(),
+                                   invstd.data_ptr(), g.data_ptr(), int(ctx.relu), int(ctx.training), _bn_workspace(dev, c).data_ptr(),
+                                   dx.data_ptr(), _ld(dx), _ptr(dres), 0 if dres is None else _ld(dres), dgamma.data_ptr(),
+                                   dbeta.data_ptr(), _stream()))
         if not ctx.affine:
             dgamma = dbeta = None
         return dx, dgamma, dbeta, dres, None, None, None, None

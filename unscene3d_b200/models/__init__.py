@@ -3,7 +3,10 @@
 `load_model(name)` mirrors the reference registry (models/__init__.py:18-31) used by the pseudo-mask
 path (pseudo_masks/unscene3d_pseudo_main.py:59).
 """
-from . import res16unet
+from . import criterion, mask3d, matcher, res16unet
+from .criterion import SetCriterion
+from .mask3d import Mask3D
+from .matcher import HungarianMatcher
 from .res16unet import (Res16UNet14, Res16UNet14A, Res16UNet18B, Res16UNet18D, Res16UNet34, Res16UNet34A,
                         Res16UNet34C, Res16UNet34CMultiRes, Res16UNet34D, Custom30M)
 

@@ -1,0 +1,114 @@
+"""Set criterion of the self-training step — mirror of the reference's models/criterion.py
+(dice_loss :22-43, sigmoid_ce_loss :51-70, SetCriterion :90-292) with the same loss keys and weights
+semantics: matcher -> weighted cross-entropy over (num_classes + no-object) -> per-scene sigmoid-CE + dice on the
+matched masks (optional DropLoss IoU gating) -> the same again for every auxiliary decoder output.
+
+The tri-plane noise-robust term (models/noise_robust_loss.py) is only evaluated when its weight is non-zero
+(models/criterion.py:170); the self-training configuration keeps it at 0 (conf/matcher/hungarian_matcher.yaml:6),
+and this implementation refuses a non-zero weight instead of silently ignoring it.
+"""
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+from torch import nn
+
+
+def _world_size():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def dice_loss(inputs, targets, num_masks, weights):
+    p = inputs.sigmoid().flatten(1)
+    numerator = 2 * (p * targets).sum(-1)
+    denominator = p.sum(-1) + targets.sum(-1)
+    return (weights * (1 - (numerator + 1) / (denominator + 1))).sum() / num_masks
+
+
+def sigmoid_ce_loss(inputs, targets, num_masks, weights):
+    loss = weights.view(-1, 1) * F.binary_cross_entropy_with_logits(inputs, targets, reduction="none")
+    return loss.mean(1).sum() / num_masks
+
+
+class SetCriterion(nn.Module):
+    def __init__(self, num_classes, matcher, weight_dict, eos_coef, losses, num_points, oversample_ratio,
+                 importance_sample_ratio, class_weights, directions="xyz", use_droploss=False, droploss_iou_thresh=0.1):
+        super().__init__()
+        self.num_classes = num_classes - 1
+        self.class_weights = class_weights
+        self.matcher, self.weight_dict, self.eos_coef, self.losses = matcher, weight_dict, eos_coef, losses
+        self.use_droploss, self.droploss_iou_thresh = use_droploss, droploss_iou_thresh
+        empty_weight = torch.ones(self.num_classes + 1)
+        empty_weight[-1] = self.eos_coef
+        if self.class_weights != -1:
+            assert len(self.class_weights) == self.num_classes, "CLASS WEIGHTS DO NOT MATCH"
+            empty_weight[:-1] = torch.tensor(self.class_weights)
+        self.register_buffer("empty_weight", empty_weight)
+        self.num_points, self.oversample_ratio, self.importance_sample_ratio = num_points, oversample_ratio, importance_sample_ratio
+        self.directions = directions
+
+    def loss_labels(self, outputs, targets, indices, num_masks, mask_type, coords=None):
+        logits = outputs["pred_logits"].float()
+        idx = self._get_src_permutation_idx(indices)
+        matched = torch.cat([t["labels"][J] for t, (_, J) in zip(targets, indices)])
+        target_classes = torch.full(logits.shape[:2], self.num_classes, dtype=torch.int64, device=logits.device)
+        target_classes[idx] = matched
+        return {"loss_ce": F.cross_entropy(logits.transpose(1, 2), target_classes, self.empty_weight, ignore_index=253)}
+
+    def loss_masks(self, outputs, targets, indices, num_masks, mask_type="masks", coords=None):
+        if self.weight_dict.get("loss_noise_robust", 0) != 0:
+            raise NotImplementedError("the tri-plane noise-robust loss (cost_noise_robust != 0) is not built")
+        ce, dice, robust = [], [], []
+        for b, (map_id, target_id) in enumerate(indices):
+            pred = outputs["pred_masks"][b][:, map_id].T
+            tgt = targets[b][mask_type][target_id]
+            robust.append(torch.as_tensor(0.0, dtype=torch.float32, device=pred.device))
+            if self.num_points != -1:
+                pidx = torch.randperm(tgt.shape[1], device=tgt.device)[:int(self.num_points * tgt.shape[1])]
+            else:
+                pidx = torch.arange(tgt.shape[1], device=tgt.device)
+            n_scene = tgt.shape[0]
+            pred, tgt = pred[:, pidx], tgt[:, pidx]
+            if self.use_droploss:
+                fg = pred > 0.0
+                iou = (fg * tgt).sum(dim=1) / (fg + tgt).sum(dim=1)
+                weights = (iou >= self.droploss_iou_thresh).float()
+            else:
+                weights = torch.ones(pred.shape[0], device=pred.device)
+            tgt = tgt.float()
+            ce.append(sigmoid_ce_loss(pred, tgt, n_scene, weights))
+            dice.append(dice_loss(pred, tgt, n_scene, weights))
+        return {"loss_mask": torch.sum(torch.stack(ce)), "loss_dice": torch.sum(torch.stack(dice)),
+                "loss_noise_robust": torch.sum(torch.stack(robust))}
+
+    @staticmethod
+    def _get_src_permutation_idx(indices):
+        batch_idx = torch.cat([torch.full_like(src, i) for i, (src, _) in enumerate(indices)])
+        return batch_idx, torch.cat([src for (src, _) in indices])
+
+    @staticmethod
+    def _get_tgt_permutation_idx(indices):
+        batch_idx = torch.cat([torch.full_like(tgt, i) for i, (_, tgt) in enumerate(indices)])
+        return batch_idx, torch.cat([tgt for (_, tgt) in indices])
+
+    def get_loss(self, loss, outputs, targets, indices, num_masks, mask_type, coords=None):
+        table = {"labels": self.loss_labels, "masks": self.loss_masks}
+        assert loss in table, f"do you really want to compute {loss} loss?"
+        return table[loss](outputs, targets, indices, num_masks, mask_type, coords)
+
+    def forward(self, outputs, targets, mask_type, coords=None):
+        main = {k: v for k, v in outputs.items() if k != "aux_outputs"}
+        indices = self.matcher(main, targets, mask_type)
+        num_masks = torch.as_tensor([sum(len(t["labels"]) for t in targets)], dtype=torch.float,
+                                    device=next(iter(outputs.values())).device)
+        if dist.is_available() and dist.is_initialized():
+            dist.all_reduce(num_masks)
+        num_masks = torch.clamp(num_masks / _world_size(), min=1).item()
+        losses = {}
+        for loss in self.losses:
+            losses.update(self.get_loss(loss, outputs, targets, indices, num_masks, mask_type, coords))
+        for i, aux in enumerate(outputs.get("aux_outputs", [])):
+            indices = self.matcher(aux, targets, mask_type)
+            for loss in self.losses:
+                losses.update({f"{k}_{i}": v for k, v in
+                               self.get_loss(loss, aux, targets, indices, num_masks, mask_type, coords).items()})
+        return losses
