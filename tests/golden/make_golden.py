@@ -158,6 +158,8 @@ def run_mask3d_case(models_pkg, me, matcher, device="cpu", criterion_cls=None):
     for b, (i, j) in enumerate(idx):
         res[f"match{b}"] = np.stack([i.numpy(), j.numpy()])
     params = dict(net.named_parameters())
+    missing = [k for k, v in params.items() if v.grad is None and not k.startswith("backbone.final")]
+    assert not missing, f"parameters without gradient: {missing[:8]} ({len(missing)} of {len(params)})"
     for k in ("mask_features_head.kernel", "class_embed_head.weight", "cross_attention.0.2.multihead_attn.in_proj_weight",
               "query_projection.layers.0.weight", "backbone.block8.1.conv2.kernel", "backbone.conv0p1s1.kernel"):
         gr = params[k].grad.detach().double().cpu().reshape(-1)

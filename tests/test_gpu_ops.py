@@ -337,3 +337,32 @@ def test_matcher_cost(eng):
 def test_cpu_tensor_is_rejected_loudly(eng):
     with pytest.raises(RuntimeError):
         eng.SparseTensor(torch.zeros(3, 1), torch.zeros(3, 4, dtype=torch.int32))
+
+
+def test_deferred_batchnorm_fusion_and_no_grad_access(eng, ora):
+    """conv -> bn -> (+= residual) -> relu is ONE fused apply pass; touching metadata or the features inside
+    torch.no_grad() (as models/mask3d.py:205-209 does with aux[-1]) must not cut the autograd graph."""
+    from unscene3d_b200 import _lib
+
+    c = random_scene(2000, 41, batch=2, extent=20)
+    x, y, fx, fy = _pair(eng, ora, c, 16)
+    bx, by = eng.MinkowskiBatchNorm(16, momentum=0.1).cuda(), ora.MinkowskiBatchNorm(16, momentum=0.1)
+    rx, ry = eng.MinkowskiReLU(inplace=True), ora.MinkowskiReLU(inplace=True)
+    ox = bx(x)
+    before = _lib.launch_count()
+    ox += x
+    ox = rx(ox)
+    assert _lib.launch_count() == before, "residual add and ReLU must stay deferred"
+    with torch.no_grad():
+        assert ox.device.type == "cuda" and ox.shape == (c.shape[0], 16)
+        _ = ox.F  # materialises here, under no_grad
+    assert ox.F.requires_grad and ox.F.grad_fn is not None
+    oy = by(y)
+    oy += y
+    oy = ry(oy)
+    assert rel_err(ox.F, oy.F) < 1e-5
+    g = torch.randn_like(oy.F)
+    ox.F.backward(g.cuda())
+    oy.F.backward(g)
+    assert rel_err(fx.grad, fy.grad) < 1e-4
+    assert rel_err(bx.bn.weight.grad, by.bn.weight.grad) < 1e-4

@@ -116,17 +116,18 @@ class SparseTensor:
 
     coordinates = C
 
+    # metadata never forces the deferred apply pass
     @property
     def device(self):
-        return self._F.device
+        return self._lazy.x.device if self._feats is None else self._feats.device
 
     @property
     def dtype(self):
-        return self._F.dtype
+        return torch.float32 if self._feats is None else self._feats.dtype
 
     @property
     def shape(self):
-        return self._F.shape
+        return self._lazy.x.shape if self._feats is None else self._feats.shape
 
     @property
     def D(self):
@@ -141,10 +142,10 @@ class SparseTensor:
         return self._F.requires_grad
 
     def size(self, *a):
-        return self._F.size(*a)
+        return self.shape if not a else self.shape[a[0]]
 
     def __len__(self):
-        return self._F.shape[0]
+        return self.shape[0]
 
     def _like(self, feats):
         return SparseTensor(feats, coordinate_map_key=self.coordinate_map_key, coordinate_manager=self.coordinate_manager)
@@ -234,21 +235,25 @@ TensorField = SparseTensor
 class _DeferredBN:
     """BatchNorm whose statistics are known and whose apply pass has not run yet."""
 
-    __slots__ = ("x", "weight", "bias", "mean", "invstd", "batch_stats", "residual", "relu")
+    __slots__ = ("x", "weight", "bias", "mean", "invstd", "batch_stats", "residual", "relu", "grad_mode")
 
-    def __init__(self, x, weight, bias, mean, invstd, batch_stats, residual=None, relu=False):
+    def __init__(self, x, weight, bias, mean, invstd, batch_stats, residual=None, relu=False, grad_mode=None):
         self.x, self.weight, self.bias, self.mean, self.invstd = x, weight, bias, mean, invstd
         self.batch_stats, self.residual, self.relu = batch_stats, residual, relu
+        # the apply pass belongs to the autograd context in which BatchNorm was CALLED, not to the one in which the
+        # features happen to be touched first (e.g. Mask3D reads aux[-1] inside torch.no_grad(), models/mask3d.py:205)
+        self.grad_mode = torch.is_grad_enabled() if grad_mode is None else grad_mode
 
     def with_residual(self, residual):
-        return _DeferredBN(self.x, self.weight, self.bias, self.mean, self.invstd, self.batch_stats, residual, self.relu)
+        return _DeferredBN(self.x, self.weight, self.bias, self.mean, self.invstd, self.batch_stats, residual, self.relu, self.grad_mode)
 
     def with_relu(self):
-        return _DeferredBN(self.x, self.weight, self.bias, self.mean, self.invstd, self.batch_stats, self.residual, True)
+        return _DeferredBN(self.x, self.weight, self.bias, self.mean, self.invstd, self.batch_stats, self.residual, True, self.grad_mode)
 
     def materialize(self):
-        return Fn.BatchNormApplyFunction.apply(self.x, self.weight, self.bias, self.residual, self.mean, self.invstd,
-                                               self.batch_stats, self.relu)
+        with torch.set_grad_enabled(self.grad_mode):
+            return Fn.BatchNormApplyFunction.apply(self.x, self.weight, self.bias, self.residual, self.mean, self.invstd,
+                                                   self.batch_stats, self.relu)
 
 
 # ------------------------------------------------------------------------------------------------
