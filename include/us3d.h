@@ -184,6 +184,19 @@ int us3d_segment_mean_bwd(const float *dout, const int64_t *index, const float *
 int us3d_matcher_cost(const float *logits, int s, int q, const float *tgt, int t, const float *prob, int ncls,
                       const int64_t *labels, float w_class, float w_mask, float w_dice, float *cost, void *stream);
 
+/* ---------------------------------------------------------------- pseudo-mask NCut step (A19, A20)
+ * get_affinity_matrix / second_smallest_eigenvector of pseudo_masks/unscene3d_pseudo_main.py:89-146.
+ *   gram:      A[s,s] = normalised-row Gram matrix of f[s,d] (fp32) + stats {min over non-zero, max, any > 0} (ordered-uint
+ *              encoded, uint32[3]) that normalize_mat (:82-86) needs; inv_norm: float[s] scratch.
+ *   threshold: averages the two normalised matrices (Ab may be NULL), thresholds at tau into a bit matrix
+ *              bits[s, ceil(s/32)] (W = eps 11^T + (1-eps) B), clears painted rows/columns (uint8[s], may be NULL) and
+ *              writes the degrees of the UNPAINTED graph (double[s]) — the reference computes D before painting.
+ *   matvec:    y = W x in fp64 (xsum = sum(x), 1 double on the device).                                      */
+int us3d_ncut_gram(const float *f, int s, int d, float *inv_norm, float *A, uint32_t *stats, void *stream);
+int us3d_ncut_threshold(const float *Aa, const float *Ab, int s, const uint32_t *stats_a, const uint32_t *stats_b, float tau,
+                        double eps, const uint8_t *painted, uint32_t *bits, double *degree, void *stream);
+int us3d_ncut_matvec(const uint32_t *bits, int s, double eps, const double *x, const double *xsum, double *y, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
