@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define US3D_ABI_VERSION 5
+#define US3D_ABI_VERSION 6
 #define US3D_MAX_KVOL 27
 
 int us3d_abi_version(void);
@@ -151,6 +151,42 @@ int us3d_bn_backward(const float *dy, int lddy, const float *x, int ldx, const f
                      float *dx, int lddx, float *dres, int lddres, float *dgamma, float *dbeta, void *stream);
 /* inference-mode BN is us3d_bn_apply with mean=running_mean, invstd=rsqrt(running_var+eps) (host computes) */
 
+/* Fused forms used by the module surface (csrc/fused_ops.cu).  `ws` = us3d_bn_workspace_bytes(c) bytes that are ZERO on
+ * entry and are left zero on exit (the block that finishes last cleans up), so no memset separates two layers.
+ *   bn_stats_fused      one launch: column sums, then mean / invstd / running statistics (nn.BatchNorm1d momentum
+ *                       rule, unbiased running variance) and num_batches_tracked += 1 (int64 scalar, may be NULL)
+ *   bn_apply_planes     us3d_bn_apply that also writes the result as bf16 planes hi (and lo = y - hi unless NULL),
+ *                       row-major [n, c] — what the tcgen05 convolution of the next layer gathers from (c % 8 == 0)
+ *   bn_backward_planes  us3d_bn_backward that also writes dx as bf16 planes (read by the input-gradient and
+ *                       weight-gradient kernels of the preceding convolution)
+ * Replace MinkowskiBatchNorm + MinkowskiReLU + `out += residual` (models/modules/common.py:20-22,
+ * models/modules/resnet_block.py:48-64). */
+int us3d_bn_workspace_bytes(int c);
+int us3d_bn_stats_fused(const float *x, int ldx, int n, int c, float eps, float momentum, float *mean, float *invstd,
+                        float *running_mean, float *running_var, long long *num_batches_tracked, double *ws, void *stream);
+int us3d_bn_apply_planes(const float *x, int ldx, int n, int c, const float *mean, const float *invstd, const float *gamma,
+                         const float *beta, const float *residual, int ldr, int relu, float *y, int ldy, void *hi, void *lo,
+                         void *stream);
+int us3d_bn_backward_planes(const float *dy, int lddy, const float *x, int ldx, const float *y, int ldy, int n, int c,
+                            const float *mean, const float *invstd, const float *gamma, int relu, int batch_terms, double *ws,
+                            float *dx, int lddx, float *dres, int lddres, float *dgamma, float *dbeta, void *dx_hi, void *dx_lo,
+                            void *stream);
+
+/* Forward (out_fwd) and input-gradient (out_dgrad: W[k]^T, offsets reversed when flip_dgrad) weight images of one
+ * convolution in one call; either pointer may be NULL.  Sizes: us3d_spconv_packed_bytes(kvol, cin, cout, passes) and
+ * us3d_spconv_packed_bytes(kvol, cout, cin, passes). */
+int us3d_spconv_pack_pair(const float *w, int kvol, int cin, int cout, int flip_dgrad, int passes, void *out_fwd,
+                          void *out_dgrad, void *stream);
+
+/* The stem convolution (conv0p1s1: 3 input channels, models/res16unet.py:219-221): its K = 3 contraction does not fill
+ * a tensor-core tile, so it runs as warp = rows, lane = output channel with the weights in shared memory.
+ * cin <= 4 forward; weight gradient for cin == 3, kvol in {1, 8, 27} (dw zero-initialised by the caller). */
+int us3d_stem_conv_supported(int cin, int cout, int kvol);
+int us3d_stem_conv_fwd(const float *x, int ldx, const int32_t *nbr, int n_rows, int kvol, const float *w, int cin, int cout,
+                       const float *bias, float *y, int ldy, void *stream);
+int us3d_stem_conv_wgrad(const float *x, int ldx, const int32_t *nbr, int n_rows, int kvol, const float *dy, int lddy, float *dw,
+                         int cin, int cout, void *stream);
+
 /* y = relu(x) ; dx = dy * (y > 0) ; z = a + b ; concat along channels / its inverse */
 int us3d_relu(const float *x, float *y, long long numel, void *stream);
 int us3d_relu_bwd(const float *dy, const float *y, float *dx, long long numel, void *stream);
@@ -174,6 +210,11 @@ int us3d_furthest_point_sampling(const float *xyz, int b, int n, int m, float *t
 /* torch_scatter.scatter_mean(src[n,c], index[n], dim=0) (models/mask3d.py:223): out[s,c] zeroed by
  * caller, count[s] float zeroed by caller; fwd accumulates then divides; bwd gathers dy/count.     */
 int us3d_segment_mean_fwd(const float *src, const int64_t *index, int n, int c, int s, float *out, float *count,
+                          void *stream);
+/* Same mean with the sum taken in fp64 (`acc` [s, c] doubles and `count` zero-filled by the caller) and rounded to fp32 once:
+ * the pseudo-mask path thresholds affinities computed from these means (pseudo_masks/unscene3d_pseudo_main.py:350-402, 89-119),
+ * so they must not depend on the order of the atomics. */
+int us3d_segment_mean_f64(const float *src, const int64_t *index, int n, int c, int s, double *acc, float *out, float *count,
                           void *stream);
 int us3d_segment_mean_bwd(const float *dout, const int64_t *index, const float *count, int n, int c, float *dsrc,
                           void *stream);

@@ -129,13 +129,59 @@ def mask3d_inputs(n=1500, batch=2, seed=404, n_seg=40, n_tgt=6):
     return coords, feats, raw, p2s, targets
 
 
-def run_mask3d_case(models_pkg, me, matcher, device="cpu", criterion_cls=None):
+def _steer_attention_masks(net, me, record=None, override=None, mismatches=None):
+    """Wraps Mask3D.mask_module.  The decoder thresholds pooled mask logits into boolean attention masks
+    (models/mask3d.py:437-446): a DISCRETE decision inside an otherwise continuous computation, and with randomly
+    initialised weights many logits sit near zero.  `record` collects the masks of every round (golden generation);
+    `override` replays recorded masks into the run under test after counting how many entries the run itself decided
+    differently (`mismatches`), so that the continuous outputs of both runs stay comparable to round-off."""
+    inner = net.mask_module
+    state = {"k": 0}
+
+    def mask_module(*args, **kwargs):
+        out = inner(*args, **kwargs)
+        if not (isinstance(out, tuple) and len(out) == 3):
+            return out
+        cls, masks, attn = out
+        bits = attn.F
+        k = state["k"]
+        state["k"] += 1
+        if record is not None:
+            record.append(bits.detach().cpu().numpy().astype(bool))
+        if override is not None:
+            want = torch.from_numpy(override[k]).to(bits.device)
+            assert want.shape == bits.shape, (k, want.shape, bits.shape)
+            if mismatches is not None:
+                mismatches.append((int((want != bits).sum()), bits.numel()))
+            attn = me.SparseTensor(features=want, coordinate_manager=attn.coordinate_manager, coordinate_map_key=attn.coordinate_map_key)
+        return cls, masks, attn
+
+    net.mask_module = mask_module
+
+
+def pack_attention(record):
+    out = {"attn_rounds": np.asarray(len(record))}
+    for k, b in enumerate(record):
+        out[f"attn{k}"] = np.packbits(b.reshape(-1))
+        out[f"attn{k}_shape"] = np.asarray(b.shape)
+    return out
+
+
+def unpack_attention(gold):
+    return [np.unpackbits(gold[f"attn{k}"])[: int(np.prod(gold[f"attn{k}_shape"]))].reshape(tuple(gold[f"attn{k}_shape"])).astype(bool)
+            for k in range(int(gold["attn_rounds"]))]
+
+
+def run_mask3d_case(models_pkg, me, matcher, device="cpu", criterion_cls=None, attn_record=None, attn_override=None,
+                    attn_mismatches=None):
     """Full self-training step (Mask3D forward, Hungarian matching, set criterion, backward)."""
     coords, feats, raw, p2s, targets = mask3d_inputs()
     backbone = models_pkg.res16unet.Res16UNet34C(3, 20, Cfg(), D=3, out_fpn=True)
     net = models_pkg.mask3d.Mask3D(type("C", (), {"backbone": backbone})(), **MASK3D_KW)
     net.load_state_dict(deterministic_state(net, 7))
     net = net.to(device).train()
+    if attn_record is not None or attn_override is not None:
+        _steer_attention_masks(net, me, attn_record, attn_override, attn_mismatches)
     weight_dict = dict(LOSS_WEIGHTS)
     for i in range(len(MASK3D_KW["hlevels"]) * MASK3D_KW["num_decoders"]):
         weight_dict.update({f"{k}_{i}": v for k, v in LOSS_WEIGHTS.items()})
@@ -172,7 +218,9 @@ def main_mask3d():
 
     ref = reference_models_on_oracle()
     matcher = ref.matcher.HungarianMatcher(cost_class=2.0, cost_mask=5.0, cost_dice=2.0, cost_noise_robust=0.0, num_points=-1)
-    res = run_mask3d_case(ref, me_cpu, matcher)
+    record = []
+    res = run_mask3d_case(ref, me_cpu, matcher, attn_record=record)
+    res.update(pack_attention(record))
     path = os.path.join(HERE, "mask3d_step.npz")
     np.savez_compressed(path, **res)
     print("mask3d_step", "loss", float(res["total_loss"]), {k: float(v) for k, v in res.items() if k.startswith("L:")},

@@ -132,7 +132,7 @@ def _sync_params(mx, my):
 @pytest.mark.parametrize("cin,cout,ks,stride,bias", [
     (3, 32, 3, 1, False), (32, 32, 2, 2, False), (32, 64, 3, 1, False), (64, 64, 3, 1, False), (128, 96, 3, 1, False),
     (96, 96, 3, 1, False), (256, 256, 3, 1, False), (384, 256, 1, 1, False), (96, 20, 1, 1, True), (5, 7, 3, 1, True),
-    (16, 24, 3, 2, False),
+    (16, 24, 3, 2, False), (384, 256, 3, 1, False), (3, 64, 2, 2, False), (3, 96, 1, 1, True),
 ])
 @pytest.mark.parametrize("mode", [0, 3, 1])
 def test_convolution_forward_backward(eng, ora, cin, cout, ks, stride, bias, mode):
@@ -236,6 +236,56 @@ def test_batchnorm_train_forward_backward(eng, n, c, relu, res):
     if res:
         assert rel_err(rg.grad, rr.grad) < 1e-6
     assert rel_err(rm, bn.running_mean) < 1e-5 and rel_err(rv, bn.running_var) < 1e-5
+
+
+def test_fused_batchnorm_planes_counters_and_workspace(eng):
+    """The fused BatchNorm passes: bf16 planes written by the apply / backward pass are bit-identical to the stand-alone
+    split kernel's and are what the neighbouring convolutions consume (no split launch between conv-bn-relu-conv);
+    num_batches_tracked is incremented on the device; the shared workspace is zero again after every pass."""
+    from unscene3d_b200 import _lib
+    from unscene3d_b200.engine import functional as Fn
+
+    torch.manual_seed(3)
+    c = random_scene(4000, 5, batch=2, extent=28)
+    feats = torch.randn(c.shape[0], 32)
+    net = torch.nn.Sequential(eng.MinkowskiConvolution(32, 64, kernel_size=3, dimension=3), eng.MinkowskiBatchNorm(64),
+                              eng.MinkowskiReLU(), eng.MinkowskiConvolution(64, 96, kernel_size=3, dimension=3),
+                              eng.MinkowskiBatchNorm(96), eng.MinkowskiReLU()).cuda().train()
+    x = eng.SparseTensor(feats.cuda().requires_grad_(), torch.from_numpy(c).cuda())
+    calls = {"n": 0}
+    real = _lib.lib.us3d_split_bf16
+
+    class Spy:
+        def __getattr__(self, name):
+            fn = getattr(_lib.lib, name)
+            if name != "us3d_split_bf16":
+                return fn
+
+            def counted(*a):
+                calls["n"] += 1
+                return real(*a)
+            return counted
+
+    Fn.lib = Spy()
+    try:
+        h = net[2](net[1](net[0](x)))
+        mid = h.F
+        planes = getattr(mid, "_us3d_planes", None)
+        assert planes is not None and planes[2] == mid._version, "BatchNorm apply did not leave bf16 planes on its output"
+        hi = torch.empty_like(planes[0]); lo = torch.empty_like(planes[1])
+        _lib.check(real(mid.data_ptr(), mid.shape[1], mid.shape[0], mid.shape[1], hi.data_ptr(), lo.data_ptr(), Fn._stream()))
+        assert torch.equal(hi.view(torch.int16), planes[0].view(torch.int16)) and torch.equal(lo.view(torch.int16), planes[1].view(torch.int16))
+        before = calls["n"]
+        out = net[5](net[4](net[3](h))).F
+        assert calls["n"] == before, "the second convolution re-split an activation that already had planes"
+        out.backward(torch.randn_like(out))
+        # backward: dy of both convolutions comes from a BatchNorm backward pass that wrote its planes
+        assert calls["n"] == before, f"{calls['n'] - before} split launches in backward"
+    finally:
+        Fn.lib = _lib.lib
+    assert int(net[1].bn.num_batches_tracked) == 1 and int(net[4].bn.num_batches_tracked) == 1
+    ws = Fn._bn_workspace(mid.device, 96)
+    assert float(ws.abs().max()) == 0.0, "BatchNorm workspace not returned to zero"
 
 
 def test_batchnorm_eval_mode(eng):

@@ -13,7 +13,7 @@ import pytest
 import torch
 from scipy.optimize import linear_sum_assignment
 
-from golden.make_golden import run_mask3d_case
+from golden.make_golden import run_mask3d_case, unpack_attention
 from helpers import our_models_on_oracle
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mask3d_step.npz")
@@ -34,13 +34,32 @@ class OracleMatcher(torch.nn.Module):
         return out
 
 
-def check(res, gold, rtol, grad_rtol):
+def assignment_gap(gold, b, match):
+    """Cost of `match` minus the optimum, both under the GOLDEN cost matrix of scene b (reference logits / masks)."""
+    from golden.make_golden import mask3d_inputs
+    from oracle import ops_cpu
+
+    tgt = mask3d_inputs()[4][b]
+    c = ops_cpu.matcher_cost(torch.from_numpy(gold["pred_logits"][b]).float(), torch.from_numpy(gold[f"pred_masks{b}"]).float(),
+                             tgt["segment_mask"], tgt["labels"], 2.0, 5.0, 2.0)
+    c = np.asarray(c, dtype=np.float64)
+    i, j = linear_sum_assignment(c)
+    assert sorted(match[1].tolist()) == list(range(c.shape[1])) and len(set(match[0].tolist())) == c.shape[1], "not an assignment"
+    return float(c[match[0], match[1]].sum() - c[i, j].sum()), float(np.abs(c[i, j]).sum())
+
+
+def check(res, gold, rtol, grad_rtol, exact_match=True):
     assert np.array_equal(res["sampled_coords"], gold["sampled_coords"]), "FPS picked different voxels"
     for k in gold:
-        if k.startswith("match"):
-            assert np.array_equal(res[k], gold[k]), f"{k}: Hungarian assignment differs"
+        if k.startswith("match") and not np.array_equal(res[k], gold[k]):
+            # The randomly initialised decoder gives near-identical queries, so the optimum is nearly degenerate: an
+            # assignment computed from features that differ by 1e-4 may pick another of the tied queries.  It must
+            # still be optimal under the reference's own cost matrix to within the feature tolerance.
+            assert not exact_match, f"{k}: Hungarian assignment differs"
+            gap, scale = assignment_gap(gold, int(k[5:]), res[k])
+            assert gap <= rtol * scale, f"{k}: assignment is {gap:.3e} above the optimum of the golden cost ({scale:.3e})"
     for k, g in gold.items():
-        if k.startswith("match") or k == "sampled_coords":
+        if k.startswith("match") or k.startswith("attn") or k == "sampled_coords":
             continue
         tol = grad_rtol if k.startswith("gnorm:") else rtol
         scale = max(float(np.abs(g).max()), 1e-12)
@@ -51,8 +70,11 @@ def check(res, gold, rtol, grad_rtol):
 def test_our_mask3d_and_criterion_on_oracle_match_reference_golden():
     from oracle import me_cpu
 
-    res = run_mask3d_case(our_models_on_oracle(), me_cpu, OracleMatcher())
-    check(res, dict(np.load(GOLD)), rtol=2e-5, grad_rtol=1e-3)
+    gold = dict(np.load(GOLD))
+    mism = []
+    res = run_mask3d_case(our_models_on_oracle(), me_cpu, OracleMatcher(), attn_override=unpack_attention(gold), attn_mismatches=mism)
+    assert len(mism) == int(gold["attn_rounds"]) and all(m == 0 for m, _ in mism), "attention masks differ from the reference's"
+    check(res, gold, rtol=2e-5, grad_rtol=1e-3)
 
 
 @pytest.mark.gpu
@@ -61,8 +83,37 @@ def test_cuda_mask3d_step_matches_golden():
     from unscene3d_b200 import engine, models
 
     matcher = models.HungarianMatcher(cost_class=2.0, cost_mask=5.0, cost_dice=2.0, cost_noise_robust=0.0, num_points=-1)
-    res = run_mask3d_case(models, engine, matcher, device="cuda")
-    check(res, dict(np.load(GOLD)), rtol=1e-3, grad_rtol=5e-2)
+    # The decoder thresholds pooled mask logits into boolean attention masks 12 times (models/mask3d.py:437-446); with the
+    # randomly initialised weights of the fixture a few logits sit within the 1e-4 feature tolerance of zero, and one
+    # flipped entry changes a query by 1e-2 and cascades.  The run therefore decides its own masks, they are compared
+    # with the reference's (<= 1 % of the entries of a round may differ: the borderline ones), and the reference's
+    # decisions are replayed so that everything continuous is comparable at 1e-3.
+    gold = dict(np.load(GOLD))
+    mism = []
+    res = run_mask3d_case(models, engine, matcher, device="cuda", attn_override=unpack_attention(gold), attn_mismatches=mism)
+    assert len(mism) == int(gold["attn_rounds"])
+    for k, (bad, total) in enumerate(mism):
+        assert bad <= max(2, 1e-2 * total), f"attention mask of round {k}: {bad} of {total} entries differ"
+    check(res, gold, rtol=1e-3, grad_rtol=5e-2, exact_match=False)
+
+
+@pytest.mark.gpu
+def test_cuda_matcher_on_golden_logits_reproduces_reference_assignment():
+    """The matcher alone, fed the reference's own logits / masks: same assignment (or one tied with it to 1e-6)."""
+    import unscene3d_b200  # noqa: F401
+    from golden.make_golden import mask3d_inputs
+    from unscene3d_b200 import models
+
+    gold = dict(np.load(GOLD))
+    targets = [{k: v.cuda() for k, v in t.items()} for t in mask3d_inputs()[4]]
+    out = {"pred_logits": torch.from_numpy(gold["pred_logits"]).float().cuda(),
+           "pred_masks": [torch.from_numpy(gold[f"pred_masks{b}"]).float().cuda() for b in range(len(targets))]}
+    matcher = models.HungarianMatcher(cost_class=2.0, cost_mask=5.0, cost_dice=2.0, cost_noise_robust=0.0, num_points=-1)
+    for b, (i, j) in enumerate(matcher(out, targets, "segment_mask")):
+        got = np.stack([i.numpy(), j.numpy()])
+        if not np.array_equal(got, gold[f"match{b}"]):
+            gap, scale = assignment_gap(gold, b, got)
+            assert gap <= 1e-6 * scale, f"scene {b}: assignment {gap:.3e} above the optimum ({scale:.3e})"
 
 
 @pytest.mark.gpu

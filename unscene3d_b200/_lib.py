@@ -38,6 +38,14 @@ PROTOTYPES = {
     "us3d_bn_bwd_apply": [_p, _i, _p, _i, _p, _i, _i, _i, _p, _p, _p, _i, _p, _p, _i, _p, _i, _p, _p, _p],
     "us3d_bn_batch_stats": [_p, _i, _i, _i, _f, _f, _p, _p, _p, _p, _p, _p],
     "us3d_bn_backward": [_p, _i, _p, _i, _p, _i, _i, _i, _p, _p, _p, _i, _i, _p, _p, _i, _p, _i, _p, _p, _p],
+    "us3d_bn_workspace_bytes": [_i],
+    "us3d_bn_stats_fused": [_p, _i, _i, _i, _f, _f, _p, _p, _p, _p, _p, _p, _p],
+    "us3d_bn_apply_planes": [_p, _i, _i, _i, _p, _p, _p, _p, _p, _i, _i, _p, _i, _p, _p, _p],
+    "us3d_bn_backward_planes": [_p, _i, _p, _i, _p, _i, _i, _i, _p, _p, _p, _i, _i, _p, _p, _i, _p, _i, _p, _p, _p, _p, _p],
+    "us3d_spconv_pack_pair": [_p, _i, _i, _i, _i, _i, _p, _p, _p],
+    "us3d_stem_conv_supported": [_i, _i, _i],
+    "us3d_stem_conv_fwd": [_p, _i, _p, _i, _i, _p, _i, _i, _p, _p, _i, _p],
+    "us3d_stem_conv_wgrad": [_p, _i, _p, _i, _i, _p, _i, _p, _i, _i, _p],
     "us3d_relu": [_p, _p, _ll, _p],
     "us3d_relu_bwd": [_p, _p, _p, _ll, _p],
     "us3d_add": [_p, _p, _p, _ll, _p],
@@ -47,6 +55,7 @@ PROTOTYPES = {
     "us3d_furthest_point_sampling": [_p, _i, _i, _i, _p, _p, _p],
     "us3d_segment_mean_fwd": [_p, _p, _i, _i, _i, _p, _p, _p],
     "us3d_segment_mean_bwd": [_p, _p, _p, _i, _i, _p, _p],
+    "us3d_segment_mean_f64": [_p, _p, _i, _i, _i, _p, _p, _p, _p],
     "us3d_ncut_gram": [_p, _i, _i, _p, _p, _p, _p],
     "us3d_ncut_threshold": [_p, _p, _i, _p, _p, _f, ctypes.c_double, _p, _p, _p, _p],
     "us3d_ncut_matvec": [_p, _i, ctypes.c_double, _p, _p, _p, _p],

@@ -52,6 +52,25 @@ inline int num_sms() {
     return sms;
 }
 
+// ---- per-launch profiling (bench.py roofline leg) ------------------------------------------------
+// When enabled, the convolution entry points bracket their kernel launch with CUDA events recorded on the launch
+// stream from inside the library — the start event sits a few microseconds of host time before the kernel, so a
+// host-bound step does not leak its launch gaps into the kernel's duration.  kind: 0 forward / input gradient
+// (as tagged by the caller), 1 weight gradient.
+void prof_begin(cudaStream_t st, int kind, int n_in, int n_rows, int kvol, int cin, int cout);
+void prof_end(cudaStream_t st);
+extern bool g_profile;
+struct ProfScope {
+    cudaStream_t st;
+    bool on;
+    ProfScope(cudaStream_t s, int kind, int n_in, int n_rows, int kvol, int cin, int cout) : st(s), on(g_profile) {
+        if (on) prof_begin(st, kind, n_in, n_rows, kvol, cin, cout);
+    }
+    ~ProfScope() {
+        if (on) prof_end(st);
+    }
+};
+
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // ---- voxel keys -------------------------------------------------------------------------------

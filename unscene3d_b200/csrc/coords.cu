@@ -13,6 +13,9 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 
 namespace us3d {
@@ -25,6 +28,34 @@ void set_error(const char *fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+// ---- per-launch profiling -----------------------------------------------------------------------
+bool g_profile = false;
+namespace {
+struct ProfRec {
+    cudaEvent_t s, e;
+    int meta[7];
+};
+std::vector<ProfRec> g_prof_recs;
+std::mutex g_prof_mu;
+int g_prof_tag = 0;
+}  // namespace
+
+void prof_begin(cudaStream_t st, int kind, int n_in, int n_rows, int kvol, int cin, int cout) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    ProfRec r;
+    cudaEventCreate(&r.s);
+    cudaEventCreate(&r.e);
+    r.meta[0] = kind == 0 ? g_prof_tag : kind;
+    r.meta[1] = n_in; r.meta[2] = n_rows; r.meta[3] = kvol; r.meta[4] = cin; r.meta[5] = cout; r.meta[6] = 0;
+    cudaEventRecord(r.s, st);
+    g_prof_recs.push_back(r);
+}
+
+void prof_end(cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (!g_prof_recs.empty()) cudaEventRecord(g_prof_recs.back().e, st);
 }
 
 constexpr int kScanThreads = 512;
@@ -213,6 +244,40 @@ extern "C" {
 int us3d_abi_version(void) { return US3D_ABI_VERSION; }
 const char *us3d_last_error(void) { return g_err; }
 long long us3d_launch_count(void) { return g_launches.load(); }
+
+/* Profiling hooks (debug surface, used by bench.py): start collecting, tag the next gather launches (0 forward,
+ * 2 input gradient), stop = synchronise and return up to `cap` records as meta[7 * i .. ] = (kind, n_in, n_rows, kvol,
+ * cin, cout, 0) and ms[i]; kind 1 = weight gradient. */
+void us3d_debug_profile_start(void) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto &r : g_prof_recs) {
+        cudaEventDestroy(r.s);
+        cudaEventDestroy(r.e);
+    }
+    g_prof_recs.clear();
+    g_profile = true;
+}
+void us3d_debug_profile_tag(int kind) { g_prof_tag = kind; }
+int us3d_debug_profile_stop(int *meta, float *ms, int cap) {
+    g_profile = false;
+    cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    int n = 0;
+    for (auto &r : g_prof_recs) {
+        if (n < cap) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, r.s, r.e) != cudaSuccess) t = -1.f;
+            for (int i = 0; i < 7; ++i) meta[7 * n + i] = r.meta[i];
+            ms[n] = t;
+            ++n;
+        }
+        cudaEventDestroy(r.s);
+        cudaEventDestroy(r.e);
+    }
+    g_prof_recs.clear();
+    cudaGetLastError();
+    return n;
+}
 void us3d_reset_launch_count(void) { g_launches.store(0); }
 
 int us3d_hash_capacity(int n) {

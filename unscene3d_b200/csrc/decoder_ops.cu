@@ -99,6 +99,29 @@ __global__ void __launch_bounds__(256) k_segment_div(float *out, const float *__
     }
 }
 
+// Exactly rounded variant for the pseudo-mask path: the thresholded affinity (> tau) is decided on these means, so the
+// sum is taken in fp64 (order-independent to 2^-53) and rounded to fp32 once — the result does not depend on the
+// order in which the atomics land.
+__global__ void __launch_bounds__(256) k_segment_sum_f64(const float *__restrict__ src, const int64_t *__restrict__ index, int n, int c,
+                                                         double *acc, float *count) {
+    long long total = (long long)n * c;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        int r = (int)(e / c), ch = (int)(e % c);
+        int s = (int)index[r];
+        atomicAdd(&acc[(size_t)s * c + ch], (double)src[e]);
+        if (ch == 0) atomicAdd(&count[s], 1.f);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_segment_div_f64(const double *__restrict__ acc, const float *__restrict__ count, int s, int c,
+                                                         float *__restrict__ out) {
+    long long total = (long long)s * c;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        float cnt = count[e / c];
+        out[e] = (float)(cnt > 1.f ? acc[e] / (double)cnt : acc[e]);
+    }
+}
+
 __global__ void __launch_bounds__(256) k_segment_mean_bwd(const float *__restrict__ dout, const int64_t *__restrict__ index,
                                                           const float *__restrict__ count, int n, int c, float *__restrict__ dsrc) {
     long long total = (long long)n * c;
@@ -177,6 +200,19 @@ int us3d_segment_mean_fwd(const float *src, const int64_t *index, int n, int c, 
     k_segment_sum<<<flat_grid2((long long)n * c), 256, 0, (cudaStream_t)stream_>>>(src, index, n, c, out, count);
     US3D_LAUNCH_CHECK();
     k_segment_div<<<flat_grid2((long long)s * c), 256, 0, (cudaStream_t)stream_>>>(out, count, s, c);
+    US3D_LAUNCH_CHECK();
+    return 0;
+}
+
+int us3d_segment_mean_f64(const float *src, const int64_t *index, int n, int c, int s, double *acc, float *out, float *count,
+                          void *stream_) {
+    US3D_CHECK_ARG(n >= 0 && c > 0 && s >= 0, "segment_mean_f64: bad shape");
+    if (s == 0) return 0;
+    if (n > 0) {
+        k_segment_sum_f64<<<flat_grid2((long long)n * c), 256, 0, (cudaStream_t)stream_>>>(src, index, n, c, acc, count);
+        US3D_LAUNCH_CHECK();
+    }
+    k_segment_div_f64<<<flat_grid2((long long)s * c), 256, 0, (cudaStream_t)stream_>>>(acc, count, s, c, out);
     US3D_LAUNCH_CHECK();
     return 0;
 }

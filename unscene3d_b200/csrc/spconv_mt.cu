@@ -364,6 +364,7 @@ static void launch(int lag, int grid, size_t smem, cudaStream_t st, const Params
 using namespace us3d;
 
 static long long *g_prof = nullptr;
+
 static int g_tune_a_slots = 0, g_tune_lag = 0, g_tune_T = 0;
 
 extern "C" {
@@ -441,12 +442,19 @@ int us3d_spconv_gather_mt(const void *x_hi, const void *x_lo, int n_in, const in
         attr_done = true;
     }
     const int grid = p.n_units < num_sms() ? p.n_units : num_sms();
-    int lag = p.a_slots - 1;
-    if (g_tune_lag >= 1 && g_tune_lag < lag) lag = g_tune_lag;
-    if (passes == 3)
-        mt::launch<3>(lag, grid, smem, st, p);
-    else
-        mt::launch<1>(lag, grid, smem, st, p);
+    // Groups a producer warp keeps in flight before it waits for the oldest.  Measured on B200 (200k voxels, 128 -> 96):
+    // three-term mode 0.521 ms at lag 3, 0.472 ms at lag 1 — with 32 KB slots a deep lag leaves the MMA warp no landed
+    // slot to run ahead on; single-pass mode is best at lag 2.
+    int lag = passes == 3 ? 1 : 2;
+    if (lag > p.a_slots - 1) lag = p.a_slots - 1;
+    if (g_tune_lag >= 1 && g_tune_lag <= p.a_slots - 1) lag = g_tune_lag;
+    {
+        ProfScope prof(st, 0, n_in, n_rows, kvol, cin, cout);
+        if (passes == 3)
+            mt::launch<3>(lag, grid, smem, st, p);
+        else
+            mt::launch<1>(lag, grid, smem, st, p);
+    }
     US3D_LAUNCH_CHECK();
     return 0;
 }

@@ -248,6 +248,7 @@ int us3d_spconv_gather(const float *x, int ldx, const int32_t *nbr, int n_rows, 
     US3D_CHECK_ARG(cin > 0 && cout > 0 && ldx >= cin && ldy >= cout, "spconv_gather: bad channel counts / leading dims");
     if (n_rows == 0) return 0;
     const int mask_tile_rows = 128;  // tile masks are always built for 128-row tiles
+    ProfScope prof(st, 0, n_rows, n_rows, kvol, cin, cout);
     if (cout % 64 == 0 || cout > 96) {
         dim3 grid(ceil_div(n_rows, TM), ceil_div(cout, 64));
         k_gather_conv<64><<<grid, NT, 0, st>>>(x, ldx, nbr, n_rows, kvol, w, cin, cout, transpose_w, flip_k, bias, out_rows,
@@ -276,6 +277,7 @@ int us3d_spconv_wgrad(const float *x, int ldx, const int32_t *nbr, int n_rows, i
     int rows_per_split = ceil_div(ceil_div(n_rows, splits), TK) * TK;
     splits = ceil_div(n_rows, rows_per_split);
     dim3 grid(kvol, ci_tiles * co_tiles, splits);
+    ProfScope prof(st, 1, n_rows, n_rows, kvol, cin, cout);
     k_wgrad<<<grid, NT, 0, st>>>(x, ldx, nbr, n_rows, kvol, dy, ldy, out_rows, dw, cin, cout, rows_per_split, co_tiles);
     US3D_LAUNCH_CHECK();
     return 0;

@@ -14,7 +14,9 @@
 // which a one-offset-per-CTA layout re-reads 27 times, is read ceil(27 / KG) times.
 //
 //   warps 0-3  producers: 16-byte cp.async into the swizzled slabs (zero-fill for absent neighbours / rows past
-//              the split), cp.async.wait_group (lag) -> fence.proxy.async -> mbarrier arrive
+//              the split); one A ring slot = one plane of one (row block, offset) = 16 KB.  Completion is
+//              signalled by cp.async.mbarrier.arrive.noinc (the producers never wait for their own copies); the
+//              MMA warp crosses the generic -> async proxy with fence.proxy.async after its wait
 //   warp 4     MMA issuer (warp-uniform control flow, one elected lane issues)
 //   warps 0-3  epilogue at the end: tcgen05.ld -> red.global.add into dW
 #include "common.cuh"
@@ -30,7 +32,7 @@ constexpr int SLAB = R * 128;     // one 64-channel block of one plane
 constexpr int PROD_WARPS = 4;
 constexpr int MMA_WARP = PROD_WARPS;
 constexpr int THREADS = (PROD_WARPS + 1) * 32;
-constexpr int MAX_A = 6, MAX_B = 3, MAX_KG = 4, MAX_LAG = 3;
+constexpr int MAX_A = 12, MAX_B = 3, MAX_KG = 4;
 
 struct Params {
     const __nv_bfloat16 *x_hi, *x_lo;    // [n_in, cin]
@@ -43,14 +45,14 @@ struct Params {
     int a_slots, b_slots, acc_cols;
 };
 
-template <int PASSES, int LAG>
+template <int PASSES>
 __global__ void __launch_bounds__(THREADS, 1) k_wgrad(Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t a_full[MAX_A], a_empty[MAX_A], b_full[MAX_B], b_empty[MAX_B], acc_full;
     __shared__ uint32_t tmem_base_s;
     constexpr int NPL = PASSES == 3 ? 2 : 1;
     constexpr int A_PLANE = 2 * SLAB;  // 128 input channels
-    constexpr int A_SLOT = NPL * A_PLANE;
+    constexpr int A_SLOT = A_PLANE;  // one plane per ring slot
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int b_plane = (p.npad / 64) * SLAB;
@@ -77,11 +79,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad(Params p) {
 
     if (tid == 0) {
         for (int s = 0; s < p.a_slots; ++s) {
-            mbar_init(smem_u32(&a_full[s]), PROD_WARPS);
+            mbar_init(smem_u32(&a_full[s]), PROD_WARPS * 32);
             mbar_init(smem_u32(&a_empty[s]), 1);
         }
         for (int s = 0; s < p.b_slots; ++s) {
-            mbar_init(smem_u32(&b_full[s]), PROD_WARPS);
+            mbar_init(smem_u32(&b_full[s]), PROD_WARPS * 32);
             mbar_init(smem_u32(&b_empty[s]), 1);
         }
         mbar_init(smem_u32(&acc_full), 1);
@@ -97,30 +99,32 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad(Params p) {
     if (warp < PROD_WARPS) {
         // ------------------------------------------------------------------ producers
         const int GB = p.cout / 8;  // 16-byte chunks per dY row
-        uint32_t pending[MAX_LAG];  // mbarriers of the committed, not yet signalled groups (oldest first)
-        int n_pending = 0;
         int as = 0, bs = 0;
         uint32_t apar = 0, bpar = 0;
-        auto commit_and_signal = [&](uint32_t bar) {
-            cp_async_commit();
-            if (n_pending == LAG) {
-                cp_async_wait<LAG>();
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(pending[0]);
+        // this thread's 8 (row, 16-byte chunk) cells of an A slot: row = 8 i + tid / 16, chunk g = tid % 16
+        const int arow0 = tid >> 4, ag = tid & 15;
+        const bool acol_ok = ci0 + ag * 8 < p.cin;
+        uint32_t adst[8];
 #pragma unroll
-                for (int i = 0; i + 1 < MAX_LAG; ++i) pending[i] = pending[i + 1];
-                --n_pending;
-            }
-#pragma unroll
-            for (int i = 0; i < MAX_LAG; ++i)
-                if (i == n_pending) pending[i] = bar;
-            ++n_pending;
-        };
+        for (int i = 0; i < 8; ++i) {
+            const int row = arow0 + 8 * i;
+            adst[i] = (uint32_t)(ag >> 3) * SLAB + (uint32_t)row * 128u + (uint32_t)(((ag & 7) ^ (row & 7)) << 4);
+        }
         for (int r0 = r_begin; r0 < r_end; r0 += R) {
             const uint32_t act = active(r0);
             if (!act) continue;
             touched |= act;
+            // neighbour rows of every offset of the group: requested first, consumed after the dY copies are issued
+            int src[MAX_KG][8];
+#pragma unroll
+            for (int kq = 0; kq < MAX_KG; ++kq) {
+                if (kq >= nk || !((act >> (k0 + kq)) & 1u)) continue;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int j = r0 + arow0 + 8 * i;
+                    src[kq][i] = j < r_end ? __ldg(p.nbr + (size_t)(k0 + kq) * p.n_rows + j) : -1;
+                }
+            }
             // ---- B item: 64 rows of dY
             mbar_wait(smem_u32(&b_empty[bs]), bpar ^ 1, 0);
             {
@@ -134,44 +138,36 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad(Params p) {
                     cp_async16(dst, p.dy_hi + off, ok ? 16u : 0u);
                     if (PASSES == 3) cp_async16(dst + b_plane, p.dy_lo + off, ok ? 16u : 0u);
                 }
-                commit_and_signal(smem_u32(&b_full[bs]));
+                cp_async_arrive_noinc(smem_u32(&b_full[bs]));
                 if (++bs == p.b_slots) {
                     bs = 0;
                     bpar ^= 1u;
                 }
             }
-            // ---- A items: gathered X rows for every active offset of the group
-            for (int kq = 0; kq < nk; ++kq) {
-                const int k = k0 + kq;
-                if (!((act >> k) & 1u)) continue;
-                mbar_wait(smem_u32(&a_empty[as]), apar ^ 1, 1);
-                const uint32_t slot = a_base + (uint32_t)as * A_SLOT;
+            // ---- A items: gathered X rows for every active offset of the group, one plane per slot
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int it = i * (PROD_WARPS * 32) + tid;
-                    const int row = it >> 4, g = it & 15;
-                    const int j = r0 + row;
-                    int src = -1;
-                    if (j < r_end) src = __ldg(p.nbr + (size_t)k * p.n_rows + j);
-                    const int c = ci0 + g * 8;
-                    const bool ok = src >= 0 && c < p.cin;
-                    const uint32_t dst = slot + (uint32_t)(g >> 3) * SLAB + (uint32_t)row * 128u + (uint32_t)(((g & 7) ^ (row & 7)) << 4);
-                    const size_t off = ok ? (size_t)src * p.cin + c : 0;
-                    cp_async16(dst, p.x_hi + off, ok ? 16u : 0u);
-                    if (PASSES == 3) cp_async16(dst + A_PLANE, p.x_lo + off, ok ? 16u : 0u);
-                }
-                commit_and_signal(smem_u32(&a_full[as]));
-                if (++as == p.a_slots) {
-                    as = 0;
-                    apar ^= 1u;
+            for (int kq = 0; kq < MAX_KG; ++kq) {
+                if (kq >= nk || !((act >> (k0 + kq)) & 1u)) continue;
+#pragma unroll
+                for (int pl = 0; pl < NPL; ++pl) {
+                    const __nv_bfloat16 *plane = pl == 0 ? p.x_hi : p.x_lo;
+                    mbar_wait(smem_u32(&a_empty[as]), apar ^ 1, 1);
+                    const uint32_t slot = a_base + (uint32_t)as * A_SLOT;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const bool ok = src[kq][i] >= 0 && acol_ok;
+                        const size_t off = ok ? (size_t)src[kq][i] * p.cin + ci0 + ag * 8 : 0;
+                        cp_async16(slot + adst[i], plane + off, ok ? 16u : 0u);
+                    }
+                    cp_async_arrive_noinc(smem_u32(&a_full[as]));
+                    if (++as == p.a_slots) {
+                        as = 0;
+                        apar ^= 1u;
+                    }
                 }
             }
         }
-        cp_async_wait<0>();
-        fence_proxy_async();
-        __syncwarp();
-        for (int i = 0; i < n_pending; ++i)
-            if (lane == 0) mbar_arrive(pending[i]);
+        cp_async_wait_all();
 
         // ------------------------------------------------------------------ epilogue: lanes = ci, columns = co
         if (touched) {
@@ -202,36 +198,44 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad(Params p) {
         for (int r0 = r_begin; r0 < r_end; r0 += R) {
             const uint32_t act = active(r0);
             if (!act) continue;
-            mbar_wait(smem_u32(&b_full[bs]), bpar, 3);
+mbar_wait(smem_u32(&b_full[bs]), bpar, 3);
             const uint64_t db_hi = b_desc0 + (uint64_t)((uint32_t)(bs * b_slot_bytes) >> 4);
             const uint64_t db_lo = db_hi + (uint64_t)((uint32_t)b_plane >> 4);
             for (int kq = 0; kq < nk; ++kq) {
                 const int k = k0 + kq;
                 if (!((act >> k) & 1u)) continue;
-                mbar_wait(smem_u32(&a_full[as]), apar, 4);
-                tc_fence_after();
-                const uint64_t da_hi = a_desc0 + (uint64_t)((uint32_t)(as * A_SLOT) >> 4);
-                const uint64_t da_lo = da_hi + (uint64_t)(A_PLANE >> 4);
                 const uint32_t acc = tmem_base + (uint32_t)(kq * p.npad);
                 const uint32_t first = (touched >> k) & 1u;
-                if (elect_one()) {
 #pragma unroll
-                    for (int kk = 0; kk < R / 16; ++kk) {
-                        const uint64_t adv = (uint64_t)(kk * (2048 >> 4));  // two 8-row groups
-                        umma(acc, da_hi + adv, db_hi + adv, idesc, first | (kk != 0));
-                        if (PASSES == 3) {
-                            umma(acc, da_lo + adv, db_hi + adv, idesc, 1);
-                            umma(acc, da_hi + adv, db_lo + adv, idesc, 1);
+                for (int pl = 0; pl < NPL; ++pl) {
+                    mbar_wait(smem_u32(&a_full[as]), apar, 4);
+                    fence_proxy_async();  // cp.async writes of the producers (generic proxy) -> tcgen05 reads (async proxy)
+                    tc_fence_after();
+                    const uint64_t da = a_desc0 + (uint64_t)((uint32_t)(as * A_SLOT) >> 4);
+                    if (elect_one()) {
+                        if (pl == 0) {
+#pragma unroll
+                            for (int kk = 0; kk < R / 16; ++kk) {
+                                const uint64_t adv = (uint64_t)(kk * (2048 >> 4));  // two 8-row groups
+                                umma(acc, da + adv, db_hi + adv, idesc, first | (kk != 0));
+                                if (PASSES == 3) umma(acc, da + adv, db_lo + adv, idesc, 1);
+                            }
+                        } else {
+#pragma unroll
+                            for (int kk = 0; kk < R / 16; ++kk) {
+                                const uint64_t adv = (uint64_t)(kk * (2048 >> 4));
+                                umma(acc, da + adv, db_hi + adv, idesc, 1);
+                            }
                         }
+                        umma_commit(smem_u32(&a_empty[as]));
                     }
-                    umma_commit(smem_u32(&a_empty[as]));
+                    __syncwarp();
+                    if (++as == p.a_slots) {
+                        as = 0;
+                        apar ^= 1u;
+                    }
                 }
-                __syncwarp();
                 touched |= 1u << k;
-                if (++as == p.a_slots) {
-                    as = 0;
-                    apar ^= 1u;
-                }
             }
             if (elect_one()) umma_commit(smem_u32(&b_empty[bs]));
             __syncwarp();
@@ -247,16 +251,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad(Params p) {
     tc_fence_before();
     __syncthreads();
     if (warp == MMA_WARP) tmem_dealloc(tmem_base, (uint32_t)p.acc_cols);
-}
-
-template <int PASSES>
-static void launch(int lag, int grid, size_t smem, cudaStream_t st, const Params &p) {
-    if (lag >= 3)
-        k_wgrad<PASSES, 3><<<grid, THREADS, smem, st>>>(p);
-    else if (lag == 2)
-        k_wgrad<PASSES, 2><<<grid, THREADS, smem, st>>>(p);
-    else
-        k_wgrad<PASSES, 1><<<grid, THREADS, smem, st>>>(p);
 }
 
 }  // namespace wg
@@ -298,35 +292,27 @@ int us3d_spconv_wgrad_planes(const void *x_hi, const void *x_lo, const void *dy_
     p.rows_per_split = ceil_div(ceil_div(n_rows, splits), 128) * 128;
     p.splits = ceil_div(n_rows, p.rows_per_split);
     const int npl = passes == 3 ? 2 : 1;
-    const int a_slot = npl * 2 * wg::SLAB, b_slot = npl * (p.npad / 64) * wg::SLAB;
-    const int budget = 208 * 1024;
+    const int a_slot = 2 * wg::SLAB, b_slot = npl * (p.npad / 64) * wg::SLAB;
+    const int budget = 220 * 1024;
     p.b_slots = 2;
     p.a_slots = (budget - p.b_slots * b_slot) / a_slot;
     if (p.a_slots > wg::MAX_A) p.a_slots = wg::MAX_A;
     US3D_CHECK_ARG(p.a_slots >= 2, "spconv_wgrad_planes: operand slots do not fit in shared memory (cout %d)", cout);
     const size_t smem = (size_t)p.a_slots * a_slot + (size_t)p.b_slots * b_slot + 1024;
-    static bool attr_done = false;
+static bool attr_done = false;
     if (!attr_done) {
-        US3D_CUDA(cudaFuncSetAttribute(wg::k_wgrad<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-        US3D_CUDA(cudaFuncSetAttribute(wg::k_wgrad<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-        US3D_CUDA(cudaFuncSetAttribute(wg::k_wgrad<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-        US3D_CUDA(cudaFuncSetAttribute(wg::k_wgrad<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-        US3D_CUDA(cudaFuncSetAttribute(wg::k_wgrad<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-        US3D_CUDA(cudaFuncSetAttribute(wg::k_wgrad<3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+        US3D_CUDA(cudaFuncSetAttribute(wg::k_wgrad<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        US3D_CUDA(cudaFuncSetAttribute(wg::k_wgrad<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
         attr_done = true;
     }
     const int grid = p.ngroups * p.mblks * p.splits;
-    // Unsignalled cp.async groups: at most a_slots - 1 (an A slot is re-used a_slots items later) and at most
-    // 2 (b_slots - 1): a row block issues >= 2 groups (dY + one offset), and the dY slot of block n + 1 may only be
-    // claimed once every group of block n + 1 - b_slots has been signalled and consumed.
-    int lag = p.a_slots - 1;
-    if (lag > 2 * (p.b_slots - 1)) lag = 2 * (p.b_slots - 1);
-    if (lag > wg::MAX_LAG) lag = wg::MAX_LAG;
-    if (lag < 1) lag = 1;
-    if (passes == 3)
-        wg::launch<3>(lag, grid, smem, st, p);
-    else
-        wg::launch<1>(lag, grid, smem, st, p);
+    {
+        ProfScope prof(st, 1, n_rows, n_rows, kvol, cin, cout);
+        if (passes == 3)
+            wg::k_wgrad<3><<<grid, wg::THREADS, smem, st>>>(p);
+        else
+            wg::k_wgrad<1><<<grid, wg::THREADS, smem, st>>>(p);
+    }
     US3D_LAUNCH_CHECK();
     return 0;
 }

@@ -32,15 +32,19 @@ def _ptr(t):
 
 
 class KernelTimer:
-    """Optional per-launch CUDA-event timing of the convolution kernels (bench.py roofline leg).
-    `records` holds (kind, n_in_rows, n_out_rows, kvol, cin, cout, start_event, end_event)."""
+    """Per-launch timing of the convolution kernels (bench.py roofline leg).  While active, libus3d brackets every
+    convolution kernel launch with CUDA events recorded on the launch stream from inside the C entry point, a few
+    microseconds of host time before the kernel — so the launch gaps of a host-bound section are not counted as kernel
+    time, and the kernels are timed where they run, with the cache state the step gives them.
+    `summary()` returns (kind, n_in_rows, n_out_rows, kvol, cin, cout, ms) per launch, in launch order."""
 
     def __init__(self):
-        self.records = []
+        self.meta = []
 
     def __enter__(self):
         global _timer
         _timer = self
+        _dbg().us3d_debug_profile_start()
         return self
 
     def __exit__(self, *exc):
@@ -48,22 +52,41 @@ class KernelTimer:
         _timer = None
 
     def summary(self):
-        torch.cuda.synchronize()
-        return [(k, ni, no, kv, ci, co, s.elapsed_time(e)) for (k, ni, no, kv, ci, co, s, e) in self.records]
+        import ctypes
+
+        cap = len(self.meta) + 16
+        meta = (ctypes.c_int * (7 * cap))()
+        ms = (ctypes.c_float * cap)()
+        n = _dbg().us3d_debug_profile_stop(meta, ms, cap)
+        assert n == len(self.meta), f"profiler saw {n} convolution launches, the host issued {len(self.meta)}"
+        return [m + (float(ms[i]),) for i, m in enumerate(self.meta)]
 
 
 _timer = None
+_dbg_lib = None
+
+
+def _dbg():
+    """Debug / profiling hooks of the library (not part of the drop-in surface)."""
+    global _dbg_lib
+    if _dbg_lib is None:
+        import ctypes
+
+        from .._lib import LIB_PATH
+
+        _dbg_lib = ctypes.CDLL(LIB_PATH)
+        _dbg_lib.us3d_debug_profile_start.restype = None
+        _dbg_lib.us3d_debug_profile_tag.argtypes = [ctypes.c_int]
+        _dbg_lib.us3d_debug_profile_tag.restype = None
+        _dbg_lib.us3d_debug_profile_stop.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        _dbg_lib.us3d_debug_profile_stop.restype = ctypes.c_int
+    return _dbg_lib
 
 
 def _timed(kind, n_in, n_out, kvol, cin, cout, launch):
-    if _timer is None:
-        return launch()
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s.record()
-    r = launch()
-    e.record()
-    _timer.records.append((kind, n_in, n_out, kvol, cin, cout, s, e))
-    return r
+    if _timer is not None:
+        _timer.meta.append((kind, n_in, n_out, kvol, cin, cout))
+    return launch()
 
 
 # Arithmetic of the sparse-conv forward / input-gradient GEMMs:
@@ -90,6 +113,61 @@ def pack_weights(w3: torch.Tensor, transpose: bool, flip_k: bool, passes: int) -
     check(lib.us3d_spconv_pack_weights(w3.data_ptr(), kvol, w_cin, w_cout, int(transpose), int(flip_k), passes,
                                        out.data_ptr(), _stream()))
     return out
+
+
+_pack_epoch = {"n": 0}
+_packed_bytes_cache = {}
+
+
+def invalidate_packed_weights():
+    """Forget every cached weight image.  The images are keyed on the parameter's version counter, which an optimizer
+    step bumps; a loop that changes weights behind autograd's back (or a benchmark that wants to pay the packing of a
+    real training step on every iteration) calls this once per step."""
+    _pack_epoch["n"] += 1
+
+
+def _packed_bytes(kvol, kdim, ndim, passes):
+    key = (kvol, kdim, ndim, passes)
+    v = _packed_bytes_cache.get(key)
+    if v is None:
+        v = _packed_bytes_cache[key] = int(lib.us3d_spconv_packed_bytes(kvol, kdim, ndim, passes))
+    return v
+
+
+def packed_weights(kernel: torch.Tensor, w3: torch.Tensor, flip_dgrad: bool, passes: int, need_dgrad: bool):
+    """(forward image or None, input-gradient image(s) or None) of one convolution's weights, built by ONE call and kept on
+    the parameter while its version counter is unchanged.  The input-gradient side is a list of (first output column,
+    columns, image): a gradient wider than 256 channels (the 384-channel concatenations of the decoder) is produced in
+    column slices of the transposed weight."""
+    key = (kernel._version, _pack_epoch["n"], passes, bool(flip_dgrad), w3.data_ptr())
+    cached = getattr(kernel, "_us3d_packs", None)
+    if cached is not None and cached[0] == key and (cached[2] is not None or not need_dgrad):
+        return cached[1], cached[2]
+    kvol, cin, cout = w3.shape
+    dev = w3.device
+    st = _stream()
+    fwd = torch.empty(_packed_bytes(kvol, cin, cout, passes), dtype=torch.uint8, device=dev) if _tc_ok(cin, cout) else None
+    bwd = None
+    if need_dgrad and _tc_ok(cout, cin):
+        bwd_img = torch.empty(_packed_bytes(kvol, cout, cin, passes), dtype=torch.uint8, device=dev)
+        bwd = [(0, cin, bwd_img)]
+        check(lib.us3d_spconv_pack_pair(w3.data_ptr(), kvol, cin, cout, int(flip_dgrad), passes, _ptr(fwd), bwd_img.data_ptr(), st))
+    else:
+        if fwd is not None:
+            check(lib.us3d_spconv_pack_pair(w3.data_ptr(), kvol, cin, cout, int(flip_dgrad), passes, fwd.data_ptr(), 0, st))
+        if need_dgrad and cin > 256 and cin % 32 == 0 and _tc_ok(cout, cin // 2):
+            half = cin // 2
+            bwd = []
+            for c0 in (0, half):
+                ws = w3[:, c0:c0 + half, :].contiguous()
+                img = torch.empty(_packed_bytes(kvol, cout, half, passes), dtype=torch.uint8, device=dev)
+                check(lib.us3d_spconv_pack_pair(ws.data_ptr(), kvol, half, cout, int(flip_dgrad), passes, 0, img.data_ptr(), st))
+                bwd.append((c0, half, img))
+    try:
+        kernel._us3d_packs = (key, fwd, bwd)
+    except Exception:  # pragma: no cover
+        pass
+    return fwd, bwd
 
 
 # forward / input-gradient tensor-core kernel: "cp" = cp.async row gather, persistent, double-buffered TMEM (default);
@@ -120,34 +198,38 @@ def _tc_ok(cin, cout):  # == us3d_spconv_tc_supported, without the FFI round tri
     return cin >= 16 and cin % 16 == 0 and cout >= 16 and cout % 16 == 0 and cout <= 256
 
 
-def spconv_gather(x, table: NeighbourTable, w3, cin, cout, transpose_w, flip_k, bias=None, out=None, accumulate=False):
+def spconv_gather(x, table: NeighbourTable, w3, cin, cout, transpose_w, flip_k, bias=None, out=None, accumulate=False, wpack=None):
+    """y[j] = sum_k x[nbr[k, j]] . W'[k]  (W' = W[k], or W[K-1-k]^T / W[k]^T for the input gradient).  `wpack` is the
+    cached weight image of packed_weights(); without it the image is built here."""
     x = _rows(x)
     y = out if out is not None else torch.empty((table.n_rows, cout), dtype=torch.float32, device=x.device)
     st = _stream()
     mode = _precision["mode"]
+    kind = "dgrad" if transpose_w else "fwd"
+    if not transpose_w and cin <= 4 and lib.us3d_stem_conv_supported(cin, cout, table.kvol) and not accumulate:
+        # stem convolution: exact fp32, warp = rows, lane = output channel
+        w3c = w3 if w3.is_contiguous() else w3.contiguous()
+        _timed(kind, x.shape[0], table.n_rows, table.kvol, cin, cout, lambda: check(
+            lib.us3d_stem_conv_fwd(x.data_ptr(), _ld(x), table.nbr.data_ptr(), table.n_rows, table.kvol, w3c.data_ptr(), cin, cout,
+                                   _ptr(bias), y.data_ptr(), _ld(y), st)))
+        return y
     if (mode != 0 and _tc_ok(cin, cout) and x.data_ptr() % 16 == 0 and _ld(x) % 4 == 0):
-        wpack = pack_weights(w3, transpose_w, flip_k, mode)
-        kind = "dgrad" if transpose_w else "fwd"
-        if _tc_kernel["fwd"] == "mt" and _timer is None:  # production path, no per-launch timing
-            hi, lo = bf16_planes(x, mode == 3)
-            check(lib.us3d_spconv_gather_mt(hi.data_ptr(), _ptr(lo), x.shape[0], table.nbr.data_ptr(), table.n_rows, table.kvol,
-                                            wpack.data_ptr(), cin, cout, mode, _ptr(bias), 0, y.data_ptr(), _ld(y),
-                                            int(accumulate), _ptr(table.mask), st))
-            return y
-        if _tc_kernel["fwd"] in ("tma", "cp", "mt"):
-            hi, lo = bf16_planes(x, mode == 3)
-            fn = {"tma": lib.us3d_spconv_gather_tma, "cp": lib.us3d_spconv_gather_cp, "mt": lib.us3d_spconv_gather_mt}[_tc_kernel["fwd"]]
+        if wpack is None:
+            wpack = pack_weights(w3, transpose_w, flip_k, mode)
+        hi, lo = bf16_planes(x, mode == 3)
+        kname = _tc_kernel["fwd"]
+        if kname in ("tma", "cp", "mt"):
+            fn = lib.us3d_spconv_gather_mt if kname == "mt" else (lib.us3d_spconv_gather_tma if kname == "tma" else lib.us3d_spconv_gather_cp)
             _timed(kind, x.shape[0], table.n_rows, table.kvol, cin, cout, lambda: check(
-                fn(hi.data_ptr(), _ptr(lo), x.shape[0], table.nbr.data_ptr(), table.n_rows, table.kvol,
-                                           wpack.data_ptr(), cin, cout, mode, _ptr(bias), 0, y.data_ptr(), _ld(y),
-                                           int(accumulate), _ptr(table.mask), st)))
+                fn(hi.data_ptr(), _ptr(lo), x.shape[0], table.nbr.data_ptr(), table.n_rows, table.kvol, wpack.data_ptr(), cin, cout,
+                   mode, _ptr(bias), 0, y.data_ptr(), _ld(y), int(accumulate), _ptr(table.mask), st)))
             return y
         _timed(kind, x.shape[0], table.n_rows, table.kvol, cin, cout, lambda: check(
             lib.us3d_spconv_gather_tc(x.data_ptr(), _ld(x), table.nbr.data_ptr(), table.n_rows, table.kvol, wpack.data_ptr(),
                                       cin, cout, mode, _ptr(bias), 0, y.data_ptr(), _ld(y), int(accumulate),
                                       _ptr(table.mask), st)))
         return y
-    _timed("dgrad" if transpose_w else "fwd", x.shape[0], table.n_rows, table.kvol, cin, cout, lambda: check(
+    _timed(kind, x.shape[0], table.n_rows, table.kvol, cin, cout, lambda: check(
         lib.us3d_spconv_gather(x.data_ptr(), _ld(x), table.nbr.data_ptr(), table.n_rows, table.kvol, w3.data_ptr(), cin, cout,
                                int(transpose_w), int(flip_k), _ptr(bias), 0, y.data_ptr(), _ld(y), int(accumulate),
                                _ptr(table.mask), st)))
@@ -159,7 +241,12 @@ def spconv_wgrad(x, table: NeighbourTable, dy, cin, cout):
     dw = torch.zeros((table.kvol, cin, cout), dtype=torch.float32, device=x.device)
     st = _stream()
     mode = _precision["mode"]
-    if (mode != 0 and lib.us3d_spconv_wgrad_tc_supported(cin, cout) and x.data_ptr() % 16 == 0 and dy.data_ptr() % 16 == 0
+    if cin == 3 and table.kvol in (1, 8, 27):
+        _timed("wgrad", x.shape[0], table.n_rows, table.kvol, cin, cout, lambda: check(
+            lib.us3d_stem_conv_wgrad(x.data_ptr(), _ld(x), table.nbr.data_ptr(), table.n_rows, table.kvol, dy.data_ptr(), _ld(dy),
+                                     dw.data_ptr(), cin, cout, st)))
+        return dw
+    if (mode != 0 and _wgrad_tc_ok(cin, cout) and x.data_ptr() % 16 == 0 and dy.data_ptr() % 16 == 0
             and _ld(x) % 4 == 0 and _ld(dy) % 4 == 0):
         if _tc_kernel["wgrad"] == "planes":
             xh, xl = bf16_planes(x, mode == 3)
@@ -178,18 +265,29 @@ def spconv_wgrad(x, table: NeighbourTable, dy, cin, cout):
     return dw
 
 
+def _wgrad_tc_ok(cin, cout):  # == us3d_spconv_wgrad_tc_supported, without the FFI round trip
+    return cin >= 8 and cin % 8 == 0 and cout >= 16 and cout % 16 == 0 and cout <= 256
+
+
 class SparseConvFunction(torch.autograd.Function):
-    """Y = conv(X) over `fwd` ([K, n_out] neighbour table); backward uses `bwd` ([K, n_in], flip flag)."""
+    """Y = conv(X) over `fwd` ([K, n_out] neighbour table); backward uses `bwd` ([K, n_in], flip flag).
+    `flip_dgrad` is the flag the backward table will carry (known from the map pair at forward time), so that the
+    forward and input-gradient weight images are packed by one call."""
 
     @staticmethod
-    def forward(ctx, x, kernel, bias, fwd: NeighbourTable, bwd_getter):
+    def forward(ctx, x, kernel, bias, fwd: NeighbourTable, bwd_getter, flip_dgrad=False):
         x = _rows(x)
         w3 = kernel.detach().contiguous().view(fwd.kvol, kernel.shape[-2], kernel.shape[-1])
         cin, cout = w3.shape[1], w3.shape[2]
         assert x.shape[1] == cin, f"input has {x.shape[1]} channels, kernel expects {cin}"
-        y = spconv_gather(x, fwd, w3, cin, cout, False, False, None if bias is None else bias.detach().contiguous())
+        mode = _precision["mode"]
+        wf = None
+        if mode != 0 and cin > 4:
+            need_dgrad = x.requires_grad and torch.is_grad_enabled()
+            wf, _ = packed_weights(kernel, w3, flip_dgrad, mode, need_dgrad)
+        y = spconv_gather(x, fwd, w3, cin, cout, False, False, None if bias is None else bias.detach().contiguous(), wpack=wf)
         ctx.save_for_backward(x, kernel)
-        ctx.fwd, ctx.bwd_getter, ctx.has_bias = fwd, bwd_getter, bias is not None
+        ctx.fwd, ctx.bwd_getter, ctx.has_bias, ctx.flip_dgrad = fwd, bwd_getter, bias is not None, flip_dgrad
         ctx.x_planes = getattr(x, "_us3d_planes", None)  # the weight gradient re-uses the forward's bf16 planes
         return y
 
@@ -205,43 +303,59 @@ class SparseConvFunction(torch.autograd.Function):
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             bwd, flip = ctx.bwd_getter()
-            dx = spconv_gather(dy, bwd, w3, cout, cin, True, flip)
+            mode = _precision["mode"]
+            chunks = None
+            if mode != 0 and flip == ctx.flip_dgrad and cin > 4:
+                chunks = packed_weights(kernel, w3, flip, mode, True)[1]
+            if chunks is None or len(chunks) == 1:
+                dx = spconv_gather(dy, bwd, w3, cout, cin, True, flip, wpack=None if chunks is None else chunks[0][2])
+            else:  # wide gradient: column slices of the transposed weight, written in place into dx
+                dx = torch.empty((bwd.n_rows, cin), dtype=torch.float32, device=dy.device)
+                for c0, nc, img in chunks:
+                    spconv_gather(dy, bwd, w3[:, c0:c0 + nc, :], cout, nc, True, flip, out=dx[:, c0:c0 + nc], wpack=img)
         if ctx.needs_input_grad[1]:
             dw = spconv_wgrad(x, fwd, dy, cin, cout).view(kernel.shape)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy.sum(0, keepdim=True)
-        return dx, dw, db, None, None
+        return dx, dw, db, None, None, None
 
 
 _bn_ws = {}
 
 
 def _bn_workspace(dev, c):
-    """Per-device scratch for the BatchNorm column reductions (2*c doubles).  Kernels on one stream are ordered,
-    so one buffer per device is enough for the single-stream execution the module surface uses."""
+    """Per-device scratch of the BatchNorm column reductions: 2*c doubles + a ticket counter, ZERO between uses (every
+    kernel that accumulates into it is followed by one whose last block zeroes it again).  Kernels on one stream are
+    ordered, so one buffer per device serves the single-stream execution the module surface uses."""
     ws = _bn_ws.get(dev.index)
-    if ws is None or ws.numel() < 2 * c:
-        ws = torch.empty(max(2 * c, 2048), dtype=torch.float64, device=dev)
+    if ws is None or ws.numel() < 2 * c + 2:
+        ws = torch.zeros(max(2 * c + 2, 2050), dtype=torch.float64, device=dev)
         _bn_ws[dev.index] = ws
     return ws
 
 
-def bn_batch_stats(x, running_mean, running_var, momentum, eps):
-    """Batch statistics of all rows (no autograd: the apply function's backward carries the dependence on them).
-    Returns (mean, invstd) fp32 [c]; updates the running statistics in place like nn.BatchNorm1d."""
+def bn_batch_stats(x, running_mean, running_var, momentum, eps, num_batches_tracked=None):
+    """Batch statistics of all rows in ONE launch (no autograd: the apply function's backward carries the dependence on
+    them).  Returns (mean, invstd) fp32 [c]; updates the running statistics and num_batches_tracked like nn.BatchNorm1d."""
     x = _rows(x)
     n, c = x.shape
     dev = x.device
     stats = torch.empty((2, c), dtype=torch.float32, device=dev)
-    check(lib.us3d_bn_batch_stats(x.data_ptr(), _ld(x), n, c, float(eps), float(momentum if momentum is not None else 0.0),
-                                  stats[0].data_ptr(), stats[1].data_ptr(), _ptr(running_mean), _ptr(running_var),
-                                  _bn_workspace(dev, c).data_ptr(), _stream()))
+    check(lib.us3d_bn_stats_fused(x.data_ptr(), _ld(x), n, c, float(eps), float(momentum if momentum is not None else 0.0),
+                                  stats.data_ptr(), stats.data_ptr() + 4 * c, _ptr(running_mean), _ptr(running_var),
+                                  _ptr(num_batches_tracked), _bn_workspace(dev, c).data_ptr(), _stream()))
     return stats[0], stats[1]
+
+
+def _want_planes(c):
+    """bf16 planes are written by the producing pass when a tensor-core convolution can consume them."""
+    return _precision["mode"] != 0 and c % 16 == 0
 
 
 class BatchNormApplyFunction(torch.autograd.Function):
     """y = [relu]( (x - mean) * invstd * gamma + beta [+ residual] ) with (mean, invstd) given.  `batch_stats`
-    says whether they are this batch's statistics (training: backward includes the two batch terms) or constants."""
+    says whether they are this batch's statistics (training: backward includes the two batch terms) or constants.
+    The same pass writes y's bf16 planes (cached on y for the convolution that follows); backward does the same for dx."""
 
     @staticmethod
     def forward(ctx, x, gamma, beta, residual, mean, invstd, batch_stats, relu):
@@ -253,8 +367,15 @@ class BatchNormApplyFunction(torch.autograd.Function):
         g = gamma.detach().contiguous() if gamma is not None else torch.ones(c, device=dev)
         b = beta.detach().contiguous() if beta is not None else torch.zeros(c, device=dev)
         y = torch.empty((n, c), dtype=torch.float32, device=dev)
-        check(lib.us3d_bn_apply(x.data_ptr(), _ld(x), n, c, mean.data_ptr(), invstd.data_ptr(), g.data_ptr(), b.data_ptr(),
-                                _ptr(residual), 0 if residual is None else _ld(residual), int(relu), y.data_ptr(), _ld(y), _stream()))
+        hi = lo = None
+        if _want_planes(c) and n > 0:
+            hi = torch.empty((n, c), dtype=torch.bfloat16, device=dev)
+            lo = torch.empty((n, c), dtype=torch.bfloat16, device=dev) if _precision["mode"] == 3 else None
+        check(lib.us3d_bn_apply_planes(x.data_ptr(), _ld(x), n, c, mean.data_ptr(), invstd.data_ptr(), g.data_ptr(), b.data_ptr(),
+                                       _ptr(residual), 0 if residual is None else _ld(residual), int(relu), y.data_ptr(), c,
+                                       _ptr(hi), _ptr(lo), _stream()))
+        if hi is not None:
+            y._us3d_planes = (hi, lo, y._version)
         ctx.save_for_backward(x, y if relu else None, mean, invstd, g)
         ctx.relu, ctx.training, ctx.has_res = bool(relu), bool(batch_stats), residual is not None
         ctx.affine = gamma is not None
@@ -270,13 +391,17 @@ class BatchNormApplyFunction(torch.autograd.Function):
         dx = torch.empty((n, c), dtype=torch.float32, device=dev)
         dres = torch.empty((n, c), dtype=torch.float32, device=dev) if ctx.has_res else None
         dgb = torch.empty((2, c), dtype=torch.float32, device=dev)
-        dgamma, dbeta = dgb[0], dgb[1]
-        check(lib.us3d_bn_backward(dy.data_ptr(), _ld(dy), x.data_ptr(), _ld(x), yy.data_ptr(), _ld(yy), n, c, mean.data_ptr(),
-                                   invstd.data_ptr(), g.data_ptr(), int(ctx.relu), int(ctx.training), _bn_workspace(dev, c).data_ptr(),
-                                   dx.data_ptr(), _ld(dx), _ptr(dres), 0 if dres is None else _ld(dres), dgamma.data_ptr(),
-                                   dbeta.data_ptr(), _stream()))
-        if not ctx.affine:
-            dgamma = dbeta = None
+        hi = lo = None
+        if _want_planes(c) and dy.data_ptr() % 16 == 0 and _ld(dy) % 4 == 0 and x.data_ptr() % 16 == 0 and _ld(x) % 4 == 0:
+            hi = torch.empty((n, c), dtype=torch.bfloat16, device=dev)
+            lo = torch.empty((n, c), dtype=torch.bfloat16, device=dev) if _precision["mode"] == 3 else None
+        check(lib.us3d_bn_backward_planes(dy.data_ptr(), _ld(dy), x.data_ptr(), _ld(x), yy.data_ptr(), _ld(yy), n, c, mean.data_ptr(),
+                                          invstd.data_ptr(), g.data_ptr(), int(ctx.relu), int(ctx.training),
+                                          _bn_workspace(dev, c).data_ptr(), dx.data_ptr(), c, _ptr(dres), c, dgb.data_ptr(),
+                                          dgb.data_ptr() + 4 * c, _ptr(hi), _ptr(lo), _stream()))
+        if hi is not None:
+            dx._us3d_planes = (hi, lo, dx._version)
+        dgamma, dbeta = (dgb[0], dgb[1]) if ctx.affine else (None, None)
         return dx, dgamma, dbeta, dres, None, None, None, None
 
 

@@ -315,6 +315,7 @@ class _ConvBase(MinkowskiModuleBase):
     def forward(self, x: SparseTensor) -> SparseTensor:
         cm, in_key = x.coordinate_manager, x.coordinate_map_key
         ks, dil = self.kernel_size, self.dilation
+        flip_dgrad = False
         if self.use_mm:
             out_key = in_key
             fwd = cm.identity_table(in_key)
@@ -323,6 +324,7 @@ class _ConvBase(MinkowskiModuleBase):
             out_key = cm.stride(in_key, self.stride)
             fwd = cm.forward_table(in_key, out_key, ks, dil)
             bwd_getter = lambda: cm.backward_table(in_key, out_key, ks, dil)
+            flip_dgrad = in_key == out_key and all(k % 2 == 1 for k in ks)  # == the flag backward_table will return
         else:
             ts = in_key.tensor_stride
             assert all(t % s == 0 for t, s in zip(ts, self.stride)), "transposed conv below tensor stride 1"
@@ -333,7 +335,7 @@ class _ConvBase(MinkowskiModuleBase):
             # backward reads the fine rows at coarse + off_k
             fwd = cm.backward_table(out_key, in_key, ks, dil)[0]
             bwd_getter = lambda: (cm.forward_table(out_key, in_key, ks, dil), False)
-        y = Fn.SparseConvFunction.apply(x.F, self.kernel, self.bias, fwd, bwd_getter)
+        y = Fn.SparseConvFunction.apply(x.F, self.kernel, self.bias, fwd, bwd_getter, flip_dgrad)
         return SparseTensor(y, coordinate_map_key=out_key, coordinate_manager=cm)
 
 
@@ -397,15 +399,18 @@ class MinkowskiBatchNorm(nn.Module):
         bn = self.bn
         use_batch = bn.training or not bn.track_running_stats
         momentum = bn.momentum
+        nbt = None
         if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
-            bn.num_batches_tracked.add_(1)
-            if momentum is None:
+            if momentum is None:  # cumulative moving average: the factor depends on the counter (host read, rare)
+                bn.num_batches_tracked.add_(1)
                 momentum = 1.0 / float(bn.num_batches_tracked)
+            else:
+                nbt = bn.num_batches_tracked  # incremented by the statistics kernel itself
         rm = bn.running_mean if (bn.track_running_stats and (bn.training or not use_batch)) else None
         rv = bn.running_var if rm is not None else None
         f = x.F
         if use_batch:
-            mean, invstd = Fn.bn_batch_stats(f.detach(), rm, rv, momentum, bn.eps)
+            mean, invstd = Fn.bn_batch_stats(f.detach(), rm, rv, momentum, bn.eps, nbt)
         else:
             mean = bn.running_mean.detach().float()
             invstd = torch.rsqrt(bn.running_var.detach().float() + bn.eps)

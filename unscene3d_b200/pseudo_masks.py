@@ -54,7 +54,13 @@ def aggregate_features(encoded_features: torch.Tensor, segment_ids: torch.Tensor
     unique_segments, index = torch.unique(segment_ids, return_inverse=True)
     valid = torch.any(encoded_features != 0, dim=-1)
     S = unique_segments.shape[0]
-    agg = Fn.SegmentMeanFunction.apply(encoded_features[valid].contiguous(), index[valid].contiguous(), S).detach()
+    src, idx = encoded_features[valid].float().contiguous(), index[valid].contiguous().long()
+    agg = torch.empty((S, src.shape[1]), dtype=torch.float32, device=src.device)
+    acc = torch.zeros((S, src.shape[1]), dtype=torch.float64, device=src.device)
+    count = torch.zeros(S, dtype=torch.float32, device=src.device)
+    # fp64 sums, rounded once: the affinity threshold downstream must not see the order of the atomics
+    check(lib.us3d_segment_mean_f64(src.data_ptr(), idx.data_ptr(), src.shape[0], src.shape[1], S, acc.data_ptr(), agg.data_ptr(),
+                                    count.data_ptr(), _stream()))
     zero = torch.all(agg == 0, dim=-1)
     if bool(zero.any()):
         first_zero = unique_segments[zero][0]
@@ -93,47 +99,64 @@ def get_affinity_matrix(feats, tau: float = 0.15, eps: float = 1e-5, painted: Op
     return NCutGraph(bits, degree, S, eps)
 
 
-def _lanczos_second_largest(matvec, S: int, dev, max_steps: int, tol: float, seed: int, check_every: int = 10) -> torch.Tensor:
-    """Unit eigenvector of the second largest eigenvalue of the symmetric operator `matvec` (fp64, full
-    re-orthogonalisation twice per step).  Stops when the residual bounds |beta_m s_m| of the THREE leading Ritz pairs
-    are below tol: in a clustered graph the leading eigenvalues are nearly degenerate and the copy that belongs to
-    the second one can appear late, after a wrong pair already looks converged."""
-    m = min(max_steps, S)
-    Q = torch.zeros((m + 1, S), dtype=torch.float64, device=dev)
+def _lanczos_top_deflated(matvec, u1: torch.Tensor, max_steps: int, tol: float, seed: int, check_every: int = 20,
+                          min_steps: int = 512, breakdown: float = 1e-10) -> torch.Tensor:
+    """Unit eigenvector of the LARGEST eigenvalue of the symmetric operator `matvec` restricted to the complement of the
+    known unit eigenvector `u1` (fp64, full re-orthogonalisation twice per step, u1 included in the basis).
+
+    Why this shape.  The leading eigenvalues of M = D^-1/2 W D^-1/2 of a clustered graph sit within 1e-5 of each other
+    and single-vector Lanczos "misconverges" there (a Ritz pair stalls on the third eigenvalue with a tiny residual
+    before moving on), so no early exit is taken before `min_steps` — with full re-orthogonalisation the recurrence run
+    to the dimension of the Krylov space is an exact tridiagonalisation, as reliable as the reference's dense LAPACK
+    solve, and S is 1-3 k segments.  Once most segments are painted the Krylov space is tiny (a handful of distinct
+    eigenvalues): the recurrence breaks down (beta -> 0) after a few steps and whatever is normalised after that is
+    rounding noise that re-discovers the trivial eigenvalue 1 as a "ghost"; deflating the known trivial vector
+    u1 = D^1/2 1 / |.| and cutting the recurrence at the first beta < `breakdown` removes both failure modes."""
+    S, dev = u1.shape[0], u1.device
+    m = min(max_steps, S - 1)
+    Q = torch.zeros((m + 2, S), dtype=torch.float64, device=dev)
+    Q[0] = u1  # row 0 is the deflated vector: part of every re-orthogonalisation, not of the recurrence
     g = torch.Generator(device="cpu").manual_seed(seed)
     q0 = torch.randn(S, generator=g, dtype=torch.float64).to(dev)
-    Q[0] = q0 / q0.norm()
+    q0 = q0 - u1 * (u1 @ q0)
+    q0 = q0 - u1 * (u1 @ q0)
+    Q[1] = q0 / q0.norm()
     alpha = torch.zeros(m, dtype=torch.float64, device=dev)
     beta = torch.zeros(m, dtype=torch.float64, device=dev)
-    steps = 0
+    steps, window = 0, 8
     for j in range(m):
-        w = matvec(Q[j])
-        alpha[j] = w @ Q[j]
-        basis = Q[: j + 1]
+        w = matvec(Q[j + 1])
+        alpha[j] = w @ Q[j + 1]
+        basis = Q[: j + 2]
         w = w - basis.T @ (basis @ w)
         w = w - basis.T @ (basis @ w)
         beta[j] = w.norm()
         steps = j + 1
-        if steps >= 3 and steps % check_every == 0 and steps < m:
+        if steps % window == 0 or steps == m:  # one host sync per window: has the Krylov space been exhausted?
+            lo = max(steps - window, 0)
+            small = torch.nonzero(beta[lo:steps] < breakdown)
+            if small.numel():
+                steps = lo + int(small[0]) + 1
+                break
+        if steps >= min_steps and steps % check_every == 0 and steps < m:
             a, b = alpha[:steps].cpu(), beta[:steps].cpu()
             T = torch.diag(a) + torch.diag(b[: steps - 1], 1) + torch.diag(b[: steps - 1], -1)
             evecs = torch.linalg.eigh(T)[1]
             if float(b[steps - 1]) * float(evecs[-1, -3:].abs().max()) < tol:
                 break
-        if float(beta[j]) < 1e-13:  # invariant subspace: the Krylov space is exhausted
-            break
-        Q[j + 1] = w / beta[j]
+        if j + 1 < m:
+            Q[j + 2] = w / beta[j].clamp_min(1e-300)
     a, b = alpha[:steps].cpu(), beta[:steps].cpu()
     T = torch.diag(a) + torch.diag(b[: steps - 1], 1) + torch.diag(b[: steps - 1], -1)
-    ritz = torch.linalg.eigh(T)[1][:, -2]
-    u = Q[:steps].T @ ritz.to(dev)
+    ritz = torch.linalg.eigh(T)[1][:, -1]
+    u = Q[1: steps + 1].T @ ritz.to(dev)
     return u / u.norm()
 
 
-def second_smallest_eigenvector(graph: NCutGraph, max_steps: int = 1000, tol: float = 1e-10, seed: int = 0) -> torch.Tensor:
+def second_smallest_eigenvector(graph: NCutGraph, max_steps: int = 4096, tol: float = 1e-10, seed: int = 0) -> torch.Tensor:
     """Eigenvector of the second smallest eigenvalue of (D - W) v = lambda D v, normalised v^T D v = 1 like
-    scipy.linalg.eigh(D - A, D): Lanczos for the second largest eigenpair of M = D^-1/2 W D^-1/2 (W x from the
-    bit matrix on the device), then v = D^-1/2 u."""
+    scipy.linalg.eigh(D - A, D): Lanczos for the largest eigenpair of M = D^-1/2 W D^-1/2 (W x from the bit matrix on
+    the device) in the complement of its known leading eigenvector D^1/2 1, then v = D^-1/2 u."""
     S, dev = graph.n, graph.bits.device
     st = _stream()
     dinv = graph.degree.rsqrt()
@@ -145,7 +168,9 @@ def second_smallest_eigenvector(graph: NCutGraph, max_steps: int = 1000, tol: fl
         check(lib.us3d_ncut_matvec(graph.bits.data_ptr(), S, float(graph.eps), x.data_ptr(), xs.data_ptr(), y.data_ptr(), st))
         return dinv * y
 
-    return dinv * _lanczos_second_largest(matvec, S, dev, max_steps, tol, seed)
+    u1 = graph.degree.sqrt()
+    u1 = u1 / u1.norm()
+    return dinv * _lanczos_top_deflated(matvec, u1, max_steps, tol, seed)
 
 
 def separate_segments(bipartition: np.ndarray, vec: np.ndarray, unique_segments: torch.Tensor, seg_connectivity: torch.Tensor, mode: str = "max"):
