@@ -47,13 +47,32 @@ def env_int(name, default):
 
 # ------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """SM clock and throttle reasons during the timed region: in-process NVML queries (nvidia_ml_py) issued by the timed
+    loop itself; `nvidia-smi -lms` in a subprocess as a fallback.  (Measured on the B200 box: NVML / nvidia-smi queries
+    stall kernel launches — a looping nvidia-smi slows this host-bound step from ~20 to 28 ms, a query per step to 24 ms —
+    so only two samples are taken, from the loop thread.)"""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
-        self.gpu, self.samples, self.proc = gpu_index, [], None
+    def __init__(self, gpu_index, period_s=0.02):
+        self.gpu, self.samples, self.proc, self.period = gpu_index, [], None, period_s
+        self.nvml, self.handle, self.stop_flag, self.thread = None, None, False, None
 
     def start(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES remaps indices: resolve through the PCI bus id of the torch device
+            import torch
+
+            bus = torch.cuda.get_device_properties(self.gpu).pci_bus_id if hasattr(torch.cuda.get_device_properties(self.gpu), "pci_bus_id") else None
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.gpu) if bus is None else self._handle_by_bus(pynvml, bus)
+            self.nvml = pynvml
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            return  # sampled from the timed loop itself (sample()), one NVML query per step: no second thread, no GIL traffic
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -61,11 +80,45 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    @staticmethod
+    def _handle_by_bus(pynvml, bus_id):
+        for i in range(pynvml.nvmlDeviceGetCount()):
+            h = pynvml.nvmlDeviceGetHandleByIndex(i)
+            if int(pynvml.nvmlDeviceGetPciInfo(h).bus) == int(bus_id):
+                return h
+        return pynvml.nvmlDeviceGetHandleByIndex(0)
+
+    def sample(self):
+        """One in-process NVML query (a few tens of microseconds); called once per step inside the timed region."""
+        nv = self.nvml
+        if nv is None:
+            return
+        try:
+            sm = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+            reasons = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            self.samples.append((time.time(), sm, reasons))
+        except Exception:
+            pass
+
     def _read(self):
         for line in self.proc.stdout:
             self.samples.append((time.time(), line.strip()))
 
     def stop(self, t0, t1):
+        if self.nvml is not None:
+            nv = self.nvml
+            names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            sm, reasons = [], set()
+            for ts, clk, bits in self.samples:
+                if t0 - 0.02 <= ts <= t1 + 0.02:
+                    sm.append(clk)
+                    reasons |= {k for k, v in names.items() if bits & v}
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.smax, "reasons": sorted(reasons), "samples": len(sm),
+                    "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -85,7 +138,8 @@ class ClockSampler:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------- CPU arm
@@ -204,14 +258,19 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, sampler=None):
         barrier()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.time()
         s.record()
-        for _ in range(steps):
+        # NVML queries contend with kernel launches for the driver (measured: two queries per step cost 4.5 ms/step on this
+        # host-bound step), so the clocks are sampled twice inside the timed region, at 1/3 and 2/3 of the steps
+        sample_at = {max(steps // 3, 1), max(2 * steps // 3, 1)} if sampler is not None else set()
+        for i in range(steps):
             flush.zero_()
             fn()
+            if i + 1 in sample_at:
+                sampler.sample()
         e.record()
         barrier()
         t1 = time.time()
@@ -223,12 +282,22 @@ def run_ours(args):
     def step_resident():
         step(c4_dev, f_dev)
 
+    # Coordinate maps are built on a dedicated high-priority stream (engine.set_coordinate_stream): their size read-back
+    # then waits for the map's own integer kernels only, not for the previous step's backward pass on the compute stream.
+    # The end-to-end leg issues the host-to-device copies of a step on the same stream, as a prefetching data loader does.
+    side = torch.cuda.Stream(device=dev, priority=-1)
+    engine.set_coordinate_stream(side, dev)
+
     def step_e2e():
-        c = c4_host.to(dev, non_blocking=True)
-        f = f_host.to(dev, non_blocking=True)
+        main = torch.cuda.current_stream(dev)
+        with torch.cuda.stream(side):
+            c = c4_host.to(dev, non_blocking=True)
+            f = f_host.to(dev, non_blocking=True)
+        main.wait_stream(side)  # the features are consumed on the compute stream
+        c.record_stream(main)
+        f.record_stream(main)
         loss = step(c, f)
-        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)  # pinned target; the timed region ends with a synchronize
 
     for _ in range(max(args.warmup, 3)):
         step_resident()
@@ -237,9 +306,11 @@ def run_ours(args):
         sampler.start()
         time.sleep(0.3)
     _lib.reset_launch_count()
-    ms_total, t0, t1 = timed(step_resident, args.steps)
+    ms_total, t0, t1 = timed(step_resident, args.steps, sampler if rank == 0 else None)
     launches = _lib.launch_count()
     clocks = sampler.stop(t0, t1) if rank == 0 else None
+    for _ in range(2):  # the end-to-end leg has its own allocator pool (copies on the coordinate stream): warm it
+        step_e2e()
     ms_e2e, _, _ = timed(step_e2e, args.steps)
 
     value = world * args.voxels * args.steps / (ms_total * 1e-3)
@@ -294,7 +365,7 @@ def run_ours(args):
             "config": {"workload": f"Res16UNet34C fwd+bwd, synthetic ScanNet-shaped {args.voxels}-voxel scene, batch=1 per GPU (BASELINE configs[1])",
                        "parallelism": f"dp{world} (one scene per GPU, no data-path collective)",
                        "l2": "256 MiB buffer written between timed iterations (L2 flush)",
-                       "step": "coordinate-manager build + forward + loss + backward"},
+                       "step": "coordinate-manager build (on a high-priority side stream) + forward + loss + backward"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(c4_host.numel() * 4 + f_host.numel() * 4),
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,

@@ -288,6 +288,39 @@ def test_fused_batchnorm_planes_counters_and_workspace(eng):
     assert float(ws.abs().max()) == 0.0, "BatchNorm workspace not returned to zero"
 
 
+def test_coordinate_stream_gives_identical_maps_and_features(eng):
+    """Coordinate maps built on a dedicated stream (engine.set_coordinate_stream) while the compute stream is busy:
+    same maps, same kernel maps, same convolution output as the single-stream path, step after step without a
+    device-wide synchronisation in between."""
+    torch.manual_seed(11)
+    conv = torch.nn.Sequential(eng.MinkowskiConvolution(16, 32, kernel_size=3, dimension=3), eng.MinkowskiBatchNorm(32), eng.MinkowskiReLU(),
+                               eng.MinkowskiConvolution(32, 32, kernel_size=2, stride=2, dimension=3)).cuda().train()
+    scenes = [random_scene(6000 + 500 * i, 40 + i, batch=2, extent=30) for i in range(3)]
+    feats = [torch.randn(c.shape[0], 16).cuda() for c in scenes]
+    coords = [torch.from_numpy(c).cuda() for c in scenes]
+
+    def run():
+        outs = []
+        busy = torch.randn(4096, 4096, device="cuda")
+        for c, f in zip(coords, feats):
+            for _ in range(3):
+                busy = busy @ busy.clamp(-1e-3, 1e-3)  # keeps the compute stream occupied while the next maps are built
+            y = conv(eng.SparseTensor(f, c))
+            outs.append((y.C.clone(), y.F.detach().clone()))
+        torch.cuda.synchronize()
+        return outs
+
+    ref = run()
+    eng.set_coordinate_stream(torch.cuda.Stream(priority=-1))
+    try:
+        got = run()
+    finally:
+        eng.set_coordinate_stream(None)
+    for (c0, f0), (c1, f1) in zip(ref, got):
+        assert torch.equal(c0, c1)
+        assert rel_err(f1, f0.cpu()) < 1e-6
+
+
 def test_batchnorm_eval_mode(eng):
     torch.manual_seed(1)
     m = eng.MinkowskiBatchNorm(16, momentum=0.1).cuda()

@@ -176,17 +176,34 @@ k_bn_bwd_reduce(const float *__restrict__ dy, int lddy, const float *__restrict_
     }
 }
 
-// W = 8 channels per thread (vector path with planes) or 1 (any shape)
+// W = 8 channels per thread (vector path with planes) or 1 (any shape).  The per-channel coefficients of
+//     dx = a[ch] * g + b[ch] * x + d[ch]        (a = invstd gamma, b = -a invstd s1 / n, d = -a s0 / n - b mean)
+// are folded once per block into shared memory (the double-precision column sums would otherwise be re-read from L2
+// by every thread for every element).
 template <int W>
 __global__ void __launch_bounds__(256)
 k_bn_bwd_apply(const float *__restrict__ dy, int lddy, const float *__restrict__ x, int ldx, const float *__restrict__ y, int ldy, int n,
                int c, const float *__restrict__ mean, const float *__restrict__ invstd, const float *__restrict__ gamma, int relu,
                double *red, float *__restrict__ dx, int lddx, float *__restrict__ dres, int lddres, float *dgamma, float *dbeta,
                int batch_terms, uint4 *__restrict__ dx_hi, uint4 *__restrict__ dx_lo) {
+    extern __shared__ float coef[];  // [3][c]
     __shared__ bool last;
+    float *ca = coef, *cb = coef + c, *cd = coef + 2 * c;
+    {
+        const double inv_n = 1.0 / (double)n;
+        for (int k = threadIdx.x; k < c; k += blockDim.x) {
+            const double is = (double)invstd[k], m = (double)mean[k];
+            const double a = is * (double)gamma[k];
+            const double s0 = batch_terms ? red[k] : 0.0, s1 = batch_terms ? red[c + k] : 0.0;
+            const double b = -a * is * s1 * inv_n;
+            ca[k] = (float)a;
+            cb[k] = (float)b;
+            cd[k] = (float)(-a * s0 * inv_n - b * m);
+        }
+    }
+    __syncthreads();
     const int g8 = c / W;
     const long long total = (long long)n * g8;
-    const float inv_n = 1.f / (float)n;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         const int r = (int)(e / g8), ch = (int)(e % g8) * W;
         float gv[W], xv[W], yv[W], o[W];
@@ -211,11 +228,7 @@ k_bn_bwd_apply(const float *__restrict__ dy, int lddy, const float *__restrict__
             float g = gv[i];
             if (relu && !(yv[i] > 0.f)) g = 0.f;
             gv[i] = g;
-            const float is = __ldg(invstd + ch + i);
-            const float xh = (xv[i] - __ldg(mean + ch + i)) * is;
-            // batch_terms = 0: the statistics were constants (inference), dx = g * invstd * gamma
-            const float s0 = batch_terms ? (float)__ldcg(&red[ch + i]) : 0.f, s1 = batch_terms ? (float)__ldcg(&red[c + ch + i]) : 0.f;
-            o[i] = (g - s0 * inv_n - xh * s1 * inv_n) * is * __ldg(gamma + ch + i);
+            o[i] = fmaf(ca[ch + i], g, fmaf(cb[ch + i], xv[i], cd[ch + i]));
         }
         if constexpr (W == 8) {
             float4 *dp = reinterpret_cast<float4 *>(dx + (size_t)r * lddx + ch);
@@ -232,7 +245,7 @@ k_bn_bwd_apply(const float *__restrict__ dy, int lddy, const float *__restrict__
             if (dres) dres[(size_t)r * lddres + ch] = gv[0];
         }
     }
-    // the block that finishes last has seen every other block leave the loop: publish dgamma / dbeta, zero the workspace
+    // the block that finishes last has seen every other block read the sums: publish dgamma / dbeta, zero the workspace
     __threadfence();
     __syncthreads();
     unsigned int *ticket = reinterpret_cast<unsigned int *>(red + 2 * c);
@@ -240,8 +253,8 @@ k_bn_bwd_apply(const float *__restrict__ dy, int lddy, const float *__restrict__
     __syncthreads();
     if (!last) return;
     for (int k = threadIdx.x; k < c; k += blockDim.x) {
-        if (dgamma) dgamma[k] = (float)__ldcg(&red[c + k]);
-        if (dbeta) dbeta[k] = (float)__ldcg(&red[k]);
+        if (dgamma) dgamma[k] = (float)red[c + k];
+        if (dbeta) dbeta[k] = (float)red[k];
         red[k] = 0.0;
         red[c + k] = 0.0;
     }
@@ -395,7 +408,7 @@ int us3d_bn_backward_planes(const float *dy, int lddy, const float *x, int ldx, 
                             float *dx, int lddx, float *dres, int lddres, float *dgamma, float *dbeta, void *dx_hi, void *dx_lo,
                             void *stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
-    US3D_CHECK_ARG(n > 0 && c > 0, "bn_backward_planes: bad shape");
+    US3D_CHECK_ARG(n > 0 && c > 0 && c <= 4096, "bn_backward_planes: bad shape");
     dim3 grid(ceil_div(n, fused::kRows), ceil_div(c, 32)), block(32, 8);
     fused::k_bn_bwd_reduce<<<grid, block, 0, st>>>(dy, lddy, x, ldx, y, ldy, n, c, mean, invstd, relu, ws);
     US3D_LAUNCH_CHECK();
@@ -403,11 +416,11 @@ int us3d_bn_backward_planes(const float *dy, int lddy, const float *x, int ldx, 
                      fused::al16(y) && fused::al16(dx) && (!dres || (lddres % 4 == 0 && fused::al16(dres)));
     US3D_CHECK_ARG(vec || dx_hi == nullptr, "bn_backward_planes: planes need c %% 8 == 0 and 16-byte aligned rows");
     if (vec)
-        fused::k_bn_bwd_apply<8><<<fused::flat_grid((long long)n * c / 8), 256, 0, st>>>(
+        fused::k_bn_bwd_apply<8><<<fused::flat_grid((long long)n * c / 8), 256, 3 * (size_t)c * sizeof(float), st>>>(
             dy, lddy, x, ldx, y, ldy, n, c, mean, invstd, gamma, relu, ws, dx, lddx, dres, lddres, dgamma, dbeta, batch_terms,
             (uint4 *)dx_hi, (uint4 *)dx_lo);
     else
-        fused::k_bn_bwd_apply<1><<<fused::flat_grid((long long)n * c), 256, 0, st>>>(
+        fused::k_bn_bwd_apply<1><<<fused::flat_grid((long long)n * c), 256, 3 * (size_t)c * sizeof(float), st>>>(
             dy, lddy, x, ldx, y, ldy, n, c, mean, invstd, gamma, relu, ws, dx, lddx, dres, lddres, dgamma, dbeta, batch_terms, nullptr,
             nullptr);
     US3D_LAUNCH_CHECK();

@@ -1,5 +1,6 @@
 """CUDA backend behind the MinkowskiEngine-compatible operator surface."""
-from .coords import CoordinateManager, CoordinateMapKey, NeighbourTable, kernel_offsets, unique_coords
+from .coords import (CoordinateManager, CoordinateMapKey, NeighbourTable, get_coordinate_stream, kernel_offsets, set_coordinate_stream,
+                     unique_coords)
 from .tensor import (KernelGenerator, MinkowskiAlgorithm, MinkowskiAvgPooling, MinkowskiAvgUnpooling, MinkowskiBatchNorm,
                      MinkowskiConvolution, MinkowskiConvolutionTranspose, MinkowskiInstanceNorm, MinkowskiMaxPooling,
                      MinkowskiNetwork, MinkowskiReLU, MinkowskiSumPooling, RegionType, SparseTensor,

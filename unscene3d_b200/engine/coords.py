@@ -13,6 +13,7 @@ Layout in HBM
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -21,6 +22,8 @@ import torch
 from .._lib import check, lib
 
 TILE_ROWS = 128
+# strided coordinate maps (x2 per level) derived when a coordinate map is inserted; Res16UNet uses strides 2..16
+EAGER_STRIDE_LEVELS = int(os.environ.get("US3D_EAGER_STRIDES", "4"))
 
 
 _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
@@ -96,11 +99,49 @@ class NeighbourTable:
         self.nbr, self.mask, self.n_rows, self.kvol = nbr, mask, n_rows, kvol
 
 
-def unique_coords(coords: torch.Tensor, tensor_stride=(1, 1, 1)):
+_coordinate_streams: Dict[int, "torch.cuda.Stream"] = {}
+
+
+def set_coordinate_stream(stream: Optional["torch.cuda.Stream"], device=None):
+    """Build coordinate maps on `stream` (None = on the current stream, the default).
+
+    De-duplicating a coordinate map hands its size back to the host — a stream synchronisation.  On the compute stream
+    that synchronisation waits for everything queued there, i.e. for the previous step's backward pass, and the host
+    cannot start queueing the next step until the device has drained.  With a dedicated (high-priority) coordinate stream
+    the host waits only for the few integer kernels of the map itself, so steps pipeline like they do behind a data
+    loader's prefetch stream.  Contract: coordinates handed to SparseTensor / CoordinateManager.insert must be complete
+    with respect to `stream` (resident tensors, or copies issued on it); anything that first needs a conversion kernel
+    falls back to the compute stream."""
+    dev = torch.cuda.current_device() if device is None else torch.device(device).index
+    if stream is None:
+        _coordinate_streams.pop(dev, None)
+    else:
+        _coordinate_streams[dev] = stream
+
+
+def get_coordinate_stream(device=None):
+    dev = torch.cuda.current_device() if device is None else torch.device(device).index
+    return _coordinate_streams.get(dev)
+
+
+def unique_coords(coords: torch.Tensor, tensor_stride=(1, 1, 1), side_ok: bool = False):
     """libus3d us3d_coords_unique on a CUDA int32 [n,4] tensor.
     Returns (CoordinateMap, first_rows int32 [m], inverse int32 [n])."""
     assert coords.is_cuda and coords.dtype == torch.int32 and coords.ndim == 2 and coords.shape[1] == 4
-    coords = coords.contiguous()
+    side = _coordinate_streams.get(coords.device.index) if side_ok and coords.is_contiguous() else None
+    if side is None:
+        return _unique_coords_on_current(coords.contiguous(), tensor_stride)
+    main = torch.cuda.current_stream(coords.device)
+    with torch.cuda.stream(side):
+        cmap, first, inverse = _unique_coords_on_current(coords, tensor_stride)
+    # the maps are consumed by kernels of the compute stream: their memory must not be recycled by the coordinate
+    # stream's allocator pool while those kernels are pending
+    for t in (cmap.coords, cmap.keys, cmap.vals, first, inverse):
+        t.record_stream(main)
+    return cmap, first, inverse
+
+
+def _unique_coords_on_current(coords: torch.Tensor, tensor_stride):
     n = coords.shape[0]
     dev = coords.device
     cap = lib.us3d_hash_capacity(n)
@@ -129,11 +170,21 @@ class CoordinateManager:
         self._identity: Dict[CoordinateMapKey, NeighbourTable] = {}
 
     # ---- coordinate maps --------------------------------------------------------------------
-    def insert(self, coords: torch.Tensor, tensor_stride=(1, 1, 1), string_id: str = ""):
+    def insert(self, coords: torch.Tensor, tensor_stride=(1, 1, 1), string_id: str = "", ready: bool = True):
+        """`ready`: the coordinate rows are complete with respect to the coordinate stream (see set_coordinate_stream)."""
         key = CoordinateMapKey(tensor_stride, string_id)
-        cmap, first, inverse = unique_coords(coords, (1, 1, 1))
+        cmap, first, inverse = unique_coords(coords, (1, 1, 1), side_ok=ready)
         self._maps[key] = cmap
         self.device = coords.device
+        # De-duplicating a map returns its size to the host (one stream synchronisation).  The strided maps of the
+        # U-Net pyramid are therefore derived right away, while the stream is still empty, instead of on first use in
+        # the middle of the forward pass — where every synchronisation would drain the launches the host has queued
+        # ahead of the device and serialise the host-bound coarse levels with the device-bound fine ones.
+        k = key
+        for _ in range(EAGER_STRIDE_LEVELS if string_id == "" else 0):
+            if self._maps[k].n <= 1:
+                break
+            k = self.stride(k, (2, 2, 2))
         return key, first, inverse
 
     def exists(self, key: CoordinateMapKey) -> bool:
@@ -152,7 +203,8 @@ class CoordinateManager:
         t_out = tuple(a * b for a, b in zip(in_key.tensor_stride, stride))
         out_key = CoordinateMapKey(t_out, "")
         if out_key not in self._maps:
-            cmap, _, inverse = unique_coords(self._maps[in_key].coords, t_out)
+            # a map of this manager is complete on whichever stream built it (the host has synchronised with it)
+            cmap, _, inverse = unique_coords(self._maps[in_key].coords, t_out, side_ok=True)
             self._maps[out_key] = cmap
             self._parents[(in_key, out_key)] = inverse
         return out_key

@@ -283,8 +283,7 @@ class SparseConvFunction(torch.autograd.Function):
         mode = _precision["mode"]
         wf = None
         if mode != 0 and cin > 4:
-            need_dgrad = x.requires_grad and torch.is_grad_enabled()
-            wf, _ = packed_weights(kernel, w3, flip_dgrad, mode, need_dgrad)
+            wf, _ = packed_weights(kernel, w3, flip_dgrad, mode, bool(ctx.needs_input_grad[0]))
         y = spconv_gather(x, fwd, w3, cin, cout, False, False, None if bias is None else bias.detach().contiguous(), wpack=wf)
         ctx.save_for_backward(x, kernel)
         ctx.fwd, ctx.bwd_getter, ctx.has_bias, ctx.flip_dgrad = fwd, bwd_getter, bias is not None, flip_dgrad

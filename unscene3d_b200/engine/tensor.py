@@ -63,7 +63,10 @@ class SparseTensor:
             coords = coords.to(torch.int32)
             if coordinate_manager is None:
                 coordinate_manager = CoordinateManager(coords.shape[1] - 1, dev)
-            coordinate_map_key, first, _ = coordinate_manager.insert(coords, _tuple(tensor_stride, coords.shape[1] - 1))
+            # untouched input rows may be read on the coordinate stream; rows that a conversion kernel just produced on
+            # the compute stream may not
+            coordinate_map_key, first, _ = coordinate_manager.insert(coords, _tuple(tensor_stride, coords.shape[1] - 1),
+                                                                     ready=coords is coordinates)
             if first.shape[0] != features.shape[0]:  # duplicates: keep the first row of each voxel
                 features = features[first.long()]
         else:

@@ -100,7 +100,7 @@ def get_affinity_matrix(feats, tau: float = 0.15, eps: float = 1e-5, painted: Op
 
 
 def _lanczos_top_deflated(matvec, u1: torch.Tensor, max_steps: int, tol: float, seed: int, check_every: int = 20,
-                          min_steps: int = 512, breakdown: float = 1e-10) -> torch.Tensor:
+                          min_steps: int = 512, breakdown: float = 1e-10, info: Optional[dict] = None) -> torch.Tensor:
     """Unit eigenvector of the LARGEST eigenvalue of the symmetric operator `matvec` restricted to the complement of the
     known unit eigenvector `u1` (fp64, full re-orthogonalisation twice per step, u1 included in the basis).
 
@@ -148,12 +148,15 @@ def _lanczos_top_deflated(matvec, u1: torch.Tensor, max_steps: int, tol: float, 
             Q[j + 2] = w / beta[j].clamp_min(1e-300)
     a, b = alpha[:steps].cpu(), beta[:steps].cpu()
     T = torch.diag(a) + torch.diag(b[: steps - 1], 1) + torch.diag(b[: steps - 1], -1)
-    ritz = torch.linalg.eigh(T)[1][:, -1]
+    evals, evecs = torch.linalg.eigh(T)
+    ritz = evecs[:, -1]
+    if info is not None:
+        info.update(steps=steps, beta=b.tolist(), ritz_values=evals[-4:].tolist())
     u = Q[1: steps + 1].T @ ritz.to(dev)
     return u / u.norm()
 
 
-def second_smallest_eigenvector(graph: NCutGraph, max_steps: int = 4096, tol: float = 1e-10, seed: int = 0) -> torch.Tensor:
+def second_smallest_eigenvector(graph: NCutGraph, max_steps: int = 4096, tol: float = 1e-10, seed: int = 0, info: Optional[dict] = None) -> torch.Tensor:
     """Eigenvector of the second smallest eigenvalue of (D - W) v = lambda D v, normalised v^T D v = 1 like
     scipy.linalg.eigh(D - A, D): Lanczos for the largest eigenpair of M = D^-1/2 W D^-1/2 (W x from the bit matrix on
     the device) in the complement of its known leading eigenvector D^1/2 1, then v = D^-1/2 u."""
@@ -170,7 +173,7 @@ def second_smallest_eigenvector(graph: NCutGraph, max_steps: int = 4096, tol: fl
 
     u1 = graph.degree.sqrt()
     u1 = u1 / u1.norm()
-    return dinv * _lanczos_top_deflated(matvec, u1, max_steps, tol, seed)
+    return dinv * _lanczos_top_deflated(matvec, u1, max_steps, tol, seed, info=info)
 
 
 def separate_segments(bipartition: np.ndarray, vec: np.ndarray, unique_segments: torch.Tensor, seg_connectivity: torch.Tensor, mode: str = "max"):
