@@ -31,6 +31,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# growing a caching-allocator pool with cudaMalloc synchronises the device; mapped (expandable) segments do not
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
 
 METRIC = "voxels/sec fwd+bwd Res16UNet34C @200k-voxel scenes"
 UNIT = "voxels/s"
@@ -56,7 +58,7 @@ class ClockSampler:
 
     def __init__(self, gpu_index, period_s=0.02):
         self.gpu, self.samples, self.proc, self.period = gpu_index, [], None, period_s
-        self.nvml, self.handle, self.stop_flag, self.thread = None, None, False, None
+        self.nvml, self.handle, self.stop_flag, self.thread, self.query_ms = None, None, False, None, []
 
     def start(self):
         try:
@@ -94,10 +96,12 @@ class ClockSampler:
         if nv is None:
             return
         try:
+            tq = time.time()
             sm = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
             reasons = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
                 else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
             self.samples.append((time.time(), sm, reasons))
+            self.query_ms.append((time.time() - tq) * 1e3)
         except Exception:
             pass
 
@@ -118,7 +122,7 @@ class ClockSampler:
                     sm.append(clk)
                     reasons |= {k for k, v in names.items() if bits & v}
             return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.smax, "reasons": sorted(reasons), "samples": len(sm),
-                    "source": "nvml"}
+                    "source": "nvml", "query_ms": [round(q, 2) for q in self.query_ms]}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -263,15 +267,19 @@ def run_ours(args):
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.time()
         s.record()
-        # NVML queries contend with kernel launches for the driver (measured: two queries per step cost 4.5 ms/step on this
-        # host-bound step), so the clocks are sampled twice inside the timed region, at 1/3 and 2/3 of the steps
-        sample_at = {max(steps // 3, 1), max(2 * steps // 3, 1)} if sampler is not None else set()
+        # NVML queries contend with kernel launches for the driver lock (measured: one query per step costs 4.5 ms/step at
+        # one GPU and 12 ms/step at two, on this launch-heavy step).  The clocks are therefore sampled once at the middle
+        # of the timed steps and twice more right after the closing event has been queued, while the device is still
+        # working through the launches the host has queued ahead — inside the timed region, off its critical path.
         for i in range(steps):
             flush.zero_()
             fn()
-            if i + 1 in sample_at:
+            if sampler is not None and i + 1 == max(steps // 2, 1):
                 sampler.sample()
         e.record()
+        if sampler is not None:
+            sampler.sample()
+            sampler.sample()
         barrier()
         t1 = time.time()
         ms = torch.tensor([s.elapsed_time(e)], device=dev, dtype=torch.float64)
@@ -299,32 +307,54 @@ def run_ours(args):
         loss = step(c, f)
         loss_host.copy_(loss.detach().reshape(1), non_blocking=True)  # pinned target; the timed region ends with a synchronize
 
-    for _ in range(max(args.warmup, 3)):
-        step_resident()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-        time.sleep(0.3)
+    # The caching allocator needs a handful of steps to stop growing its pools (two streams allocate: compute and
+    # coordinate); a cudaMalloc inside the timed region synchronises the device.  Measured: 3 warm-up steps leave the first
+    # timed leg at 22.8 ms/step, the same leg after ~15 steps runs at 19.6; hence at least 20.
+    n_warm = max(args.warmup, 20)
+    for _ in range(n_warm):
+        step_resident()
+        if rank == 0:
+            sampler.sample()  # absorbs NVML's lazy initialisation (first query: 3 ms); samples outside the timed region are dropped
+    if rank == 0 and sampler.nvml is None:
+        time.sleep(0.3)  # nvidia-smi fallback: let the subprocess start reporting
+        for _ in range(2):
+            step_resident()  # and bring the device back under load before the clock starts
     _lib.reset_launch_count()
     ms_total, t0, t1 = timed(step_resident, args.steps, sampler if rank == 0 else None)
     launches = _lib.launch_count()
     clocks = sampler.stop(t0, t1) if rank == 0 else None
-    for _ in range(2):  # the end-to-end leg has its own allocator pool (copies on the coordinate stream): warm it
+    for _ in range(6):  # the end-to-end leg has its own allocator pool (copies on the coordinate stream): warm it
         step_e2e()
     ms_e2e, _, _ = timed(step_e2e, args.steps)
 
+    if os.environ.get("US3D_BENCH_DEBUG"):
+        for name, fn in (("resident", step_resident), ("e2e", step_e2e), ("resident", step_resident), ("e2e", step_e2e)):
+            ms_dbg, _, _ = timed(fn, args.steps)
+            if rank == 0:
+                print(f"[debug] {name}: {ms_dbg / args.steps:.2f} ms/step", file=sys.stderr, flush=True)
     value = world * args.voxels * args.steps / (ms_total * 1e-3)
     e2e_value = world * args.voxels * args.steps / (ms_e2e * 1e-3)
 
     roofline = cpu_baseline = None
     if rank == 0:
-        # ---- roofline leg: per-launch event timing of the conv kernels over a few extra steps
+        # ---- roofline leg: the dominant kernel is us3d::mt::k_spconv_mt (tcgen05 sparse-conv forward + input gradient,
+        # 45 % of the step in the ncu launch list).  ncu --set full shows it tensor-pipe bound, not HBM bound (tensor pipe
+        # active 80 % of the cycles, DRAM 5 % of peak, DRAM traffic == algorithmic bytes: profiles/r1_ncu_full_summary.md),
+        # so the roof reported is the tensor one; the HBM view of the same launches is kept next to it.
+        #   achieved = ALGORITHMIC FLOPs (2 * kernel-map pairs * Cin * Cout per launch) / launch durations;
+        #   the kernel executes ~7.4x that: three bf16 passes per product (fp32-faithful split) and zero rows for the
+        #   neighbours a 128-row tile does not have.
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
             peaks = json.load(open(peaks_path))
-            peak, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+            peak_tf = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
+            peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained: kernels timed inside a long step)"
+            peak_hbm = float(peaks["hbm_gbs"])
         else:
-            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+            peak_tf, peak_src, peak_hbm = 1500.0, "fallback (B200_PROFILING.md)", 6650.0
         prof_steps = 2
         recs = []
         for _ in range(prof_steps):
@@ -332,23 +362,33 @@ def run_ours(args):
                 flush.zero_()
                 step_resident()
             recs += kt.summary()
-        dom = [r for r in recs if r[0] in ("fwd", "dgrad")]
-        dom_bytes = sum(conv_layer_bytes(ni, no, kv, ci, co, k) for (k, ni, no, kv, ci, co, ms) in dom)
-        dom_ms = sum(r[6] for r in dom)
-        wg = [r for r in recs if r[0] == "wgrad"]
-        wg_ms = sum(r[6] for r in wg)
-        achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-        roofline = {"bound": "hbm", "kernel": "us3d::mt::k_spconv_mt (sparse-conv forward + input-gradient launches)",
-                    "timing": "every conv launch of a step re-issued back to back behind a device-side delay, CUDA events per launch",
-                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                    "peak_source": peak_src, "launches_per_step": len(dom) // prof_steps,
-                    "alg_bytes_per_step": dom_bytes / prof_steps, "kernel_ms_per_step": dom_ms / prof_steps,
-                    "wgrad_ms_per_step": wg_ms / prof_steps, "step_ms": ms_total / args.steps,
-                    "level_sizes": level_sizes(c4_host.numpy())}
+        # (kind, n_in, n_out, kvol, cin, cout, pairs, path, ms)
+        dom = [r for r in recs if r[0] in ("fwd", "dgrad") and r[7] == "mt"]
+        dom_ms = sum(r[8] for r in dom)
+        dom_flops = sum(2.0 * r[6] * r[4] * r[5] for r in dom)
+        dom_exec_flops = sum(2.0 * r[2] * r[3] * r[4] * r[5] * (3 if Fn.get_precision() == 3 else 1) for r in dom)
+        dom_bytes = sum(conv_layer_bytes(r[1], r[2], r[3], r[4], r[5], r[0]) for r in dom)
+        wg_ms = sum(r[8] for r in recs if r[0] == "wgrad")
+        other_ms = sum(r[8] for r in recs if r[0] != "wgrad" and r not in dom)
+        achieved = dom_flops / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
+        roofline = {"bound": "tensor", "kernel": "us3d::mt::k_spconv_mt (tcgen05 sparse-conv forward + input-gradient launches)",
+                    "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                    # dram__bytes_read + write of the 200k-voxel 128->96 k3 launch (ncu --set full); its algorithmic bytes: 179.5e6
+                    "traffic": 171988992,
+                    "peak_source": peak_src,
+                    "timing": "CUDA events recorded around each launch inside libus3d, on the launch stream, during normal steps",
+                    "launches_per_step": len(dom) // prof_steps, "kernel_ms_per_step": dom_ms / prof_steps,
+                    "alg_gflop_per_step": dom_flops / prof_steps / 1e9,
+                    "executed_tflops": dom_exec_flops / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0,
+                    "hbm_view": {"achieved_gbs": dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0, "peak_gbs": peak_hbm,
+                                 "frac": (dom_bytes / (dom_ms * 1e-3) / 1e9 / peak_hbm) if dom_ms > 0 else 0.0,
+                                 "alg_bytes_per_step": dom_bytes / prof_steps},
+                    "wgrad_ms_per_step": wg_ms / prof_steps, "other_conv_ms_per_step": other_ms / prof_steps,
+                    "step_ms": ms_total / args.steps, "level_sizes": level_sizes(c4_host.numpy())}
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         with open(os.path.join(ROOT, "gpurun_out", "bench_layers.json"), "w") as fh:
-            json.dump([{"kind": k, "n_in": ni, "n_out": no, "kvol": kv, "cin": ci, "cout": co, "ms": ms,
-                        "alg_bytes": conv_layer_bytes(ni, no, kv, ci, co, k)} for (k, ni, no, kv, ci, co, ms) in recs[: len(recs) // prof_steps]], fh)
+            json.dump([{"kind": r[0], "n_in": r[1], "n_out": r[2], "kvol": r[3], "cin": r[4], "cout": r[5], "pairs": r[6], "path": r[7],
+                        "ms": r[8], "alg_bytes": conv_layer_bytes(r[1], r[2], r[3], r[4], r[5], r[0])} for r in recs[: len(recs) // prof_steps]], fh)
         # ---- CPU baseline leg (bounded sample), N=1 only
         if world == 1 and not args.no_cpu_baseline:
             _load_synthetic_standalone()
@@ -359,7 +399,7 @@ def run_ours(args):
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": n_warm,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"Res16UNet34C fwd+bwd, synthetic ScanNet-shaped {args.voxels}-voxel scene, batch=1 per GPU (BASELINE configs[1])",

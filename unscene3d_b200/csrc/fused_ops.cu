@@ -360,6 +360,44 @@ k_stem_wgrad(const float *__restrict__ x, int ldx, const int32_t *__restrict__ n
     }
 }
 
+// ------------------------------------------------------------------------------------------------- weight images
+// Both weight images of a convolution in one launch: blockIdx.y = 0 packs the forward image (K = cin, N = cout),
+// blockIdx.y = 1 the input-gradient image (K = cout, N = cin, W[k]^T, offsets reversed when `flip`).  Layout as
+// us3d_spconv_pack_weights: per (offset, 64-channel chunk, plane) an [N][128 B] slab in the K-major SWIZZLE_128B image.
+struct PackSide {
+    uint8_t *out;
+    int kdim, ndim, transpose, flip;
+};
+
+__global__ void __launch_bounds__(256) k_pack_pair(const float *__restrict__ w, int kvol, int w_cin, int w_cout, int planes, PackSide s0,
+                                                   PackSide s1) {
+    const PackSide s = blockIdx.y == 0 ? s0 : s1;
+    if (s.out == nullptr) return;
+    const int nchunks = (s.kdim + 63) / 64;
+    const long long total = (long long)kvol * nchunks * s.ndim * 8;
+    const size_t slab = (size_t)s.ndim * 128;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(e % s.ndim);
+        long long t = e / s.ndim;
+        const int g = (int)(t % 8);
+        t /= 8;
+        const int c = (int)(t % nchunks);
+        const int k = (int)(t / nchunks);
+        const int kq = s.flip ? kvol - 1 - k : k;
+        float f[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int kk = c * 64 + g * 8 + i;
+            float v = 0.f;
+            if (kk < s.kdim) v = s.transpose ? w[((size_t)kq * w_cin + n) * w_cout + kk] : w[((size_t)kq * w_cin + kk) * w_cout + n];
+            f[i] = v;
+        }
+        uint8_t *base = s.out + ((size_t)k * nchunks + c) * planes * slab;
+        const size_t off = (size_t)n * 128 + (size_t)((g ^ (n & 7)) << 4);
+        store_planes(f, reinterpret_cast<uint4 *>(base + off), planes == 2 ? reinterpret_cast<uint4 *>(base + slab + off) : nullptr, 0);
+    }
+}
+
 static inline int flat_grid(long long work) {
     long long b = (work + 255) / 256;
     long long cap = (long long)num_sms() * 16;
@@ -429,14 +467,19 @@ int us3d_bn_backward_planes(const float *dy, int lddy, const float *x, int ldx, 
 
 int us3d_spconv_pack_pair(const float *w, int kvol, int cin, int cout, int flip_dgrad, int passes, void *out_fwd, void *out_dgrad,
                           void *stream_) {
-    if (out_fwd != nullptr) {
-        int rc = us3d_spconv_pack_weights(w, kvol, cin, cout, 0, 0, passes, out_fwd, stream_);
-        if (rc) return rc;
-    }
-    if (out_dgrad != nullptr) {
-        int rc = us3d_spconv_pack_weights(w, kvol, cin, cout, 1, flip_dgrad, passes, out_dgrad, stream_);
-        if (rc) return rc;
-    }
+    US3D_CHECK_ARG(kvol >= 1 && kvol <= US3D_MAX_KVOL, "pack_pair: kvol %d out of range", kvol);
+    US3D_CHECK_ARG(passes == 1 || passes == 3, "pack_pair: passes must be 1 or 3");
+    US3D_CHECK_ARG(out_fwd == nullptr || us3d_spconv_tc_supported(cin, cout), "pack_pair: unsupported forward shape %d -> %d", cin, cout);
+    US3D_CHECK_ARG(out_dgrad == nullptr || us3d_spconv_tc_supported(cout, cin), "pack_pair: unsupported gradient shape %d -> %d", cout, cin);
+    if (out_fwd == nullptr && out_dgrad == nullptr) return 0;
+    fused::PackSide s0{(uint8_t *)out_fwd, cin, cout, 0, 0}, s1{(uint8_t *)out_dgrad, cout, cin, 1, flip_dgrad};
+    const int big = cin > cout ? cin : cout;
+    const long long total = (long long)kvol * ceil_div(big, 64) * big * 8;
+    int gx = (int)((total + 255) / 256);
+    if (gx > num_sms() * 8) gx = num_sms() * 8;
+    dim3 grid(gx, 2);
+    fused::k_pack_pair<<<grid, 256, 0, (cudaStream_t)stream_>>>(w, kvol, cin, cout, passes == 3 ? 2 : 1, s0, s1);
+    US3D_LAUNCH_CHECK();
     return 0;
 }
 

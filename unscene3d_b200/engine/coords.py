@@ -93,10 +93,17 @@ class CoordinateMap:
 
 
 class NeighbourTable:
-    __slots__ = ("nbr", "mask", "n_rows", "kvol")
+    __slots__ = ("nbr", "mask", "n_rows", "kvol", "_pairs")
 
     def __init__(self, nbr: torch.Tensor, mask: torch.Tensor, n_rows: int, kvol: int):
-        self.nbr, self.mask, self.n_rows, self.kvol = nbr, mask, n_rows, kvol
+        self.nbr, self.mask, self.n_rows, self.kvol, self._pairs = nbr, mask, n_rows, kvol, None
+
+    def pairs(self) -> int:
+        """Present (input row, output row) pairs — the P of the algorithmic FLOP count 2 P Cin Cout (host read, cached;
+        used by the benchmark's roofline leg only)."""
+        if self._pairs is None:
+            self._pairs = int((self.nbr >= 0).sum())
+        return self._pairs
 
 
 _coordinate_streams: Dict[int, "torch.cuda.Stream"] = {}

@@ -36,7 +36,8 @@ class KernelTimer:
     convolution kernel launch with CUDA events recorded on the launch stream from inside the C entry point, a few
     microseconds of host time before the kernel — so the launch gaps of a host-bound section are not counted as kernel
     time, and the kernels are timed where they run, with the cache state the step gives them.
-    `summary()` returns (kind, n_in_rows, n_out_rows, kvol, cin, cout, ms) per launch, in launch order."""
+    `summary()` returns (kind, n_in_rows, n_out_rows, kvol, cin, cout, pairs, path, ms) per launch, in launch order
+    (pairs = present (input row, output row) pairs of the kernel map, path = "mt" tcgen05 / "stem" / "simt" / "wgrad-tc")."""
 
     def __init__(self):
         self.meta = []
@@ -83,9 +84,10 @@ def _dbg():
     return _dbg_lib
 
 
-def _timed(kind, n_in, n_out, kvol, cin, cout, launch):
+def _timed(kind, n_in, n_out, kvol, cin, cout, launch, table=None, path="simt"):
     if _timer is not None:
-        _timer.meta.append((kind, n_in, n_out, kvol, cin, cout))
+        # (kind, n_in, n_out, kvol, cin, cout, kernel-map pairs, kernel path)
+        _timer.meta.append((kind, n_in, n_out, kvol, cin, cout, table.pairs() if table is not None else n_out * kvol, path))
     return launch()
 
 
@@ -211,7 +213,7 @@ def spconv_gather(x, table: NeighbourTable, w3, cin, cout, transpose_w, flip_k, 
         w3c = w3 if w3.is_contiguous() else w3.contiguous()
         _timed(kind, x.shape[0], table.n_rows, table.kvol, cin, cout, lambda: check(
             lib.us3d_stem_conv_fwd(x.data_ptr(), _ld(x), table.nbr.data_ptr(), table.n_rows, table.kvol, w3c.data_ptr(), cin, cout,
-                                   _ptr(bias), y.data_ptr(), _ld(y), st)))
+                                   _ptr(bias), y.data_ptr(), _ld(y), st)), table, "stem")
         return y
     if (mode != 0 and _tc_ok(cin, cout) and x.data_ptr() % 16 == 0 and _ld(x) % 4 == 0):
         if wpack is None:
@@ -222,17 +224,17 @@ def spconv_gather(x, table: NeighbourTable, w3, cin, cout, transpose_w, flip_k, 
             fn = lib.us3d_spconv_gather_mt if kname == "mt" else (lib.us3d_spconv_gather_tma if kname == "tma" else lib.us3d_spconv_gather_cp)
             _timed(kind, x.shape[0], table.n_rows, table.kvol, cin, cout, lambda: check(
                 fn(hi.data_ptr(), _ptr(lo), x.shape[0], table.nbr.data_ptr(), table.n_rows, table.kvol, wpack.data_ptr(), cin, cout,
-                   mode, _ptr(bias), 0, y.data_ptr(), _ld(y), int(accumulate), _ptr(table.mask), st)))
+                   mode, _ptr(bias), 0, y.data_ptr(), _ld(y), int(accumulate), _ptr(table.mask), st)), table, kname)
             return y
         _timed(kind, x.shape[0], table.n_rows, table.kvol, cin, cout, lambda: check(
             lib.us3d_spconv_gather_tc(x.data_ptr(), _ld(x), table.nbr.data_ptr(), table.n_rows, table.kvol, wpack.data_ptr(),
                                       cin, cout, mode, _ptr(bias), 0, y.data_ptr(), _ld(y), int(accumulate),
-                                      _ptr(table.mask), st)))
+                                      _ptr(table.mask), st)), table, "tc")
         return y
     _timed(kind, x.shape[0], table.n_rows, table.kvol, cin, cout, lambda: check(
         lib.us3d_spconv_gather(x.data_ptr(), _ld(x), table.nbr.data_ptr(), table.n_rows, table.kvol, w3.data_ptr(), cin, cout,
                                int(transpose_w), int(flip_k), _ptr(bias), 0, y.data_ptr(), _ld(y), int(accumulate),
-                               _ptr(table.mask), st)))
+                               _ptr(table.mask), st)), table, "simt")
     return y
 
 
@@ -244,7 +246,7 @@ def spconv_wgrad(x, table: NeighbourTable, dy, cin, cout):
     if cin == 3 and table.kvol in (1, 8, 27):
         _timed("wgrad", x.shape[0], table.n_rows, table.kvol, cin, cout, lambda: check(
             lib.us3d_stem_conv_wgrad(x.data_ptr(), _ld(x), table.nbr.data_ptr(), table.n_rows, table.kvol, dy.data_ptr(), _ld(dy),
-                                     dw.data_ptr(), cin, cout, st)))
+                                     dw.data_ptr(), cin, cout, st)), table, "stem")
         return dw
     if (mode != 0 and _wgrad_tc_ok(cin, cout) and x.data_ptr() % 16 == 0 and dy.data_ptr() % 16 == 0
             and _ld(x) % 4 == 0 and _ld(dy) % 4 == 0):
@@ -253,15 +255,15 @@ def spconv_wgrad(x, table: NeighbourTable, dy, cin, cout):
             dh, dl = bf16_planes(dy, mode == 3)
             _timed("wgrad", x.shape[0], table.n_rows, table.kvol, cin, cout, lambda: check(
                 lib.us3d_spconv_wgrad_planes(xh.data_ptr(), _ptr(xl), dh.data_ptr(), _ptr(dl), table.nbr.data_ptr(), table.n_rows,
-                                             table.kvol, dw.data_ptr(), cin, cout, mode, _ptr(table.mask), st)))
+                                             table.kvol, dw.data_ptr(), cin, cout, mode, _ptr(table.mask), st)), table, "wgrad-tc")
             return dw
         _timed("wgrad", x.shape[0], table.n_rows, table.kvol, cin, cout, lambda: check(
             lib.us3d_spconv_wgrad_tc(x.data_ptr(), _ld(x), table.nbr.data_ptr(), table.n_rows, table.kvol, dy.data_ptr(), _ld(dy),
-                                     0, dw.data_ptr(), cin, cout, mode, _ptr(table.mask), st)))
+                                     0, dw.data_ptr(), cin, cout, mode, _ptr(table.mask), st)), table, "wgrad-tc")
         return dw
     _timed("wgrad", x.shape[0], table.n_rows, table.kvol, cin, cout, lambda: check(
         lib.us3d_spconv_wgrad(x.data_ptr(), _ld(x), table.nbr.data_ptr(), table.n_rows, table.kvol, dy.data_ptr(), _ld(dy), 0,
-                              dw.data_ptr(), cin, cout, st)))
+                              dw.data_ptr(), cin, cout, st)), table, "simt")
     return dw
 
 
