@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define US3D_ABI_VERSION 6
+#define US3D_ABI_VERSION 7
 #define US3D_MAX_KVOL 27
 
 int us3d_abi_version(void);
@@ -218,6 +218,23 @@ int us3d_segment_mean_f64(const float *src, const int64_t *index, int n, int c, 
                           void *stream);
 int us3d_segment_mean_bwd(const float *dout, const int64_t *index, const float *count, int n, int c, float *dsrc,
                           void *stream);
+
+/* Masked multi-head cross-attention core of the decoder (nn.MultiheadAttention inside CrossAttentionLayer,
+ * models/mask3d.py:561-651, called at models/mask3d.py:355-365): out = softmax(scale * q k^T, hidden keys removed) v per
+ * (scene, head).  q [nq, b, h*head_dim], k / v [nk, b, h*head_dim] and out / dout / dq / dk / dv alike: fp32, contiguous,
+ * sequence-first as the reference passes them (already projected).  mask: uint8 / bool, non-zero = key hidden from query
+ * (the reference's memory_mask), element (scene, head, query, key) at mask[scene*sb + head*sh + query*sq + key*sk] — the
+ * decoder's own [b, nk, nq] tensor is passed with sh = 0, the reference layout [b*h, nq, nk] with sb = h*nq*nk; NULL = no
+ * mask.  lse [b, h, nq] receives the row log-sum-exp (saved for backward).  ws: us3d_xattn_workspace_bytes() bytes.
+ * Nothing of size nq x nk is written; no atomics (run-to-run deterministic).  head_dim 16 or 32.
+ * A query whose keys are all hidden yields NaN, as torch's softmax does (the decoder un-hides such rows, mask3d.py:349). */
+long long us3d_xattn_workspace_bytes(int b, int h, int nq, int nk, int head_dim);
+int us3d_xattn_fwd(const float *q, const float *k, const float *v, const uint8_t *mask, long long mask_sb, long long mask_sh,
+                   long long mask_sq, long long mask_sk, int b, int h, int nq, int nk, int head_dim, float scale, float *ws,
+                   float *out, float *lse, void *stream);
+int us3d_xattn_bwd(const float *q, const float *k, const float *v, const uint8_t *mask, long long mask_sb, long long mask_sh,
+                   long long mask_sq, long long mask_sk, const float *out, const float *lse, const float *dout, int b, int h,
+                   int nq, int nk, int head_dim, float scale, float *ws, float *dq, float *dk, float *dv, void *stream);
 
 /* Hungarian matcher cost (models/matcher.py:97-168):  C[q,t] = w_mask * BCE + w_class * (-p[q, label_t])
  * + w_dice * dice,  logits[s,q] (pred_masks[b], row = segment/point), tgt[t,s] float {0,1},

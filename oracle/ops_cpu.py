@@ -101,6 +101,31 @@ def _scatter_minmax(src, index, dim, reduce):
     return out, None
 
 
+def multihead_cross_attention(mha, query, key, value, attn_mask=None):
+    """What the reference's CrossAttentionLayer executes (models/mask3d.py:561-651): nn.MultiheadAttention itself, with the
+    boolean memory_mask (True = hidden) in torch's [B*h, Q, K] layout."""
+    if hasattr(attn_mask, "torch_layout"):  # the decoder's own [B,K,Q] tensor (unscene3d_b200 models): expand as mask3d.py:358 does
+        attn_mask = attn_mask.torch_layout(mha.num_heads)
+    return mha(query=query, key=key, value=value, attn_mask=attn_mask, key_padding_mask=None)[0]
+
+
+def masked_attention_core(q, k, v, mask_bhqk, num_heads):
+    """Explicit restatement of the attention core on projected tensors: q [Q,B,E], k / v [K,B,E], mask [B,h,Q,K] bool
+    (True = hidden) -> [Q,B,E]; softmax(q k^T / sqrt(head_dim)) v per (scene, head) as torch's
+    multi_head_attention_forward computes it.  Differentiable (float64 capable)."""
+    Q, B, E = q.shape
+    K = k.shape[0]
+    hd = E // num_heads
+    qh = q.reshape(Q, B, num_heads, hd).permute(1, 2, 0, 3)
+    kh = k.reshape(K, B, num_heads, hd).permute(1, 2, 0, 3)
+    vh = v.reshape(K, B, num_heads, hd).permute(1, 2, 0, 3)
+    s = (qh @ kh.transpose(-1, -2)) * (float(hd) ** -0.5)
+    if mask_bhqk is not None:
+        s = s.masked_fill(mask_bhqk, float("-inf"))
+    o = torch.softmax(s, dim=-1) @ vh  # [B,h,Q,hd]
+    return o.permute(2, 0, 1, 3).reshape(Q, B, E)
+
+
 def as_module_tree():
     """Module objects `torch_scatter`, `pointnet2`, `pointnet2._ext` exporting the CPU restatements."""
     import types

@@ -78,7 +78,11 @@ def load_package(pkg_dir: str, alias: str, me_modules: dict):
 
 
 def our_models_on_oracle():
-    return load_package(os.path.join(REPO, "unscene3d_b200", "models"), "oracle_backed_models", oracle_me_modules())
+    from oracle import ops_cpu
+
+    mod = load_package(os.path.join(REPO, "unscene3d_b200", "models"), "oracle_backed_models", oracle_me_modules())
+    mod.mask3d.CrossAttentionLayer.attention_core = staticmethod(ops_cpu.multihead_cross_attention)
+    return mod
 
 
 def have_reference() -> bool:

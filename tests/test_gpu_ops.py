@@ -367,16 +367,31 @@ def test_relu_add_cat_pool(eng, ora):
 
 
 # --------------------------------------------------------------------------------------------- decoder helpers
-@pytest.mark.parametrize("n,m", [(5, 3), (31, 10), (100, 100), (777, 100), (5000, 100)])
-def test_fps_indices_bit_exact_on_integer_coords(eng, n, m):
+# n chosen to cover every residency tier of the cluster kernel: one CTA (<= 8192 rows), 2..16 CTAs with all rows in
+# registers (<= 131072), rows in shared memory (<= 327680), rows streamed from L2 beyond that
+@pytest.mark.parametrize("n,m,span", [(1, 1, 8), (5, 3, 8), (31, 10, 8), (100, 100, 8), (777, 100, 8), (5000, 100, 8), (20000, 60, 20),
+                                      (131072, 40, 40), (200000, 100, 150), (340000, 30, 60)])
+def test_fps_indices_bit_exact_on_integer_coords(eng, n, m, span):
     from oracle import ops_cpu
     from unscene3d_b200.engine import functional as Fn
 
     rng = np.random.default_rng(n)
-    pts = rng.integers(-8, 9, size=(2, n, 3)).astype(np.float32)  # many exact distance ties, some |p|^2 = 0
+    pts = rng.integers(-span, span + 1, size=(2, n, 3)).astype(np.float32)  # many exact distance ties, some |p|^2 = 0
+    temp_probe = n >= 20000
     got = Fn.furthest_point_sampling(torch.from_numpy(pts).cuda(), m).cpu().numpy()
     for b in range(2):
         assert np.array_equal(got[b], ops_cpu.furthest_point_sampling(pts[b], m))
+    if temp_probe:  # run-to-run identical (no atomics, fixed reduction order)
+        again = Fn.furthest_point_sampling(torch.from_numpy(pts).cuda(), m).cpu().numpy()
+        assert np.array_equal(got, again)
+
+
+def test_fps_all_rows_skipped_returns_row_zero(eng):
+    """Rows with |p|^2 <= 1e-3 never win (sampling_gpu.cu:103-104): a scene of such rows yields index 0 throughout."""
+    from unscene3d_b200.engine import functional as Fn
+
+    pts = torch.zeros(1, 700, 3).cuda()
+    assert torch.equal(Fn.furthest_point_sampling(pts, 7).cpu(), torch.zeros(1, 7, dtype=torch.int32))
 
 
 def test_segment_mean(eng):

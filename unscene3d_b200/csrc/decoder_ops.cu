@@ -1,6 +1,10 @@
 // Mask-decoder / matcher helpers: furthest point sampling, segment mean,
 // Hungarian cost matrix.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace us3d {
 
@@ -15,67 +19,161 @@ namespace us3d {
 //     position on ties.  Two tied slots first meet at h = lowest set bit of (a xor b) and the one whose
 //     bit h is clear survives, i.e. the winner is the tied slot with the smallest BIT-REVERSED index.
 //     That is a total order, so any reduction shape that uses the comparator below gives the same row.
-struct Cand {
-    float d;
-    int i;
-    unsigned rslot;  // __brev(thread slot)
+//
+// B200 formulation: one thread-block CLUSTER per scene (up to 16 CTAs x 512 threads).  Every row lives on chip for
+// the whole sampling loop — 16 rows per thread in registers (x, y, z, running distance), further rows as float4 in
+// shared memory, and only what exceeds ~333k rows per scene is streamed from L2 — so a sampling round is a few
+// FMAs per row plus one cluster barrier instead of a pass of one CTA over the whole scene.  The winner of a
+// round is the maximum of a 64-bit key
+//     [ bits(min-distance) + 1 | ~( bitrev(slot) : row / T ) ]          (0 = "slot saw no valid row", as best = -1)
+// which orders candidates exactly like the reference's scan + tree; each CTA posts its best key together with
+// the row's coordinates into every peer's shared memory (DSMEM), so the next round starts without a global load.
+constexpr int kFpsThreads = 512;
+constexpr int kFpsRegRows = 16;          // rows per thread kept in registers
+constexpr int kFpsMaxSmemSlots = 24;     // rows per thread kept in shared memory (24 * 512 * 16 B = 192 KB)
+
+struct __align__(16) FpsRec {
+    unsigned long long key;
+    float x, y, z;
+    int pad;
 };
 
-__device__ __forceinline__ Cand fps_better(Cand a, Cand b) {
-    if (a.d != b.d) return a.d > b.d ? a : b;
-    return a.rslot <= b.rslot ? a : b;
+__device__ __forceinline__ unsigned fps_tie(int k, int lt) {
+    // smaller = preferred on equal distance: bit-reversed slot (k mod T) first, then the earlier row of the slot
+    unsigned slot = (unsigned)k & ((1u << lt) - 1u);
+    unsigned r = lt ? (__brev(slot) >> (32 - lt)) : 0u;
+    return (r << 22) | ((unsigned)k >> lt);
+}
+__device__ __forceinline__ int fps_row_of(unsigned tie, int lt) {
+    unsigned r = tie >> 22, q = tie & ((1u << 22) - 1u);
+    unsigned slot = lt ? (__brev(r) >> (32 - lt)) : 0u;
+    return (int)((q << lt) | slot);
 }
 
-__global__ void __launch_bounds__(512) k_fps(const float *__restrict__ xyz, int n, int m, int T, float *__restrict__ temp,
-                                             int32_t *__restrict__ idx) {
-    if (m <= 0) return;
-    __shared__ float sd[16];
-    __shared__ int si[16];
-    __shared__ unsigned sr[16];
-    __shared__ int s_old;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = (blockDim.x + 31) >> 5;
-    xyz += (size_t)blockIdx.x * n * 3;
-    temp += (size_t)blockIdx.x * n;
-    idx += (size_t)blockIdx.x * m;
-    int old = 0;
-    if (tid == 0) idx[0] = 0;
-    for (int j = 1; j < m; ++j) {
-        Cand c{tid < T ? -1.f : -3.f, 0, __brev((unsigned)tid)};
-        const float x1 = xyz[old * 3 + 0], y1 = xyz[old * 3 + 1], z1 = xyz[old * 3 + 2];
-        if (tid < T)
-            for (int k = tid; k < n; k += T) {
-                float x2 = xyz[k * 3 + 0], y2 = xyz[k * 3 + 1], z2 = xyz[k * 3 + 2];
-                float mag = (x2 * x2) + (y2 * y2) + (z2 * z2);
-                if ((double)mag <= 1e-3) continue;
-                float d = (x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1) + (z2 - z1) * (z2 - z1);
-                float d2 = fminf(d, temp[k]);
-                temp[k] = d2;
-                if (d2 > c.d) {
-                    c.d = d2;
-                    c.i = k;
-                }
-            }
+// max over the warp of a 64-bit key; returns the lowest lane holding it
+__device__ __forceinline__ int fps_warp_argmax(unsigned long long key, unsigned long long &best) {
+    unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+    unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+    unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    unsigned who = __ballot_sync(0xffffffffu, hi == mh && lo == ml);
+    best = ((unsigned long long)mh << 32) | ml;
+    return __ffs(who) - 1;
+}
+
+__global__ void __launch_bounds__(kFpsThreads, 1)
+k_fps_cluster(const float *__restrict__ xyz, int n, int m, int lt, int smem_slots, float *__restrict__ temp,
+              int32_t *__restrict__ idx) {
+    extern __shared__ float4 s_rows[];  // [smem_slots][kFpsThreads]
+    __shared__ FpsRec s_warp[kFpsThreads / 32];
+    __shared__ FpsRec s_cta[2][16];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int stride = C * kFpsThreads, g = rank * kFpsThreads + tid;
+    xyz += (size_t)blockIdx.y * n * 3;
+    temp += (size_t)blockIdx.y * n;
+    idx += (size_t)blockIdx.y * m;
+
+    // ---- load the rows this thread owns: row(i) = i * stride + g
+    float rx[kFpsRegRows], ry[kFpsRegRows], rz[kFpsRegRows], rt[kFpsRegRows];
+    unsigned valid = 0;
 #pragma unroll
-        for (int h = 16; h >= 1; h >>= 1) {
-            Cand o{__shfl_xor_sync(0xffffffffu, c.d, h), __shfl_xor_sync(0xffffffffu, c.i, h),
-                   __shfl_xor_sync(0xffffffffu, c.rslot, h)};
-            c = fps_better(c, o);
+    for (int i = 0; i < kFpsRegRows; ++i) {
+        int k = i * stride + g;
+        rx[i] = ry[i] = rz[i] = 0.f;
+        rt[i] = 0.f;
+        if (k < n) {
+            rx[i] = xyz[(size_t)k * 3 + 0], ry[i] = xyz[(size_t)k * 3 + 1], rz[i] = xyz[(size_t)k * 3 + 2];
+            rt[i] = temp[k];
+            float mag = (rx[i] * rx[i]) + (ry[i] * ry[i]) + (rz[i] * rz[i]);
+            if (!((double)mag <= 1e-3)) valid |= 1u << i;
         }
-        if (lane == 0) {
-            sd[warp] = c.d;
-            si[warp] = c.i;
-            sr[warp] = c.rslot;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            Cand w{sd[0], si[0], sr[0]};
-            for (int q = 1; q < nwarps; ++q) w = fps_better(w, Cand{sd[q], si[q], sr[q]});
-            s_old = w.i;
-            idx[j] = w.i;
-        }
-        __syncthreads();
-        old = s_old;
     }
+    for (int j = 0; j < smem_slots; ++j) {
+        int k = (kFpsRegRows + j) * stride + g;
+        float4 v = make_float4(0.f, 0.f, 0.f, -1.f);  // w < 0: no row / skipped row (distances are >= 0)
+        if (k < n) {
+            v.x = xyz[(size_t)k * 3 + 0], v.y = xyz[(size_t)k * 3 + 1], v.z = xyz[(size_t)k * 3 + 2];
+            float mag = (v.x * v.x) + (v.y * v.y) + (v.z * v.z);
+            if (!((double)mag <= 1e-3)) v.w = temp[k];
+        }
+        s_rows[j * kFpsThreads + tid] = v;
+    }
+    const int k_stream0 = (kFpsRegRows + smem_slots) * stride + g;  // rows beyond the on-chip capacity
+
+    float x1 = xyz[0], y1 = xyz[1], z1 = xyz[2];
+    if (g == 0) idx[0] = 0;
+    for (int j = 1; j < m; ++j) {
+        unsigned long long best = 0ull;
+        float bx = 0.f, by = 0.f, bz = 0.f;
+#pragma unroll
+        for (int i = 0; i < kFpsRegRows; ++i) {
+            if (valid >> i & 1u) {
+                float d = (rx[i] - x1) * (rx[i] - x1) + (ry[i] - y1) * (ry[i] - y1) + (rz[i] - z1) * (rz[i] - z1);
+                float d2 = fminf(d, rt[i]);
+                rt[i] = d2;
+                unsigned long long key =
+                    ((unsigned long long)(__float_as_uint(d2) + 1u) << 32) | (0xffffffffu - fps_tie(i * stride + g, lt));
+                if (key > best) best = key, bx = rx[i], by = ry[i], bz = rz[i];
+            }
+        }
+        for (int s = 0; s < smem_slots; ++s) {
+            float4 v = s_rows[s * kFpsThreads + tid];
+            if (v.w >= 0.f) {
+                float d = (v.x - x1) * (v.x - x1) + (v.y - y1) * (v.y - y1) + (v.z - z1) * (v.z - z1);
+                float d2 = fminf(d, v.w);
+                s_rows[s * kFpsThreads + tid].w = d2;
+                unsigned long long key = ((unsigned long long)(__float_as_uint(d2) + 1u) << 32) |
+                                         (0xffffffffu - fps_tie((kFpsRegRows + s) * stride + g, lt));
+                if (key > best) best = key, bx = v.x, by = v.y, bz = v.z;
+            }
+        }
+        for (int k = k_stream0; k < n; k += stride) {
+            float x2 = xyz[(size_t)k * 3 + 0], y2 = xyz[(size_t)k * 3 + 1], z2 = xyz[(size_t)k * 3 + 2];
+            float mag = (x2 * x2) + (y2 * y2) + (z2 * z2);
+            if ((double)mag <= 1e-3) continue;
+            float d = (x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1) + (z2 - z1) * (z2 - z1);
+            float d2 = fminf(d, temp[k]);
+            temp[k] = d2;
+            unsigned long long key = ((unsigned long long)(__float_as_uint(d2) + 1u) << 32) | (0xffffffffu - fps_tie(k, lt));
+            if (key > best) best = key, bx = x2, by = y2, bz = z2;
+        }
+        // ---- warp -> CTA -> cluster
+        unsigned long long wbest;
+        int wl = fps_warp_argmax(best, wbest);
+        if (lane == wl) s_warp[warp] = FpsRec{best, bx, by, bz, 0};
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long cbest;
+            int ww = fps_warp_argmax(s_warp[lane & (kFpsThreads / 32 - 1)].key, cbest);
+            FpsRec rec = s_warp[ww];
+            if (lane < C) *cluster.map_shared_rank(&s_cta[j & 1][rank], lane) = rec;
+        }
+        cluster.sync();
+        unsigned long long gbest;
+        int wc = fps_warp_argmax(s_cta[j & 1][lane & (C - 1)].key, gbest);
+        FpsRec win = s_cta[j & 1][wc];
+        int old = 0;
+        if ((unsigned)(gbest >> 32) == 0u) {  // no valid row anywhere: the reference's tree returns index 0
+            x1 = xyz[0], y1 = xyz[1], z1 = xyz[2];
+        } else {
+            old = fps_row_of(0xffffffffu - (unsigned)gbest, lt);
+            x1 = win.x, y1 = win.y, z1 = win.z;
+        }
+        if (g == 0) idx[j] = old;
+    }
+    // ---- the running distances are an in/out argument of the reference op
+#pragma unroll
+    for (int i = 0; i < kFpsRegRows; ++i) {
+        int k = i * stride + g;
+        if (k < n) temp[k] = rt[i];
+    }
+    for (int s = 0; s < smem_slots; ++s) {
+        int k = (kFpsRegRows + s) * stride + g;
+        float w = s_rows[s * kFpsThreads + tid].w;
+        if (k < n && w >= 0.f) temp[k] = w;
+    }
+    cluster.sync();  // no CTA may exit while a peer can still write into its shared memory
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -186,9 +284,33 @@ extern "C" {
 int us3d_furthest_point_sampling(const float *xyz, int b, int n, int m, float *temp, int32_t *idx, void *stream_) {
     US3D_CHECK_ARG(b >= 0 && n > 0 && m >= 0, "fps: bad shape");
     if (b == 0 || m == 0) return 0;
-    int slots = 1;
-    while (slots * 2 <= n && slots < 512) slots *= 2;  // opt_n_threads of the reference (cuda_utils.h:15-21)
-    k_fps<<<b, slots < 32 ? 32 : slots, 0, (cudaStream_t)stream_>>>(xyz, n, m, slots, temp, idx);
+    int lt = 0;
+    while ((2 << lt) <= n && lt < 9) ++lt;  // T = 2^lt slots = opt_n_threads of the reference (cuda_utils.h:15-21)
+    static int max_cluster = 0;
+    if (!max_cluster) {
+        max_cluster = cudaFuncSetAttribute(k_fps_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess ? 16 : 8;
+        US3D_CUDA(cudaFuncSetAttribute(k_fps_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kFpsMaxSmemSlots * kFpsThreads * (int)sizeof(float4)));
+        cudaGetLastError();
+    }
+    int C = 1;
+    while (C < max_cluster && (long long)C * kFpsThreads * kFpsRegRows < n) C *= 2;
+    long long in_regs = (long long)C * kFpsThreads * kFpsRegRows;
+    int smem_slots = n > in_regs ? (int)((n - in_regs + (long long)C * kFpsThreads - 1) / ((long long)C * kFpsThreads)) : 0;
+    if (smem_slots > kFpsMaxSmemSlots) smem_slots = kFpsMaxSmemSlots;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(C, b, 1);
+    cfg.blockDim = dim3(kFpsThreads, 1, 1);
+    cfg.dynamicSmemBytes = (size_t)smem_slots * kFpsThreads * sizeof(float4);
+    cfg.stream = (cudaStream_t)stream_;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    US3D_CUDA(cudaLaunchKernelEx(&cfg, k_fps_cluster, xyz, n, m, lt, smem_slots, temp, idx));
     US3D_LAUNCH_CHECK();
     return 0;
 }

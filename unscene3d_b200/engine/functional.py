@@ -552,3 +552,92 @@ def matcher_cost(logits_sq, tgt_ts, prob_qc, labels_t, w_class, w_mask, w_dice):
     check(lib.us3d_matcher_cost(logits_sq.data_ptr(), S, Q, tgt_ts.data_ptr(), T, prob_qc.data_ptr(), prob_qc.shape[1],
                                 labels_t.data_ptr(), float(w_class), float(w_mask), float(w_dice), cost.data_ptr(), _stream()))
     return cost
+
+
+# ------------------------------------------------------------------------------------------- decoder cross-attention
+class DecoderMask:
+    """The decoder's attention mask as it is built, [B, K, Q] bool with True = hidden and shared by all heads
+    (models/mask3d.py:338-349), i.e. BEFORE the reference's repeat_interleave(num_heads) + permute to [B*h, Q, K]
+    (:358).  The kernels read it in place; `torch_layout` gives what nn.MultiheadAttention would need."""
+
+    def __init__(self, bkq: torch.Tensor):
+        self.bkq = bkq
+
+    def torch_layout(self, num_heads: int) -> torch.Tensor:
+        return self.bkq.repeat_interleave(num_heads, dim=0).permute((0, 2, 1))
+
+
+def _mask_view(mask, B, H, Q, K):
+    """(pointer-holding tensor, batch/head/query/key strides in elements) of a boolean attention mask given either as the
+    decoder's own [B, K, Q] tensor (models/mask3d.py:338-349, before its repeat_interleave + permute) or in
+    nn.MultiheadAttention's layouts [Q, K] / [B*H, Q, K] (any strides: a permuted or expanded view is read in place)."""
+    if mask is None:
+        return None, (0, 0, 0, 0)
+    if hasattr(mask, "bkq"):
+        m = mask.bkq
+        if m.dtype != torch.bool or tuple(m.shape) != (B, K, Q):
+            raise RuntimeError(f"masked_cross_attention: decoder mask must be bool [B,K,Q] = {(B, K, Q)}, got {m.dtype} {tuple(m.shape)}")
+        m = m.view(torch.uint8)
+        return m, (m.stride(0), 0, m.stride(2), m.stride(1))
+    if mask.dtype != torch.bool and mask.dtype != torch.uint8:
+        raise RuntimeError("masked_cross_attention: only boolean masks (True = hidden) are supported")
+    if mask.dtype == torch.bool:
+        mask = mask.view(torch.uint8)
+    if mask.ndim == 2 and tuple(mask.shape) == (Q, K):
+        return mask, (0, 0, mask.stride(0), mask.stride(1))
+    if mask.ndim == 3 and tuple(mask.shape) == (B * H, Q, K):
+        return mask, (H * mask.stride(0), mask.stride(0), mask.stride(1), mask.stride(2))
+    raise RuntimeError(f"masked_cross_attention: mask shape {tuple(mask.shape)} is neither [Q,K] nor [B*H,Q,K]")
+
+
+class MaskedCrossAttentionFunction(torch.autograd.Function):
+    """softmax(scale * q k^T + mask) v per (scene, head) on projected q [Q,B,E], k / v [K,B,E] (csrc/attention.cu)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, mask, num_heads):
+        if not q.is_cuda:
+            raise RuntimeError("unscene3d_b200 operators run on CUDA tensors only (no CPU fallback)")
+        q, k, v = q.float().contiguous(), k.float().contiguous(), v.float().contiguous()
+        Q, B, E = q.shape
+        K = k.shape[0]
+        hd = E // num_heads
+        scale = float(hd) ** -0.5
+        mview, ms = _mask_view(mask, B, num_heads, Q, K)
+        ws = torch.empty(int(lib.us3d_xattn_workspace_bytes(B, num_heads, Q, K, hd)) // 4, dtype=torch.float32, device=q.device)
+        out = torch.empty_like(q)
+        lse = torch.empty((B, num_heads, Q), dtype=torch.float32, device=q.device)
+        check(lib.us3d_xattn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), _ptr(mview), *ms, B, num_heads, Q, K, hd, scale,
+                                 ws.data_ptr(), out.data_ptr(), lse.data_ptr(), _stream()))
+        ctx.save_for_backward(q, k, v, out, lse)
+        ctx.mask, ctx.ms, ctx.dims = mview, ms, (B, num_heads, Q, K, hd, scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, k, v, out, lse = ctx.saved_tensors
+        B, H, Q, K, hd, scale = ctx.dims
+        dout = dout.float().contiguous()
+        ws = torch.empty(int(lib.us3d_xattn_workspace_bytes(B, H, Q, K, hd)) // 4, dtype=torch.float32, device=q.device)
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        check(lib.us3d_xattn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), _ptr(ctx.mask), *ctx.ms, out.data_ptr(), lse.data_ptr(),
+                                 dout.data_ptr(), B, H, Q, K, hd, scale, ws.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
+                                 _stream()))
+        return dq, dk, dv, None, None
+
+
+def multihead_cross_attention(mha: torch.nn.MultiheadAttention, query, key, value, attn_mask=None):
+    """`mha(query, key, value, attn_mask=attn_mask)[0]` for a sequence-first nn.MultiheadAttention with a boolean mask —
+    same parameters (`in_proj_weight`, `in_proj_bias`, `out_proj`), so state dicts are interchangeable; the three input
+    projections and the output projection are library GEMMs, the attention core is the libus3d kernel."""
+    if mha.batch_first or not mha._qkv_same_embed_dim or mha.bias_k is not None or mha.add_zero_attn:
+        raise RuntimeError("multihead_cross_attention: unsupported nn.MultiheadAttention configuration")
+    if mha.dropout > 0.0 and mha.training:
+        raise RuntimeError("multihead_cross_attention: attention dropout is not implemented (every shipped config uses 0.0)")
+    E = mha.embed_dim
+    w, b = mha.in_proj_weight, mha.in_proj_bias
+    bq, bk, bv = (None, None, None) if b is None else (b[:E], b[E:2 * E], b[2 * E:])
+    q = torch.nn.functional.linear(query, w[:E], bq)
+    k = torch.nn.functional.linear(key, w[E:2 * E], bk)
+    v = torch.nn.functional.linear(value, w[2 * E:], bv)
+    ctx = MaskedCrossAttentionFunction.apply(q, k, v, attn_mask, mha.num_heads)
+    return mha.out_proj(ctx)

@@ -107,7 +107,29 @@ class SelfAttentionLayer(_DecoderLayer):
         return tgt if self.normalize_before else self.norm(tgt)
 
 
+class HeadSharedMask:
+    """[B, K, Q] bool attention mask (True = hidden), the same for every head — the decoder's tensor before the
+    reference's `repeat_interleave(num_heads, dim=0).permute((0, 2, 1))` (models/mask3d.py:358)."""
+
+    def __init__(self, bkq):
+        self.bkq = bkq
+
+    def torch_layout(self, num_heads):
+        return self.bkq.repeat_interleave(num_heads, dim=0).permute((0, 2, 1))
+
+
+def _cuda_attention_core(mha, query, key, value, attn_mask=None):
+    from unscene3d_b200.engine import functional as Fn  # CUDA only: there is no CPU path
+
+    return Fn.multihead_cross_attention(mha, query, key, value, attn_mask=attn_mask)
+
+
 class CrossAttentionLayer(_DecoderLayer):
+    # The masked attention core is the libus3d kernel (csrc/attention.cu).  Like the sparse operators, which these model
+    # files take from whatever is importable as `MinkowskiEngine`, it can be swapped: the CPU tests that run these
+    # definitions over the oracle install the oracle's restatement here (tests/helpers.py).
+    attention_core = None
+
     def __init__(self, d_model, nhead, dropout=0.0, activation="relu", normalize_before=False):
         nn.Module.__init__(self)
         self.multihead_attn = nn.MultiheadAttention(d_model, nhead, dropout=dropout)
@@ -119,8 +141,11 @@ class CrossAttentionLayer(_DecoderLayer):
 
     def forward(self, tgt, memory, memory_mask=None, memory_key_padding_mask=None, pos=None, query_pos=None):
         src = self.norm(tgt) if self.normalize_before else tgt
-        out = self.multihead_attn(query=self.with_pos_embed(src, query_pos), key=self.with_pos_embed(memory, pos),
-                                  value=memory, attn_mask=memory_mask, key_padding_mask=memory_key_padding_mask)[0]
+        if memory_key_padding_mask is not None:
+            raise RuntimeError("CrossAttentionLayer: memory_key_padding_mask is not used by the reference (models/mask3d.py:358)")
+        core = type(self).attention_core or _cuda_attention_core
+        out = core(self.multihead_attn, self.with_pos_embed(src, query_pos), self.with_pos_embed(memory, pos), memory,
+                   attn_mask=memory_mask)
         tgt = tgt + self.dropout(out)
         return tgt if self.normalize_before else self.norm(tgt)
 
@@ -317,9 +342,9 @@ class Mask3D(nn.Module):
                 src_pcd = self.lin_squeeze[decoder_counter][i](batched_aux.permute((1, 0, 2)))
                 if self.use_level_embed:
                     src_pcd += self.level_embed.weight[i]
+                # the reference expands the mask to [B*h, Q, K] here (:358); the attention core reads [B, K, Q] in place
                 output = self.cross_attention[decoder_counter][i](
-                    queries.permute((1, 0, 2)), src_pcd,
-                    memory_mask=batched_attn.repeat_interleave(self.num_heads, dim=0).permute((0, 2, 1)),
+                    queries.permute((1, 0, 2)), src_pcd, memory_mask=HeadSharedMask(batched_attn),
                     memory_key_padding_mask=None, pos=batched_pos_enc.permute((1, 0, 2)), query_pos=query_pos)
                 output = self.self_attention[decoder_counter][i](output, tgt_mask=None, tgt_key_padding_mask=None, query_pos=query_pos)
                 queries = self.ffn_attention[decoder_counter][i](output).permute((1, 0, 2))
