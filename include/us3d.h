@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define US3D_ABI_VERSION 7
+#define US3D_ABI_VERSION 8
 #define US3D_MAX_KVOL 27
 
 int us3d_abi_version(void);
@@ -254,6 +254,27 @@ int us3d_ncut_gram(const float *f, int s, int d, float *inv_norm, float *A, uint
 int us3d_ncut_threshold(const float *Aa, const float *Ab, int s, const uint32_t *stats_a, const uint32_t *stats_b, float tau,
                         double eps, const uint8_t *painted, uint32_t *bits, double *degree, void *stream);
 int us3d_ncut_matvec(const uint32_t *bits, int s, double eps, const double *x, const double *xsum, double *y, void *stream);
+
+/* ---------------------------------------------------------------- FreeMask-style pseudo masks (A22)
+ * Segment branch of the scene loop of pseudo_masks/freemask_main.py:203-417.
+ *   soft_masks:     soft[s,s] = cosine_sim(f, f) (utils/freemask_utils.py:8-18: rows L2-normalised with eps 1e-9, Gram matrix,
+ *                   per-row min subtracted, divided by row max + eps), columns of all-zero rows of f set to 0 (:266);
+ *                   norm: float[s] scratch (receives the row norms).
+ *   row_stats:      per row of soft[m,s] (leading dimension ld): count[m] = #(soft >= thr) (:267-268, 343-344), soft_sum[m] =
+ *                   sum of those values (numerator of maskness, :353); optional points[m] = sum of weights[s] (int32 points per
+ *                   segment = masks.sum(1) on the mapped masks, :395) and bbox[m,6] (min xyz, max xyz over seg_min/seg_max
+ *                   [s,3] doubles = extent of the mapped mask, :382-383).  weights / seg_min / seg_max / points / bbox may be NULL.
+ *   weighted_inter: inter[m,m] = sum_s weights[s] [soft[i,s] >= thr][soft[j,s] >= thr] = (mask_i * mask_j).sum() of
+ *                   matrix_nms(kernel='mask') on the mapped masks (utils/pc_utils.py:746).
+ *   separate_h:     HOST function (all pointers host memory): the blob separation of :289-326, see csrc/freemask.cu.   */
+int us3d_freemask_soft_masks(const float *f, int s, int d, float *norm, float *soft, void *stream);
+int us3d_freemask_row_stats(const float *soft, int ld, int m, int s, float thr, const int32_t *weights, const double *seg_min,
+                            const double *seg_max, int32_t *count, float *soft_sum, long long *points, double *bbox, void *stream);
+int us3d_freemask_weighted_inter(const float *soft, int ld, int m, int s, float thr, const int32_t *weights, int32_t *inter,
+                                 void *stream);
+int us3d_freemask_separate_h(const uint8_t *masks_h, int m, int s, const int32_t *adj_ptr_h, const int32_t *adj_h,
+                             int32_t *blob_query_h, int32_t *blob_ptr_h, int32_t *blob_members_h, int max_blobs,
+                             long long max_members);
 
 #ifdef __cplusplus
 }

@@ -62,6 +62,10 @@ PROTOTYPES = {
     "us3d_xattn_workspace_bytes": [_i, _i, _i, _i, _i],
     "us3d_xattn_fwd": [_p, _p, _p, _p, _ll, _ll, _ll, _ll, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p],
     "us3d_xattn_bwd": [_p, _p, _p, _p, _ll, _ll, _ll, _ll, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p],
+    "us3d_freemask_soft_masks": [_p, _i, _i, _p, _p, _p],
+    "us3d_freemask_row_stats": [_p, _i, _i, _i, _f, _p, _p, _p, _p, _p, _p, _p, _p],
+    "us3d_freemask_weighted_inter": [_p, _i, _i, _i, _f, _p, _p, _p],
+    "us3d_freemask_separate_h": [_p, _i, _i, _p, _p, _p, _p, _p, _i, _ll],
     "us3d_matcher_cost": [_p, _i, _i, _p, _i, _p, _i, _p, _f, _f, _f, _p, _p],
 }
 _RESTYPE = {"us3d_last_error": ctypes.c_char_p, "us3d_launch_count": _ll, "us3d_reset_launch_count": None,

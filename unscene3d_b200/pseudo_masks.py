@@ -247,3 +247,156 @@ def unscene3d(aggregated_features, unique_segments, seg_connectivity, affinity_t
         masks.append(np.isin(ids, list(part - foreground)))
         foreground |= part
     return np.stack(masks) if masks else np.zeros((0, S), dtype=bool)
+
+
+# ------------------------------------------------------------------------------------------- FreeMask-style variant (A22)
+def _row_stats(soft, thr, weights=None, seg_min=None, seg_max=None):
+    m, s = soft.shape
+    dev = soft.device
+    count = torch.empty(m, dtype=torch.int32, device=dev)
+    soft_sum = torch.empty(m, dtype=torch.float32, device=dev)
+    points = torch.empty(m, dtype=torch.int64, device=dev) if weights is not None else None
+    bbox = torch.empty((m, 6), dtype=torch.float64, device=dev) if seg_min is not None else None
+    check(lib.us3d_freemask_row_stats(soft.data_ptr(), soft.stride(0), m, s, float(thr), Fn._ptr(weights), Fn._ptr(seg_min), Fn._ptr(seg_max),
+                                      count.data_ptr(), soft_sum.data_ptr(), Fn._ptr(points), Fn._ptr(bbox), _stream()))
+    return count, soft_sum, points, bbox
+
+
+def freemask(keys_F: torch.Tensor, matching_segment_ids: torch.Tensor, seg_connectivity: torch.Tensor, lr_coords, coords: torch.Tensor,
+             hard_mask_threshold: float = 0.35, nms_maskness_threshold: float = 0.6, instance_to_scene_max_ratio: float = 0.8,
+             max_instance_num: int = 50, nms_thr: float = 0.5):
+    """Segment branch of the scene loop of pseudo_masks/freemask_main.py:203-417 (defaults: pseudo_masks/config/default.yaml:57-63).
+
+    keys_F [N, C] low-resolution point features (CUDA), matching_segment_ids [N] int64, seg_connectivity [E, 2] int64 (directed),
+    lr_coords [N, 3] low-resolution point coordinates, coords [N0, 4] (batch, xyz) of the full-resolution cloud.
+    Returns (soft_masks [M, N] float32 on the low-resolution points, maskness [M]) on the host like the reference (:405-406), or
+    None where the reference skips the scene.
+
+    Device: segment means, soft masks, every per-candidate statistic and the pairwise intersections; host: the blob separation
+    (libus3d host function) and the greedy suppression decisions over the intersection matrix — as in the reference, which runs
+    both as Python loops.  No [M, N] tensor is formed before the final <= max_instance_num masks."""
+    if not keys_F.is_cuda:
+        raise RuntimeError("unscene3d_b200 operators run on CUDA tensors only (no CPU fallback)")
+    dev, st, thr = keys_F.device, _stream(), float(hard_mask_threshold)
+    ids = matching_segment_ids.to(dev).long()
+    unique_all, index = torch.unique(ids, return_inverse=True)
+    S_all = unique_all.shape[0]
+    # ---- :203-222 per-segment mean over the valid rows; segments whose mean is all-zero are dropped
+    valid = torch.any(keys_F != 0, dim=-1)
+    src, idx = keys_F[valid].float().contiguous(), index[valid].contiguous()
+    feats = torch.empty((S_all, keys_F.shape[1]), dtype=torch.float32, device=dev)
+    acc = torch.zeros((S_all, keys_F.shape[1]), dtype=torch.float64, device=dev)
+    cnt = torch.zeros(S_all, dtype=torch.float32, device=dev)
+    check(lib.us3d_segment_mean_f64(src.data_ptr(), idx.data_ptr(), src.shape[0], src.shape[1], S_all, acc.data_ptr(), feats.data_ptr(),
+                                    cnt.data_ptr(), st))
+    valid_seg = torch.any(feats != 0, dim=-1)
+    feats = feats[valid_seg].contiguous()
+    unique_segments = unique_all[valid_seg]
+    S = feats.shape[0]
+    if S == 0:
+        return None
+    pos_of_all = torch.full((S_all,), -1, dtype=torch.int64, device=dev)
+    pos_of_all[valid_seg] = torch.arange(S, device=dev)
+    point_pos = pos_of_all[index]                                     # position of every point's segment, -1 = dropped segment
+    # ---- :242-279 soft masks, hard threshold, candidates with more than 2 segments
+    soft = torch.empty((S, S), dtype=torch.float32, device=dev)
+    norm = torch.empty(S, dtype=torch.float32, device=dev)
+    check(lib.us3d_freemask_soft_masks(feats.data_ptr(), S, feats.shape[1], norm.data_ptr(), soft.data_ptr(), st))
+    count, _, _, _ = _row_stats(soft, thr)
+    keep = count > 2
+    if not bool(keep.any()):
+        return None
+    soft = soft[keep].contiguous()
+    # ---- :282-349 separation of non-connected blobs (host), candidates with more than 3 segments
+    conn = seg_connectivity.to(dev).long()
+    a = torch.searchsorted(unique_segments, conn[:, 0].contiguous())
+    b = torch.searchsorted(unique_segments, conn[:, 1].contiguous())
+    a_c, b_c = a.clamp(max=S - 1), b.clamp(max=S - 1)
+    ok = (unique_segments[a_c] == conn[:, 0]) & (unique_segments[b_c] == conn[:, 1])   # edges between kept segments
+    a, b = a_c[ok], b_c[ok]
+    order = torch.argsort(a, stable=True)
+    adj = b[order].to(torch.int32).cpu().numpy()
+    adj_ptr = np.zeros(S + 1, dtype=np.int32)
+    np.cumsum(torch.bincount(a, minlength=S).cpu().numpy(), out=adj_ptr[1:])
+    masks_h = (soft >= thr).to(torch.uint8).cpu().numpy()
+    m = masks_h.shape[0]
+    members_cap = int(masks_h.sum())
+    blobs_cap = members_cap
+    blob_query = np.empty(max(blobs_cap, 1), dtype=np.int32)
+    blob_ptr = np.empty(max(blobs_cap, 1) + 1, dtype=np.int32)
+    blob_members = np.empty(max(members_cap, 1), dtype=np.int32)
+    nb = lib.us3d_freemask_separate_h(masks_h.ctypes.data, m, S, adj_ptr.ctypes.data, adj.ctypes.data, blob_query.ctypes.data,
+                                      blob_ptr.ctypes.data, blob_members.ctypes.data, blobs_cap, members_cap)
+    if nb < 0:
+        check(nb)
+    if nb == 0:
+        return None
+    sizes = np.diff(blob_ptr[: nb + 1])
+    rows = torch.from_numpy(np.repeat(np.arange(nb), sizes)).to(dev)
+    qrows = torch.from_numpy(np.repeat(blob_query[:nb], sizes).astype(np.int64)).to(dev)
+    cols = torch.from_numpy(blob_members[: int(blob_ptr[nb])].astype(np.int64)).to(dev)
+    sep = torch.zeros((nb, S), dtype=torch.float32, device=dev)
+    sep[rows, cols] = soft[qrows, cols]
+    count, soft_sum, _, _ = _row_stats(sep, thr)
+    keep = count > 3
+    sep, count, soft_sum = sep[keep].contiguous(), count[keep], soft_sum[keep]
+    if sep.shape[0] == 0:
+        return None
+    # ---- :353-356 maskness, descending
+    maskness = soft_sum / count.to(torch.int64)
+    sort_inds = torch.argsort(maskness, descending=True, stable=True)
+    maskness, sep = maskness[sort_inds], sep[sort_inds].contiguous()
+    segment_level_counts = count.to(torch.int64)                       # the reference's stale `sum_masks` (pre-sort order), see below
+    # ---- :359-396 mapped onto the points only in effect: per-segment point counts and boxes stand in for the [M, N] masks
+    lr = torch.as_tensor(lr_coords, device=dev).double()
+    member = point_pos >= 0
+    weights = torch.bincount(point_pos[member], minlength=S).to(torch.int32)
+    pp = point_pos[member][:, None].expand(-1, 3)
+    seg_min = torch.full((S, 3), float("inf"), dtype=torch.float64, device=dev).scatter_reduce(0, pp, lr[member], "amin")
+    seg_max = torch.full((S, 3), float("-inf"), dtype=torch.float64, device=dev).scatter_reduce(0, pp, lr[member], "amax")
+    _, _, points, bbox = _row_stats(sep, thr, weights, seg_min.contiguous(), seg_max.contiguous())
+    scene_extents = (coords[:, 1:].max(0)[0] - coords[:, 1:].min(0)[0]).cpu().numpy()
+    points_h, bbox_h = points.cpu().numpy(), bbox.cpu().numpy()
+    lr_is_int = not torch.as_tensor(lr_coords).is_floating_point()
+    filtered = []
+    for mask_id in range(sep.shape[0]):
+        if points_h[mask_id] == 0:
+            continue
+        inst_extent = bbox_h[mask_id, 3:] - bbox_h[mask_id, :3]
+        if lr_is_int:
+            inst_extent = inst_extent.astype(np.int64)
+        if np.any((inst_extent / scene_extents)[:2] > instance_to_scene_max_ratio):
+            continue
+        filtered.append(mask_id)
+    if filtered:
+        sel = torch.tensor(filtered, device=dev)
+        sep, maskness = sep[sel].contiguous(), maskness[sel]
+        sum_masks = points_h[filtered]
+    else:  # the reference keeps every mask and its previous, segment-level `sum_masks` (:391-396)
+        sum_masks = segment_level_counts.cpu().numpy()
+    # ---- :398 matrix_nms(kernel='mask'): intersections on the device, the greedy decisions on the host
+    M = sep.shape[0]
+    inter = torch.empty((M, M), dtype=torch.int32, device=dev)
+    check(lib.us3d_freemask_weighted_inter(sep.data_ptr(), sep.stride(0), M, S, thr, weights.data_ptr(), inter.data_ptr(), st))
+    inter_h = inter.cpu().numpy().astype(np.float32)
+    keep_h = np.ones(M, dtype=bool)
+    sums_f = sum_masks.astype(np.int64)
+    for i in range(M - 1):
+        if not keep_h[i]:
+            continue
+        union = (sums_f[i] + sums_f[i + 1:]).astype(np.float32) - inter_h[i, i + 1:]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            drop = np.where(union > 0, inter_h[i, i + 1:] / union > np.float32(nms_thr), True)
+        keep_h[i + 1:] &= ~drop
+    maskness = maskness.clone()
+    maskness[torch.from_numpy(~keep_h).to(dev)] = 0.0
+    # ---- :400-417 ranking, top max_instance_num, maskness threshold
+    sort_inds = torch.argsort(maskness, descending=True, stable=True)[:max_instance_num]
+    maskness, sep = maskness[sort_inds], sep[sort_inds]
+    keep = maskness > nms_maskness_threshold
+    if not bool(keep.any()):
+        return None
+    sep, maskness = sep[keep], maskness[keep]
+    out = torch.zeros((sep.shape[0], ids.shape[0]), dtype=torch.float32, device=dev)
+    out[:, member] = sep[:, point_pos[member]]
+    return out.cpu(), maskness.cpu()
