@@ -190,6 +190,84 @@ def test_transposed_convolution_forward_backward(eng, ora, cin, cout):
     assert rel_err(ux.kernel.grad, uy.kernel.grad) < 5e-5
 
 
+def test_pattern_ordered_table_is_a_permutation_of_the_table(eng):
+    """Integer work, bit-exact: order is a permutation (stable within equal patterns), column j of the re-ordered table is
+    column order[j] of the table, tile masks are the unions over 128-row tiles, keys sort the rarest offset first."""
+    from unscene3d_b200.engine import coords as C
+
+    c = random_scene(5000, 5, batch=2, extent=30)
+    x = eng.SparseTensor(torch.zeros(c.shape[0], 1, device="cuda"), torch.from_numpy(c).cuda())
+    cm, key = x.coordinate_manager, x.coordinate_map_key
+    C.set_row_ordering(1)
+    try:
+        table = cm.forward_table(key, key, (3, 3, 3))
+        nbr_o, mask_o, order = (t.cpu().numpy() for t in table.ordered())
+    finally:
+        C.set_row_ordering(32768)
+    nbr = table.nbr.cpu().numpy()
+    n = nbr.shape[1]
+    assert np.array_equal(np.sort(order), np.arange(n))
+    assert np.array_equal(nbr_o, nbr[:, order])
+    present = nbr >= 0
+    freq = present.sum(1)
+    pos = np.argsort(np.argsort(-freq, kind="stable"), kind="stable")      # most frequent offset -> bit 0, ties by offset index
+    keys = (present.astype(np.int64) << pos[:, None]).sum(0)
+    assert np.array_equal(order, np.argsort(keys, kind="stable"))
+    tiles = (n + 127) // 128
+    want = np.zeros(tiles, dtype=np.int64)
+    for k in range(27):
+        hit = np.zeros(tiles * 128, bool)
+        hit[:n] = nbr_o[k] >= 0
+        want |= hit.reshape(tiles, 128).any(1).astype(np.int64) << k
+    assert np.array_equal(mask_o.astype(np.int64) & 0x7FFFFFF, want)
+    # the point of the exercise: fewer active (tile, offset) pairs than in input order
+    assert sum(bin(int(v)).count("1") for v in want) < sum(bin(int(v) & 0x7FFFFFF).count("1") for v in table.mask.cpu().numpy())
+
+
+@pytest.mark.parametrize("cin,cout,ks,stride", [(96, 96, 3, 1), (32, 64, 3, 1), (32, 32, 2, 2), (128, 96, 3, 2)])
+def test_convolution_on_pattern_ordered_tables(eng, ora, cin, cout, ks, stride):
+    """Rows grouped by neighbour pattern (large maps in production; forced here): same results as the unordered run (per
+    row the same products in the same order, only all-zero tile x offset products are skipped; the weight gradient sums
+    rows in another order), and everything within tolerance of the oracle."""
+    from unscene3d_b200.engine import coords as C
+
+    outs = []
+    for min_rows in (0, 1):
+        C.set_row_ordering(min_rows)
+        try:
+            c = random_scene(4000, 31, batch=2, extent=28)
+            x, y, fx, fy = _pair(eng, ora, c, cin)
+            mx = eng.MinkowskiConvolution(cin, cout, kernel_size=ks, stride=stride, bias=False, dimension=3).cuda()
+            my = ora.MinkowskiConvolution(cin, cout, kernel_size=ks, stride=stride, bias=False, dimension=3)
+            torch.manual_seed(4)
+            with torch.no_grad():
+                mx.kernel.normal_(0, 0.05)
+            _sync_params(mx, my)
+            ox, oy = mx(x), my(y)
+            g = torch.randn(oy.F.shape, generator=torch.Generator().manual_seed(9))
+            ox.F.backward(g.cuda())
+            oy.F.backward(g)
+            assert rel_err(ox.F, oy.F) < 5e-5 and rel_err(fx.grad, fy.grad) < 5e-5 and rel_err(mx.kernel.grad, my.kernel.grad) < 5e-5
+            outs.append((ox.F.detach().clone(), fx.grad.clone(), mx.kernel.grad.clone()))
+        finally:
+            C.set_row_ordering(32768)
+    # (not bit-identical at this size: the unordered run of a small map deals its offsets to several CTAs that meet in
+    # fp32 atomics; per row both runs add the same products)
+    assert rel_err(outs[1][0], outs[0][0]) < 1e-5
+    assert rel_err(outs[1][1], outs[0][1]) < 1e-5
+    assert rel_err(outs[1][2], outs[0][2]) < 1e-5
+
+
+def test_transposed_convolution_on_pattern_ordered_tables(eng, ora):
+    from unscene3d_b200.engine import coords as C
+
+    C.set_row_ordering(1)
+    try:
+        test_transposed_convolution_forward_backward(eng, ora, 128, 96)
+    finally:
+        C.set_row_ordering(32768)
+
+
 def test_empty_and_single_voxel(eng, ora):
     c = np.array([[0, 5, -3, 2]], dtype=np.int32)
     x, y, fx, fy = _pair(eng, ora, c, 8)

@@ -98,7 +98,20 @@ def test_cuda_backbone_matches_golden(name):
 
 
 @pytest.mark.gpu
-def test_cuda_backbone_matches_oracle_live_forward_backward():
+@pytest.mark.parametrize("row_order_min", [32768, 1])
+def test_cuda_backbone_matches_oracle_live_forward_backward(row_order_min):
+    """row_order_min = 1 forces the neighbour-pattern row order that production applies to maps of >= 32768 rows."""
+    import unscene3d_b200
+    from unscene3d_b200 import engine
+
+    engine.set_row_ordering(row_order_min)
+    try:
+        _backbone_live()
+    finally:
+        engine.set_row_ordering(32768)
+
+
+def _backbone_live():
     import unscene3d_b200
     from oracle import me_cpu
     from unscene3d_b200 import engine, models

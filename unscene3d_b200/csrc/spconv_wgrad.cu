@@ -42,6 +42,7 @@ struct Params {
     float *dw;
     int cin, cout, npad, mblks, splits, rows_per_split, kg, ngroups;
     const uint32_t *tile_mask;
+    const int32_t *dy_rows;  // optional: table column j pairs with dY row dy_rows[j] (pattern-ordered tables)
     int a_slots, b_slots, acc_cols;
 };
 
@@ -134,7 +135,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad(Params p) {
                     const int j = r0 + row;
                     const bool ok = j < r_end;
                     const uint32_t dst = slot + (uint32_t)(g >> 3) * SLAB + (uint32_t)row * 128u + (uint32_t)(((g & 7) ^ (row & 7)) << 4);
-                    const size_t off = ok ? (size_t)j * p.cout + g * 8 : 0;
+                    const int jr = (ok && p.dy_rows) ? __ldg(p.dy_rows + j) : j;
+                    const size_t off = ok ? (size_t)jr * p.cout + g * 8 : 0;
                     cp_async16(dst, p.dy_hi + off, ok ? 16u : 0u);
                     if (PASSES == 3) cp_async16(dst + b_plane, p.dy_lo + off, ok ? 16u : 0u);
                 }
@@ -198,7 +200,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad(Params p) {
         for (int r0 = r_begin; r0 < r_end; r0 += R) {
             const uint32_t act = active(r0);
             if (!act) continue;
-mbar_wait(smem_u32(&b_full[bs]), bpar, 3);
+            mbar_wait(smem_u32(&b_full[bs]), bpar, 3);
             const uint64_t db_hi = b_desc0 + (uint64_t)((uint32_t)(bs * b_slot_bytes) >> 4);
             const uint64_t db_lo = db_hi + (uint64_t)((uint32_t)b_plane >> 4);
             for (int kq = 0; kq < nk; ++kq) {
@@ -262,7 +264,7 @@ extern "C" {
 
 int us3d_spconv_wgrad_planes(const void *x_hi, const void *x_lo, const void *dy_hi, const void *dy_lo, const int32_t *nbr,
                              int n_rows, int kvol, float *dw, int cin, int cout, int passes, const uint32_t *tile_mask,
-                             void *stream_) {
+                             const int32_t *dy_rows, void *stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     US3D_CHECK_ARG(kvol >= 1 && kvol <= US3D_MAX_KVOL, "spconv_wgrad_planes: kvol %d out of range", kvol);
     US3D_CHECK_ARG(passes == 1 || passes == 3, "spconv_wgrad_planes: passes must be 1 or 3");
@@ -272,7 +274,7 @@ int us3d_spconv_wgrad_planes(const void *x_hi, const void *x_lo, const void *dy_
     wg::Params p;
     p.x_hi = (const __nv_bfloat16 *)x_hi; p.x_lo = (const __nv_bfloat16 *)x_lo;
     p.dy_hi = (const __nv_bfloat16 *)dy_hi; p.dy_lo = (const __nv_bfloat16 *)dy_lo;
-    p.nbr = nbr; p.n_rows = n_rows; p.kvol = kvol; p.dw = dw; p.cin = cin; p.cout = cout; p.tile_mask = tile_mask;
+    p.nbr = nbr; p.n_rows = n_rows; p.kvol = kvol; p.dw = dw; p.cin = cin; p.cout = cout; p.tile_mask = tile_mask; p.dy_rows = dy_rows;
     p.npad = ceil_div(cout, 64) * 64;
     p.mblks = ceil_div(cin, 128);
     int kg = 512 / p.npad;
@@ -299,7 +301,7 @@ int us3d_spconv_wgrad_planes(const void *x_hi, const void *x_lo, const void *dy_
     if (p.a_slots > wg::MAX_A) p.a_slots = wg::MAX_A;
     US3D_CHECK_ARG(p.a_slots >= 2, "spconv_wgrad_planes: operand slots do not fit in shared memory (cout %d)", cout);
     const size_t smem = (size_t)p.a_slots * a_slot + (size_t)p.b_slots * b_slot + 1024;
-static bool attr_done = false;
+    static bool attr_done = false;
     if (!attr_done) {
         US3D_CUDA(cudaFuncSetAttribute(wg::k_wgrad<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
         US3D_CUDA(cudaFuncSetAttribute(wg::k_wgrad<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));

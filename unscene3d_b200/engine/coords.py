@@ -92,11 +92,48 @@ class CoordinateMap:
         self._batch_slices: Optional[List] = None
 
 
+# Tables with at least this many rows are also kept in neighbour-pattern order for the tcgen05 kernels (0 disables)
+_row_order = {"min_rows": int(os.environ.get("US3D_ROW_ORDER_MIN", "32768"))}
+
+
+def set_row_ordering(min_rows: int):
+    """Tables with >= min_rows rows (and more than one kernel offset) are handed to the tensor-core kernels in
+    neighbour-pattern order (see NeighbourTable.ordered); 0 switches the re-ordering off."""
+    _row_order["min_rows"] = int(min_rows)
+
+
 class NeighbourTable:
-    __slots__ = ("nbr", "mask", "n_rows", "kvol", "_pairs")
+    __slots__ = ("nbr", "mask", "n_rows", "kvol", "_pairs", "_ordered")
 
     def __init__(self, nbr: torch.Tensor, mask: torch.Tensor, n_rows: int, kvol: int):
-        self.nbr, self.mask, self.n_rows, self.kvol, self._pairs = nbr, mask, n_rows, kvol, None
+        self.nbr, self.mask, self.n_rows, self.kvol, self._pairs, self._ordered = nbr, mask, n_rows, kvol, None, None
+
+    def ordered(self):
+        """(nbr, tile mask, order) with the table's rows grouped by neighbour pattern, or None for small tables.
+
+        The tensor-core kernels skip a kernel offset for a 128-row tile only if no row of the tile has a neighbour there.
+        Spatially consecutive rows of a voxelised surface keep every offset active (200k-voxel scene: 100 % of the
+        (tile, offset) pairs at a pair density of 49 %); rows sorted by presence pattern, rarest offset most significant,
+        leave 67 % (k3) and 1/8 (the fine side of a k2s2 map: every row has exactly one parent).  Column j of the
+        re-ordered table belongs to row order[j]; results are written to / read from their natural rows, so nothing
+        outside the convolution kernels sees the order.  Built on first use: two integer kernels + one stable sort."""
+        if self._ordered is None:
+            m = _row_order["min_rows"]
+            if m <= 0 or self.n_rows < m or self.kvol == 1:
+                self._ordered = False
+            else:
+                dev = self.nbr.device
+                n, kvol, st = self.n_rows, self.kvol, _stream()
+                scratch = torch.empty(n + 32, dtype=torch.int32, device=dev)
+                keys = torch.empty(n, dtype=torch.int32, device=dev)
+                check(lib.us3d_neighbour_pattern_keys(self.nbr.data_ptr(), n, kvol, scratch.data_ptr(), keys.data_ptr(), st))
+                order = torch.sort(keys, stable=True)[1].to(torch.int32)
+                nbr = torch.empty_like(self.nbr)
+                mask = torch.empty_like(self.mask)
+                check(lib.us3d_kernel_map_reorder(self.nbr.data_ptr(), n, kvol, order.data_ptr(), nbr.data_ptr(), mask.data_ptr(),
+                                                  TILE_ROWS, st))
+                self._ordered = (nbr, mask, order)
+        return self._ordered or None
 
     def pairs(self) -> int:
         """Present (input row, output row) pairs — the P of the algorithmic FLOP count 2 P Cin Cout (host read, cached;

@@ -222,9 +222,10 @@ def spconv_gather(x, table: NeighbourTable, w3, cin, cout, transpose_w, flip_k, 
         kname = _tc_kernel["fwd"]
         if kname in ("tma", "cp", "mt"):
             fn = lib.us3d_spconv_gather_mt if kname == "mt" else (lib.us3d_spconv_gather_tma if kname == "tma" else lib.us3d_spconv_gather_cp)
+            nbr, mask, order = (table.ordered() if kname == "mt" else None) or (table.nbr, table.mask, None)
             _timed(kind, x.shape[0], table.n_rows, table.kvol, cin, cout, lambda: check(
-                fn(hi.data_ptr(), _ptr(lo), x.shape[0], table.nbr.data_ptr(), table.n_rows, table.kvol, wpack.data_ptr(), cin, cout,
-                   mode, _ptr(bias), 0, y.data_ptr(), _ld(y), int(accumulate), _ptr(table.mask), st)), table, kname)
+                fn(hi.data_ptr(), _ptr(lo), x.shape[0], nbr.data_ptr(), table.n_rows, table.kvol, wpack.data_ptr(), cin, cout,
+                   mode, _ptr(bias), _ptr(order), y.data_ptr(), _ld(y), int(accumulate), _ptr(mask), st)), table, kname)
             return y
         _timed(kind, x.shape[0], table.n_rows, table.kvol, cin, cout, lambda: check(
             lib.us3d_spconv_gather_tc(x.data_ptr(), _ld(x), table.nbr.data_ptr(), table.n_rows, table.kvol, wpack.data_ptr(),
@@ -253,9 +254,13 @@ def spconv_wgrad(x, table: NeighbourTable, dy, cin, cout):
         if _tc_kernel["wgrad"] == "planes":
             xh, xl = bf16_planes(x, mode == 3)
             dh, dl = bf16_planes(dy, mode == 3)
+            # pattern order pays for the weight gradient only on k2s2 maps (one parent per fine row: 1/8 of the tile x offset
+            # products remain); on k3 maps the scattered dY rows cost more than the skipped products save (measured on B200:
+            # 200k voxels 96 -> 96, 0.55 -> 0.62 ms ordered, k2s2 0.171 -> 0.125 ms)
+            nbr, mask, order = (table.ordered() if table.kvol <= 8 else None) or (table.nbr, table.mask, None)
             _timed("wgrad", x.shape[0], table.n_rows, table.kvol, cin, cout, lambda: check(
-                lib.us3d_spconv_wgrad_planes(xh.data_ptr(), _ptr(xl), dh.data_ptr(), _ptr(dl), table.nbr.data_ptr(), table.n_rows,
-                                             table.kvol, dw.data_ptr(), cin, cout, mode, _ptr(table.mask), st)), table, "wgrad-tc")
+                lib.us3d_spconv_wgrad_planes(xh.data_ptr(), _ptr(xl), dh.data_ptr(), _ptr(dl), nbr.data_ptr(), table.n_rows,
+                                             table.kvol, dw.data_ptr(), cin, cout, mode, _ptr(mask), _ptr(order), st)), table, "wgrad-tc")
             return dw
         _timed("wgrad", x.shape[0], table.n_rows, table.kvol, cin, cout, lambda: check(
             lib.us3d_spconv_wgrad_tc(x.data_ptr(), _ld(x), table.nbr.data_ptr(), table.n_rows, table.kvol, dy.data_ptr(), _ld(dy),
