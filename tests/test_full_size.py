@@ -1,0 +1,179 @@
+"""Parity at BASELINE.json's full size (configs[1]: 200k-voxel ScanNet-shaped scene), where the torch oracle would take
+minutes: integer work is checked bit-exact against numpy restatements that are cheap at this size, floating-point kernels
+through size-independent properties of the operator (linearity, adjointness of forward and input gradient, the weight
+gradient as the derivative of the forward in W, equivalence of the pattern-ordered and the natural row order) — all on the
+production path (tcgen05 three-term mode, neighbour-pattern row order active: maps >= 32768 rows).
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+N_VOXELS = 200_000
+
+
+@pytest.fixture(scope="module")
+def scene():
+    import unscene3d_b200  # noqa: F401
+    from unscene3d_b200.synthetic import make_scene
+
+    s = make_scene(N_VOXELS, seed=0, with_masks=False)
+    c4 = np.concatenate([np.zeros((s.n, 1), np.int32), s.coords], 1).astype(np.int32)
+    return s, c4
+
+
+def _key(c):
+    b = 1 << 17
+    c = c.astype(np.int64)
+    return (c[:, 0] << 54) | ((c[:, 1] + b) << 36) | ((c[:, 2] + b) << 18) | (c[:, 3] + b)
+
+
+def _first_occurrence_unique(c):
+    """Unique rows in order of first occurrence + inverse (MinkowskiEngine map semantics)."""
+    k = _key(c)
+    _, first, inv = np.unique(k, return_index=True, return_inverse=True)
+    order = np.argsort(first, kind="stable")
+    rank = np.empty_like(order)
+    rank[order] = np.arange(order.shape[0])
+    return c[np.sort(first)], rank[inv]
+
+
+def test_coordinate_pyramid_and_kernel_maps_bit_exact_at_200k(scene):
+    from unscene3d_b200 import engine
+
+    s, c4 = scene
+    x = engine.SparseTensor(torch.zeros(s.n, 1, device="cuda"), torch.from_numpy(c4).cuda())
+    cm, key = x.coordinate_manager, x.coordinate_map_key
+    assert np.array_equal(x.C.cpu().numpy(), c4)                      # stride-1 rows keep input order
+    cur, cur_key = c4, key
+    for level in range(4):
+        stride = 2 << level
+        nxt_key = cm.stride(cur_key, (2, 2, 2))
+        q = cur.copy()
+        q[:, 1:] = np.floor_divide(q[:, 1:], stride) * stride
+        want, _ = _first_occurrence_unique(q)
+        got = cm.get_coordinates(nxt_key).cpu().numpy()
+        assert np.array_equal(got, want), f"stride {stride}"
+        # k3 kernel map of the level below: nbr[k, o] = row of coords[o] + off_k
+        table = cm.forward_table(cur_key, cur_key, (3, 3, 3)).nbr.cpu().numpy()
+        keys = _key(cur)
+        srt = np.argsort(keys, kind="stable")
+        ts = stride // 2
+        k = 0
+        for dz in (-1, 0, 1):
+            for dy in (-1, 0, 1):
+                for dx in (-1, 0, 1):
+                    qq = cur.copy()
+                    qq[:, 1] += dx * ts
+                    qq[:, 2] += dy * ts
+                    qq[:, 3] += dz * ts
+                    qk = _key(qq)
+                    pos = np.clip(np.searchsorted(keys[srt], qk), 0, len(keys) - 1)
+                    hit = keys[srt][pos] == qk
+                    want_k = np.where(hit, srt[pos], -1)
+                    assert np.array_equal(table[k], want_k), f"stride {ts} offset {k}"
+                    k += 1
+        cur, cur_key = want, nxt_key
+
+
+def _conv_setup(scene, cin, cout, seed):
+    from unscene3d_b200 import engine
+
+    s, c4 = scene
+    x0 = engine.SparseTensor(torch.zeros(s.n, 1, device="cuda"), torch.from_numpy(c4).cuda())
+    cm, key = x0.coordinate_manager, x0.coordinate_map_key
+    table = cm.forward_table(key, key, (3, 3, 3))
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.randn(s.n, cin, device="cuda", generator=g)
+    w = torch.randn(27, cin, cout, device="cuda", generator=g) * 0.05
+    dy = torch.randn(s.n, cout, device="cuda", generator=g)
+    return table, x, w, dy
+
+
+def _rel(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm().clamp(min=1e-30))
+
+
+def test_pattern_order_is_active_and_equivalent_at_200k(scene):
+    """Production size: the ordered table is in use; forward and input gradient are BIT-IDENTICAL to the natural order (same
+    per-row products in the same order — only all-zero tile x offset products are skipped, no atomics at this size)."""
+    from unscene3d_b200 import engine
+    from unscene3d_b200.engine import functional as Fn
+
+    table, x, w, dy = _conv_setup(scene, 96, 96, 1)
+    nbr_o, mask_o, order = table.ordered()
+    assert torch.equal(torch.sort(order.long())[0], torch.arange(table.n_rows, device="cuda"))
+    active = sum(bin(int(v) & 0x7FFFFFF).count("1") for v in mask_o.cpu().numpy())
+    assert active < 0.75 * 27 * mask_o.shape[0], "pattern order should prune at least a quarter of the tile x offset products"
+    y_ord = Fn.spconv_gather(x, table, w, 96, 96, False, False)
+    dx_ord = Fn.spconv_gather(dy, table, w, 96, 96, True, True)
+    engine.set_row_ordering(0)
+    try:
+        plain = engine.NeighbourTable(table.nbr, table.mask, table.n_rows, table.kvol)
+        y_nat = Fn.spconv_gather(x, plain, w, 96, 96, False, False)
+        dx_nat = Fn.spconv_gather(dy, plain, w, 96, 96, True, True)
+    finally:
+        engine.set_row_ordering(32768)
+    assert torch.equal(y_ord, y_nat)
+    assert torch.equal(dx_ord, dx_nat)
+
+
+@pytest.mark.parametrize("cin,cout", [(96, 96), (128, 96), (32, 32)])
+def test_convolution_properties_at_200k(scene, cin, cout):
+    """Linearity in x; <conv(x), g> = <x, dX(g)> (the input gradient is the adjoint of the forward); <dW(x, g), V> =
+    <conv_V(x), g> (the weight gradient is the derivative of the forward in W).  Tolerances: the three-term split is
+    fp32-faithful (5e-5 per kernel); the inner products are taken in fp64."""
+    from unscene3d_b200.engine import functional as Fn
+
+    table, x, w, g = _conv_setup(scene, cin, cout, 2)
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    x2 = torch.randn(x.shape, device="cuda", generator=gen)
+    v = torch.randn(w.shape, device="cuda", generator=gen) * 0.05
+    conv = lambda inp, wt: Fn.spconv_gather(inp, table, wt, cin, cout, False, False)
+    y1, y2 = conv(x, w), conv(x2, w)
+    assert _rel(conv(0.5 * x - 2.0 * x2, w), 0.5 * y1 - 2.0 * y2) < 5e-5
+    dx = Fn.spconv_gather(g, table, w, cout, cin, True, True)
+    lhs, rhs = (y1.double() * g.double()).sum(), (x.double() * dx.double()).sum()
+    assert abs(float(lhs - rhs)) < 5e-5 * float(y1.double().norm() * g.double().norm())
+    dw = Fn.spconv_wgrad(x, table, g, cin, cout)
+    lhs, rhs = (dw.double() * v.double()).sum(), (conv(x, v).double() * g.double()).sum()
+    assert abs(float(lhs - rhs)) < 5e-5 * float(dw.double().norm() * v.double().norm())
+    # exact-fp32 SIMT kernel on a 4096-row sample of the same map as the independent reference of the values themselves
+    rows = torch.arange(0, table.n_rows, table.n_rows // 4096, device="cuda")[:4096]
+    nb = table.nbr[:, rows].long()
+    ref = torch.zeros(rows.shape[0], cout, dtype=torch.float64, device="cuda")
+    for k in range(27):
+        ok = nb[k] >= 0
+        ref[ok] += x[nb[k][ok]].double() @ w[k].double()
+    assert _rel(y1[rows], ref) < 5e-5
+
+
+def test_backbone_step_at_200k_is_finite_normalised_and_reproducible(scene):
+    """Res16UNet34C forward + backward on the full scene: BatchNorm outputs are normalised, every gradient is finite, and two
+    runs agree (coarse levels combine partial sums with fp32 atomics — 1e-7 per layer, amplified through 60 normalised
+    layers —, everything else is order-deterministic)."""
+    from unscene3d_b200 import engine, models
+    from unscene3d_b200.utils import BackboneConfig, seeded_state
+
+    s, c4 = scene
+    net = models.Res16UNet34C(3, 20, BackboneConfig(), D=3, out_fpn=True)
+    net.load_state_dict(seeded_state(net, 0))
+    net = net.cuda().train()
+    feats = torch.from_numpy(s.colors).cuda()
+    w = torch.linspace(-1, 1, 96, device="cuda")
+    runs = []
+    for _ in range(2):
+        out, aux = net(engine.SparseTensor(feats, torch.from_numpy(c4).cuda()))
+        (out.F * w).mean().backward()
+        grads = {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}
+        net.zero_grad(set_to_none=True)
+        runs.append((out.F.detach().clone(), grads))
+    out_f, grads = runs[0]
+    assert out_f.shape == (N_VOXELS, 96) and bool(torch.isfinite(out_f).all())
+    assert all(bool(torch.isfinite(g).all()) for g in grads.values())
+    assert len(grads) >= 180
+    assert _rel(runs[1][0], out_f) < 1e-4  # measured 1.5e-5
+    worst = max(_rel(runs[1][1][k], grads[k]) for k in grads)
+    assert worst < 1e-3, worst
+    assert len(aux) == 5  # s16 ... s1 feature maps
