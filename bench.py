@@ -247,9 +247,10 @@ def run_ours(args):
     loss_host = torch.zeros(1).pin_memory()
 
     def step(coords, feats):
-        # a training step packs the (updated) weights of every convolution once; with no optimizer in the metric the
-        # cached images would otherwise survive from step to step
-        Fn.invalidate_packed_weights()
+        # a training step packs the (updated) weights of every convolution once — all images in one launch, as a loop does
+        # after its optimizer update; with no optimizer in the metric the cached images would otherwise survive from step
+        # to step
+        Fn.pack_network(net)
         x = engine.SparseTensor(feats, coords)
         out, _ = net(x)
         loss = (out.F * wvec).mean()

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define US3D_ABI_VERSION 9
+#define US3D_ABI_VERSION 10
 #define US3D_MAX_KVOL 27
 
 int us3d_abi_version(void);
@@ -190,6 +190,12 @@ int us3d_bn_backward_planes(const float *dy, int lddy, const float *x, int ldx, 
  * us3d_spconv_packed_bytes(kvol, cout, cin, passes). */
 int us3d_spconv_pack_pair(const float *w, int kvol, int cin, int cout, int flip_dgrad, int passes, void *out_fwd,
                           void *out_dgrad, void *stream);
+/* Every weight image of a network in one launch (what a training step does after the optimizer update).  items: DEVICE array
+ * of n_items descriptors { const float *w; uint8_t *out; int32 kvol, w_cin, w_cout, w_ci0, kdim, ndim, transpose, flip; }
+ * (48 bytes): image `out` of the [kvol, w_cin, w_cout] weight, K = kdim, N = ndim; transpose = 0: forward image of input
+ * channels w_ci0 .. w_ci0 + kdim; transpose = 1: input-gradient image (W^T, offsets reversed when flip) of input channels
+ * w_ci0 .. w_ci0 + ndim.  Layout of each image as us3d_spconv_pack_weights.                                      */
+int us3d_spconv_pack_many(const void *items, int n_items, int passes, void *stream);
 
 /* The stem convolution (conv0p1s1: 3 input channels, models/res16unet.py:219-221): its K = 3 contraction does not fill
  * a tensor-core tile, so it runs as warp = rows, lane = output channel with the weights in shared memory.

@@ -63,7 +63,7 @@ def scene_batch(n_scenes, n_voxels, seed0, dev):
 
 def train_step(net, crit, weight_dict, batch, world):
     coords, colors, raw, p2s, targets = batch
-    Fn.invalidate_packed_weights()
+    Fn.pack_network(net)
     x = engine.SparseTensor(colors, coords)
     out = net(x, point2segment=p2s, raw_coordinates=raw)
     losses = crit(out, targets, mask_type="segment_mask")

@@ -268,6 +268,48 @@ def test_transposed_convolution_on_pattern_ordered_tables(eng, ora):
         C.set_row_ordering(32768)
 
 
+def test_pack_network_images_equal_the_per_layer_images(eng):
+    """One launch packs every convolution of a network; byte-identical to the per-layer packing, including the column slices
+    of the 384-channel decoder convolutions, and marked current so that the convolutions do not pack again."""
+    from unscene3d_b200 import models
+    from unscene3d_b200.engine import functional as Fn
+    from unscene3d_b200.utils import BackboneConfig, seeded_state
+
+    net = models.Res16UNet34C(3, 20, BackboneConfig(), D=3, out_fpn=True)
+    net.load_state_dict(seeded_state(net, 0))
+    net = net.cuda()
+    Fn.pack_network(net)
+    seen = wide = 0
+    for m in net.modules():
+        if not (hasattr(m, "kernel_volume") and hasattr(m, "IS_TRANSPOSE")) or m.kernel.shape[-2] <= 4:
+            continue
+        if not hasattr(m.kernel, "_us3d_packs"):  # shapes the tensor-core kernels do not take (`final`: 96 -> 20)
+            assert m.kernel.shape[-1] % 16 != 0
+            continue
+        key, fwd, bwd = m.kernel._us3d_packs
+        fwd, bwd = fwd.clone(), [(c0, nc, img.clone()) for c0, nc, img in bwd]
+        w3 = m.kernel.detach().view(m.kernel_volume, m.kernel.shape[-2], m.kernel.shape[-1])
+        # the plan's images are current: no packing on use
+        before = unscene3d_launches()
+        f2, b2 = Fn.packed_weights(m.kernel, w3, key[3], 3, True)
+        assert unscene3d_launches() == before and f2.data_ptr() == m.kernel._us3d_packs[1].data_ptr()
+        del m.kernel._us3d_packs
+        f3, b3 = Fn.packed_weights(m.kernel, w3, key[3], 3, True)   # per-layer packing
+        assert torch.equal(fwd, f3)
+        assert len(bwd) == len(b3)
+        for (c0, nc, img), (d0, dn, img3) in zip(bwd, b3):
+            assert (c0, nc) == (d0, dn) and torch.equal(img, img3)
+        seen += 1
+        wide += len(bwd) > 1
+    assert seen >= 60 and wide >= 1
+
+
+def unscene3d_launches():
+    from unscene3d_b200 import _lib
+
+    return _lib.launch_count()
+
+
 def test_empty_and_single_voxel(eng, ora):
     c = np.array([[0, 5, -3, 2]], dtype=np.int32)
     x, y, fx, fy = _pair(eng, ora, c, 8)

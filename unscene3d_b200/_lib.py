@@ -45,6 +45,7 @@ PROTOTYPES = {
     "us3d_bn_apply_planes": [_p, _i, _i, _i, _p, _p, _p, _p, _p, _i, _i, _p, _i, _p, _p, _p],
     "us3d_bn_backward_planes": [_p, _i, _p, _i, _p, _i, _i, _i, _p, _p, _p, _i, _i, _p, _p, _i, _p, _i, _p, _p, _p, _p, _p],
     "us3d_spconv_pack_pair": [_p, _i, _i, _i, _i, _i, _p, _p, _p],
+    "us3d_spconv_pack_many": [_p, _i, _i, _p],
     "us3d_stem_conv_supported": [_i, _i, _i],
     "us3d_stem_conv_fwd": [_p, _i, _p, _i, _i, _p, _i, _i, _p, _p, _i, _p],
     "us3d_stem_conv_wgrad": [_p, _i, _p, _i, _i, _p, _i, _p, _i, _i, _p],

@@ -398,6 +398,47 @@ __global__ void __launch_bounds__(256) k_pack_pair(const float *__restrict__ w, 
     }
 }
 
+// Every weight image of a network in ONE launch (a training step re-packs all convolutions after the optimizer update:
+// 62 launches for Res16UNet34C otherwise).  blockIdx.y = image; descriptors live in device memory.  `w_ci0` / the image's own
+// kdim / ndim select a column slice of the input channels (input gradients wider than 256 channels are produced in slices).
+struct PackItem {
+    const float *w;      // [kvol, w_cin, w_cout] fp32
+    uint8_t *out;        // image, layout as us3d_spconv_pack_weights
+    int kvol, w_cin, w_cout, w_ci0;
+    int kdim, ndim, transpose, flip;
+};
+static_assert(sizeof(PackItem) == 48, "PackItem is mirrored by a numpy dtype in engine/functional.py");
+
+__global__ void __launch_bounds__(256) k_pack_many(const PackItem *__restrict__ items, int planes) {
+    const PackItem s = items[blockIdx.y];
+    const int nchunks = (s.kdim + 63) / 64;
+    const long long total = (long long)s.kvol * nchunks * s.ndim * 8;
+    const size_t slab = (size_t)s.ndim * 128;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(e % s.ndim);
+        long long t = e / s.ndim;
+        const int g = (int)(t % 8);
+        t /= 8;
+        const int c = (int)(t % nchunks);
+        const int k = (int)(t / nchunks);
+        const int kq = s.flip ? s.kvol - 1 - k : k;
+        float f[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int kk = c * 64 + g * 8 + i;
+            float v = 0.f;
+            // forward: K = input channel (kk), N = output channel (n);  gradient: K = output channel, N = input channel
+            if (kk < s.kdim)
+                v = s.transpose ? s.w[((size_t)kq * s.w_cin + s.w_ci0 + n) * s.w_cout + kk]
+                                : s.w[((size_t)kq * s.w_cin + s.w_ci0 + kk) * s.w_cout + n];
+            f[i] = v;
+        }
+        uint8_t *base = s.out + ((size_t)k * nchunks + c) * planes * slab;
+        const size_t off = (size_t)n * 128 + (size_t)((g ^ (n & 7)) << 4);
+        store_planes(f, reinterpret_cast<uint4 *>(base + off), planes == 2 ? reinterpret_cast<uint4 *>(base + slab + off) : nullptr, 0);
+    }
+}
+
 static inline int flat_grid(long long work) {
     long long b = (work + 255) / 256;
     long long cap = (long long)num_sms() * 16;
@@ -479,6 +520,15 @@ int us3d_spconv_pack_pair(const float *w, int kvol, int cin, int cout, int flip_
     if (gx > num_sms() * 8) gx = num_sms() * 8;
     dim3 grid(gx, 2);
     fused::k_pack_pair<<<grid, 256, 0, (cudaStream_t)stream_>>>(w, kvol, cin, cout, passes == 3 ? 2 : 1, s0, s1);
+    US3D_LAUNCH_CHECK();
+    return 0;
+}
+
+int us3d_spconv_pack_many(const void *items, int n_items, int passes, void *stream_) {
+    US3D_CHECK_ARG(n_items >= 0 && n_items <= 65535, "pack_many: %d images", n_items);
+    US3D_CHECK_ARG(passes == 1 || passes == 3, "pack_many: passes must be 1 or 3");
+    if (n_items == 0) return 0;
+    fused::k_pack_many<<<dim3(96, n_items), 256, 0, (cudaStream_t)stream_>>>((const fused::PackItem *)items, passes == 3 ? 2 : 1);
     US3D_LAUNCH_CHECK();
     return 0;
 }

@@ -172,6 +172,59 @@ def packed_weights(kernel: torch.Tensor, w3: torch.Tensor, flip_dgrad: bool, pas
     return fwd, bwd
 
 
+_PACK_ITEM = [("w", "<u8"), ("out", "<u8"), ("kvol", "<i4"), ("w_cin", "<i4"), ("w_cout", "<i4"), ("w_ci0", "<i4"),
+              ("kdim", "<i4"), ("ndim", "<i4"), ("transpose", "<i4"), ("flip", "<i4")]  # == fused::PackItem (csrc/fused_ops.cu)
+_pack_plans = {}
+
+
+def pack_network(net: torch.nn.Module):
+    """Re-pack the weight images of EVERY tensor-core convolution under `net` with one kernel launch and mark them current —
+    what a training loop calls once per step after the optimizer update (instead of invalidate_packed_weights(), after which
+    each of the 62 convolutions of Res16UNet34C packs its own pair on first use).  Images live in buffers owned by the plan
+    and are overwritten in stream order.  Convolutions the plan does not cover (exact-fp32 mode, shapes the tensor-core
+    kernels do not take) keep packing lazily."""
+    import numpy as np
+
+    mode = _precision["mode"]
+    _pack_epoch["n"] += 1
+    if mode == 0:
+        return
+    convs = [m for m in net.modules() if hasattr(m, "kernel_volume") and hasattr(m, "IS_TRANSPOSE") and isinstance(getattr(m, "kernel", None), torch.nn.Parameter)]
+    convs = [m for m in convs if m.kernel.is_cuda and m.kernel.is_contiguous() and m.kernel.dtype == torch.float32 and m.kernel.shape[-2] > 4]
+    if not convs:
+        return
+    sig = (mode, tuple(m.kernel.data_ptr() for m in convs))
+    plan = _pack_plans.get(id(net))
+    if plan is None or plan["sig"] != sig:
+        dev = convs[0].kernel.device
+        rows, entries = [], []
+        for m in convs:
+            kvol, cin, cout = m.kernel_volume, m.kernel.shape[-2], m.kernel.shape[-1]
+            flip = (not m.IS_TRANSPOSE) and kvol > 1 and all(s == 1 for s in m.stride) and all(k % 2 == 1 for k in m.kernel_size)
+            wptr = m.kernel.data_ptr()
+            fwd = None
+            if _tc_ok(cin, cout):
+                fwd = torch.empty(_packed_bytes(kvol, cin, cout, mode), dtype=torch.uint8, device=dev)
+                rows.append((wptr, fwd.data_ptr(), kvol, cin, cout, 0, cin, cout, 0, 0))
+            bwd = None
+            slices = [(0, cin)] if _tc_ok(cout, cin) else ([(0, cin // 2), (cin // 2, cin // 2)] if cin > 256 and cin % 32 == 0 and _tc_ok(cout, cin // 2) else [])
+            if slices:
+                bwd = []
+                for c0, nc in slices:
+                    img = torch.empty(_packed_bytes(kvol, cout, nc, mode), dtype=torch.uint8, device=dev)
+                    rows.append((wptr, img.data_ptr(), kvol, cin, cout, c0, cout, nc, 1, int(flip)))
+                    bwd.append((c0, nc, img))
+            if fwd is not None or bwd is not None:
+                entries.append((m, bool(flip), fwd, bwd))
+        table = torch.from_numpy(np.array(rows, dtype=_PACK_ITEM).view(np.uint8).copy()).to(dev)
+        plan = _pack_plans[id(net)] = {"sig": sig, "table": table, "n": len(rows), "entries": entries, "mode": mode}
+    check(lib.us3d_spconv_pack_many(plan["table"].data_ptr(), plan["n"], mode, _stream()))
+    epoch = _pack_epoch["n"]
+    for m, flip, fwd, bwd in plan["entries"]:
+        k = m.kernel
+        k._us3d_packs = ((k._version, epoch, mode, flip, k.data_ptr()), fwd, bwd)
+
+
 # forward / input-gradient tensor-core kernel: "cp" = cp.async row gather, persistent, double-buffered TMEM (default);
 # "tma" = same pipeline with TMA tile::gather4 (slower: ~80 cycles per gather4); "ldg" = register-staged gather
 # "mt" = "cp" + up to 4 output tiles sharing each weight slab (production).  Weight gradient: "planes" = cp.async
