@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define US3D_ABI_VERSION 10
+#define US3D_ABI_VERSION 11
 #define US3D_MAX_KVOL 27
 
 int us3d_abi_version(void);
@@ -260,6 +260,17 @@ int us3d_xattn_bwd(const float *q, const float *k, const float *v, const uint8_t
  * prob[q,ncls] softmaxed class probabilities, labels[t] int64 (253 = ignore -> class cost -1).     */
 int us3d_matcher_cost(const float *logits, int s, int q, const float *tgt, int t, const float *prob, int ncls,
                       const int64_t *labels, float w_class, float w_mask, float w_dice, float *cost, void *stream);
+
+/* Mask losses of the set criterion for the matched pairs of one scene (models/criterion.py:22-73 dice_loss / sigmoid_ce_loss,
+ * called from loss_masks :168-216):  logits[s, q] fp32 (pred_masks of the scene), tgt[t_all, s] (float32, or uint8 / bool when
+ * tgt_is_float == 0), qidx[t] / tidx[t] int64 = matched query / target of pair t, weights[t] (may be NULL = 1; the DropLoss
+ * gate), n = the scene's normaliser.  fwd: stats[t, 4] (per-pair sums kept for backward), out[2] = (loss_mask, loss_dice).
+ * bwd: gout[2] = upstream gradients of the two losses (device), dlogits[s, q] (zero outside the matched columns).      */
+int us3d_mask_loss_fwd(const float *logits, int s, int q, const void *tgt, int tgt_is_float, const int64_t *qidx,
+                       const int64_t *tidx, int t, const float *weights, float n, float *stats, float *out, void *stream);
+int us3d_mask_loss_bwd(const float *logits, int s, int q, const void *tgt, int tgt_is_float, const int64_t *qidx,
+                       const int64_t *tidx, int t, const float *weights, float n, const float *stats, const float *gout,
+                       float *dlogits, void *stream);
 
 /* ---------------------------------------------------------------- pseudo-mask NCut step (A19, A20)
  * get_affinity_matrix / second_smallest_eigenvector of pseudo_masks/unscene3d_pseudo_main.py:89-146.

@@ -126,6 +126,30 @@ def masked_attention_core(q, k, v, mask_bhqk, num_heads):
     return o.permute(2, 0, 1, 3).reshape(Q, B, E)
 
 
+def dice_loss(inputs, targets, num_masks, weights):
+    """models/criterion.py:22-39."""
+    inputs = inputs.sigmoid().flatten(1)
+    numerator = 2 * (inputs * targets).sum(-1)
+    denominator = inputs.sum(-1) + targets.sum(-1)
+    loss = weights * (1 - (numerator + 1) / (denominator + 1))
+    return loss.sum() / num_masks
+
+
+def sigmoid_ce_loss(inputs, targets, num_masks, weights):
+    """models/criterion.py:47-65."""
+    loss = weights.view(-1, 1) * torch.nn.functional.binary_cross_entropy_with_logits(inputs, targets, reduction="none")
+    return loss.mean(1).sum() / num_masks
+
+
+def mask_losses(logits_sq, targets_ts, qidx, tidx, weights, n):
+    """(loss_mask, loss_dice) of one scene as models/criterion.py:176-216 computes them: matched columns of the [S, Q] logits
+    against the matched rows of the [T_all, S] targets."""
+    pred = logits_sq[:, qidx].T
+    tgt = targets_ts[tidx].float()
+    w = torch.ones(pred.shape[0], device=pred.device) if weights is None else weights
+    return sigmoid_ce_loss(pred, tgt, n, w), dice_loss(pred, tgt, n, w)
+
+
 def as_module_tree():
     """Module objects `torch_scatter`, `pointnet2`, `pointnet2._ext` exporting the CPU restatements."""
     import types

@@ -514,6 +514,36 @@ def test_fps_all_rows_skipped_returns_row_zero(eng):
     assert torch.equal(Fn.furthest_point_sampling(pts, 7).cpu(), torch.zeros(1, 7, dtype=torch.int32))
 
 
+@pytest.mark.parametrize("S,Q,T_all,T,tgt_dtype,weighted", [(1500, 100, 20, 20, torch.bool, False), (333, 100, 30, 7, torch.float32, True),
+                                                             (64, 10, 5, 0, torch.bool, False), (2000, 100, 25, 25, torch.uint8, True)])
+def test_mask_losses_match_oracle(eng, S, Q, T_all, T, tgt_dtype, weighted):
+    """Set-criterion mask losses of one scene (models/criterion.py:22-73, 176-216): forward and the gradient with respect to
+    the mask logits against the oracle's restatement evaluated in float64; 1e-5 relative."""
+    from oracle import ops_cpu
+    from unscene3d_b200.engine import functional as Fn
+
+    g = torch.Generator().manual_seed(S + T)
+    logits = torch.randn(S, Q, generator=g) * 3
+    tgt = (torch.rand(T_all, S, generator=g) < 0.2).to(tgt_dtype)
+    qidx = torch.randperm(Q, generator=g)[:T]
+    tidx = torch.randperm(T_all, generator=g)[:T]
+    w = (torch.rand(T, generator=g) < 0.7).float() if weighted else None
+    n = max(T, 1)
+    ref_in = logits.clone().double().requires_grad_()
+    r_ce, r_dice = ops_cpu.mask_losses(ref_in, tgt.double(), qidx, tidx, None if w is None else w.double(), n)
+    gu = torch.tensor([0.7, -1.3])
+    (gu[0] * r_ce + gu[1] * r_dice).backward()
+    cu_in = logits.clone().cuda().requires_grad_()
+    c_ce, c_dice = Fn.mask_losses(cu_in, tgt.cuda(), qidx.cuda(), tidx.cuda(), None if w is None else w.cuda(), n)
+    (gu[0] * c_ce + gu[1] * c_dice).backward()
+    assert abs(float(c_ce) - float(r_ce)) <= 1e-5 * max(abs(float(r_ce)), 1e-6)
+    assert abs(float(c_dice) - float(r_dice)) <= 1e-5 * max(abs(float(r_dice)), 1e-6)
+    if T:
+        assert rel_err(cu_in.grad, ref_in.grad) < 1e-5
+    else:
+        assert float(cu_in.grad.abs().max()) == 0.0
+
+
 def test_segment_mean(eng):
     from oracle import ops_cpu
     from unscene3d_b200.engine import functional as Fn

@@ -269,6 +269,76 @@ k_matcher_cost(const float *__restrict__ logits, int S, int Q, const float *__re
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Mask losses of the set criterion (models/criterion.py:22-73, 168-216): for the matched (query, target) pairs of one scene
+//   loss_mask = sum_t w_t * mean_s BCE(x[s, q_t], y[t_t, s]) / n        loss_dice = sum_t w_t * (1 - (2 sum p y + 1) / (sum p + sum y + 1)) / n
+// One block per pair reads the pair's logit column and target row once; per-pair sums are kept for backward.
+// The reference runs ~20 element-wise / reduction kernels per scene and decoder output for this (x 13 x B per step).
+template <typename TT>
+__global__ void __launch_bounds__(256)
+k_mask_loss_pairs(const float *__restrict__ logits, int S, int Q, const TT *__restrict__ tgt, const int64_t *__restrict__ qidx,
+                  const int64_t *__restrict__ tidx, float *__restrict__ stats) {
+    __shared__ double red[4][8];
+    const int t = blockIdx.x;
+    const int q = (int)qidx[t];
+    const TT *y = tgt + (size_t)tidx[t] * S;
+    double a[4] = {0, 0, 0, 0};
+    for (int s = threadIdx.x; s < S; s += blockDim.x) {
+        const float x = logits[(size_t)s * Q + q];
+        const float z = (float)y[s];
+        a[0] += fmaxf(x, 0.f) - x * z + log1pf(expf(-fabsf(x)));  // binary_cross_entropy_with_logits
+        const float p = 1.f / (1.f + expf(-x));
+        a[1] += p * z;
+        a[2] += p;
+        a[3] += z;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) a[j] += __shfl_xor_sync(0xffffffffu, a[j], o);
+        if ((threadIdx.x & 31) == 0) red[j][threadIdx.x >> 5] = a[j];
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double v = 0;
+        for (int w = 0; w < 8; ++w) v += red[threadIdx.x][w];
+        stats[t * 4 + threadIdx.x] = (float)v;
+    }
+}
+
+// out[0] = loss_mask, out[1] = loss_dice of the scene (fixed summation order)
+__global__ void k_mask_loss_finish(const float *__restrict__ stats, const float *__restrict__ weights, int T, int S, float n, float *out) {
+    if (threadIdx.x != 0) return;
+    float ce = 0.f, dice = 0.f;
+    for (int t = 0; t < T; ++t) {
+        const float w = weights ? weights[t] : 1.f;
+        ce += w * (stats[t * 4] / (float)S);
+        dice += w * (1.f - (2.f * stats[t * 4 + 1] + 1.f) / (stats[t * 4 + 2] + stats[t * 4 + 3] + 1.f));
+    }
+    out[0] = ce / n;
+    out[1] = dice / n;
+}
+
+// dlogits[s, q_t] = g_ce * w / (n S) * (p - y) - g_dice * w / n * (2 y D - (2 num + 1)) p (1 - p) / D^2 ; other columns stay zero
+template <typename TT>
+__global__ void __launch_bounds__(256)
+k_mask_loss_bwd(const float *__restrict__ logits, int S, int Q, const TT *__restrict__ tgt, const int64_t *__restrict__ qidx,
+                const int64_t *__restrict__ tidx, const float *__restrict__ stats, const float *__restrict__ weights, float n,
+                const float *__restrict__ gout, float *__restrict__ dlogits) {
+    const int t = blockIdx.x;
+    const int q = (int)qidx[t];
+    const TT *y = tgt + (size_t)tidx[t] * S;
+    const float w = weights ? weights[t] : 1.f;
+    const float g_ce = gout[0] * w / (n * (float)S), g_dice = gout[1] * w / n;
+    const float num2 = 2.f * stats[t * 4 + 1] + 1.f, D = stats[t * 4 + 2] + stats[t * 4 + 3] + 1.f;
+    for (int s = threadIdx.x; s < S; s += blockDim.x) {
+        const float x = logits[(size_t)s * Q + q];
+        const float z = (float)y[s];
+        const float p = 1.f / (1.f + expf(-x));
+        dlogits[(size_t)s * Q + q] = g_ce * (p - z) - g_dice * (2.f * z * D - num2) * p * (1.f - p) / (D * D);
+    }
+}
+
 static inline int flat_grid2(long long work) {
     long long b = (work + 255) / 256;
     long long cap = (long long)num_sms() * 16;
@@ -354,6 +424,36 @@ int us3d_matcher_cost(const float *logits, int s, int q, const float *tgt, int t
     if (t == 0) return 0;
     dim3 grid(ceil_div(q, 32), t), block(32, 8);
     k_matcher_cost<<<grid, block, 0, (cudaStream_t)stream_>>>(logits, s, q, tgt, t, prob, ncls, labels, w_class, w_mask, w_dice, cost);
+    US3D_LAUNCH_CHECK();
+    return 0;
+}
+
+int us3d_mask_loss_fwd(const float *logits, int s, int q, const void *tgt, int tgt_is_float, const int64_t *qidx, const int64_t *tidx,
+                       int t, const float *weights, float n, float *stats, float *out, void *stream_) {
+    US3D_CHECK_ARG(s > 0 && q > 0 && t >= 0 && n >= 0.f, "mask_loss_fwd: bad shape");  // n == 0 (scene without targets): NaN, as the reference
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (t > 0) {
+        if (tgt_is_float)
+            k_mask_loss_pairs<float><<<t, 256, 0, st>>>(logits, s, q, (const float *)tgt, qidx, tidx, stats);
+        else
+            k_mask_loss_pairs<uint8_t><<<t, 256, 0, st>>>(logits, s, q, (const uint8_t *)tgt, qidx, tidx, stats);
+        US3D_LAUNCH_CHECK();
+    }
+    k_mask_loss_finish<<<1, 32, 0, st>>>(stats, weights, t, s, n, out);
+    US3D_LAUNCH_CHECK();
+    return 0;
+}
+
+int us3d_mask_loss_bwd(const float *logits, int s, int q, const void *tgt, int tgt_is_float, const int64_t *qidx, const int64_t *tidx,
+                       int t, const float *weights, float n, const float *stats, const float *gout, float *dlogits, void *stream_) {
+    US3D_CHECK_ARG(s > 0 && q > 0 && t >= 0 && n >= 0.f, "mask_loss_bwd: bad shape");
+    cudaStream_t st = (cudaStream_t)stream_;
+    US3D_CUDA(cudaMemsetAsync(dlogits, 0, sizeof(float) * (size_t)s * q, st));
+    if (t == 0) return 0;
+    if (tgt_is_float)
+        k_mask_loss_bwd<float><<<t, 256, 0, st>>>(logits, s, q, (const float *)tgt, qidx, tidx, stats, weights, n, gout, dlogits);
+    else
+        k_mask_loss_bwd<uint8_t><<<t, 256, 0, st>>>(logits, s, q, (const uint8_t *)tgt, qidx, tidx, stats, weights, n, gout, dlogits);
     US3D_LAUNCH_CHECK();
     return 0;
 }

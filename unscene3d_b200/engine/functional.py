@@ -699,3 +699,51 @@ def multihead_cross_attention(mha: torch.nn.MultiheadAttention, query, key, valu
     v = torch.nn.functional.linear(value, w[2 * E:], bv)
     ctx = MaskedCrossAttentionFunction.apply(q, k, v, attn_mask, mha.num_heads)
     return mha.out_proj(ctx)
+
+
+# ------------------------------------------------------------------------------------------- set-criterion mask losses
+class MaskLossFunction(torch.autograd.Function):
+    """(loss_mask, loss_dice) of the matched pairs of one scene — models/criterion.py:22-73 applied as in loss_masks
+    (:168-216): logits [S, Q] (pred_masks of the scene), targets [T_all, S] (bool / uint8 / float), matched query ids and
+    target ids [T], per-pair weights or None, the scene's normaliser n.  One pass over each matched column forward, one
+    backward (csrc/decoder_ops.cu)."""
+
+    @staticmethod
+    def forward(ctx, logits, targets, qidx, tidx, weights, n):
+        if not logits.is_cuda:
+            raise RuntimeError("unscene3d_b200 operators run on CUDA tensors only (no CPU fallback)")
+        logits = logits.float().contiguous()
+        S, Q = logits.shape
+        if targets.dtype == torch.bool:
+            targets = targets.view(torch.uint8)
+        elif targets.dtype not in (torch.uint8, torch.float32):
+            targets = targets.float()
+        targets = targets.contiguous()
+        assert targets.shape[1] == S, f"targets have {targets.shape[1]} columns, logits {S} rows"
+        qidx, tidx = qidx.to(logits.device).long().contiguous(), tidx.to(logits.device).long().contiguous()
+        T = qidx.shape[0]
+        w = None if weights is None else weights.float().contiguous()
+        stats = torch.empty((max(T, 1), 4), dtype=torch.float32, device=logits.device)
+        out = torch.empty(2, dtype=torch.float32, device=logits.device)
+        is_float = int(targets.dtype == torch.float32)
+        check(lib.us3d_mask_loss_fwd(logits.data_ptr(), S, Q, targets.data_ptr(), is_float, qidx.data_ptr(), tidx.data_ptr(), T, _ptr(w),
+                                     float(n), stats.data_ptr(), out.data_ptr(), _stream()))
+        ctx.save_for_backward(logits, targets, qidx, tidx, stats)
+        ctx.w, ctx.n, ctx.is_float = w, float(n), is_float
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        logits, targets, qidx, tidx, stats = ctx.saved_tensors
+        S, Q = logits.shape
+        gout = gout.float().contiguous()
+        dlogits = torch.empty_like(logits)
+        check(lib.us3d_mask_loss_bwd(logits.data_ptr(), S, Q, targets.data_ptr(), ctx.is_float, qidx.data_ptr(), tidx.data_ptr(),
+                                     qidx.shape[0], _ptr(ctx.w), ctx.n, stats.data_ptr(), gout.data_ptr(), dlogits.data_ptr(), _stream()))
+        return dlogits, None, None, None, None, None
+
+
+def mask_losses(logits_sq, targets_ts, qidx, tidx, weights, n):
+    """-> (loss_mask, loss_dice) scalars of one scene."""
+    out = MaskLossFunction.apply(logits_sq, targets_ts, qidx, tidx, weights, n)
+    return out[0], out[1]

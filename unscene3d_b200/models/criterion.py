@@ -17,19 +17,18 @@ def _world_size():
     return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
 
-def dice_loss(inputs, targets, num_masks, weights):
-    p = inputs.sigmoid().flatten(1)
-    numerator = 2 * (p * targets).sum(-1)
-    denominator = p.sum(-1) + targets.sum(-1)
-    return (weights * (1 - (numerator + 1) / (denominator + 1))).sum() / num_masks
+def _cuda_mask_losses(logits_sq, targets_ts, qidx, tidx, weights, n):
+    from unscene3d_b200.engine import functional as Fn  # CUDA only: there is no CPU path
 
-
-def sigmoid_ce_loss(inputs, targets, num_masks, weights):
-    loss = weights.view(-1, 1) * F.binary_cross_entropy_with_logits(inputs, targets, reduction="none")
-    return loss.mean(1).sum() / num_masks
+    return Fn.mask_losses(logits_sq, targets_ts, qidx, tidx, weights, n)
 
 
 class SetCriterion(nn.Module):
+    # (loss_mask, loss_dice) of one scene's matched pairs: the libus3d kernels (one pass over the matched columns).  Like the
+    # sparse operators these model files take from `MinkowskiEngine`, the core can be swapped: the CPU tests that run the
+    # definitions over the oracle install the oracle's restatement of dice_loss / sigmoid_ce_loss here (tests/helpers.py).
+    mask_loss_core = None
+
     def __init__(self, num_classes, matcher, weight_dict, eos_coef, losses, num_points, oversample_ratio,
                  importance_sample_ratio, class_weights, directions="xyz", use_droploss=False, droploss_iou_thresh=0.1):
         super().__init__()
@@ -58,25 +57,25 @@ class SetCriterion(nn.Module):
         if self.weight_dict.get("loss_noise_robust", 0) != 0:
             raise NotImplementedError("the tri-plane noise-robust loss (cost_noise_robust != 0) is not built")
         ce, dice, robust = [], [], []
+        core = type(self).mask_loss_core or _cuda_mask_losses
         for b, (map_id, target_id) in enumerate(indices):
-            pred = outputs["pred_masks"][b][:, map_id].T
-            tgt = targets[b][mask_type][target_id]
-            robust.append(torch.as_tensor(0.0, dtype=torch.float32, device=pred.device))
-            if self.num_points != -1:
-                pidx = torch.randperm(tgt.shape[1], device=tgt.device)[:int(self.num_points * tgt.shape[1])]
-            else:
-                pidx = torch.arange(tgt.shape[1], device=tgt.device)
-            n_scene = tgt.shape[0]
-            pred, tgt = pred[:, pidx], tgt[:, pidx]
+            logits = outputs["pred_masks"][b]                 # [S, Q]
+            tgt_all = targets[b][mask_type]                   # [T_all, S]
+            robust.append(torch.as_tensor(0.0, dtype=torch.float32, device=logits.device))
+            if self.num_points != -1:  # sub-sample the points shared by all masks (models/criterion.py:184-191)
+                pidx = torch.randperm(tgt_all.shape[1], device=tgt_all.device)[:int(self.num_points * tgt_all.shape[1])]
+                logits, tgt_all = logits[pidx], tgt_all[:, pidx]
+            n_scene = len(target_id)
+            weights = None
             if self.use_droploss:
+                pred = logits[:, map_id].T
+                tgt = tgt_all[target_id]
                 fg = pred > 0.0
                 iou = (fg * tgt).sum(dim=1) / (fg + tgt).sum(dim=1)
                 weights = (iou >= self.droploss_iou_thresh).float()
-            else:
-                weights = torch.ones(pred.shape[0], device=pred.device)
-            tgt = tgt.float()
-            ce.append(sigmoid_ce_loss(pred, tgt, n_scene, weights))
-            dice.append(dice_loss(pred, tgt, n_scene, weights))
+            l_ce, l_dice = core(logits, tgt_all, map_id, target_id, weights, n_scene)
+            ce.append(l_ce)
+            dice.append(l_dice)
         return {"loss_mask": torch.sum(torch.stack(ce)), "loss_dice": torch.sum(torch.stack(dice)),
                 "loss_noise_robust": torch.sum(torch.stack(robust))}
 
