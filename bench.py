@@ -314,7 +314,7 @@ def run_ours(args):
     # The caching allocator needs a handful of steps to stop growing its pools (two streams allocate: compute and
     # coordinate); a cudaMalloc inside the timed region synchronises the device.  Measured: 3 warm-up steps leave the first
     # timed leg at 22.8 ms/step, the same leg after ~15 steps runs at 19.6; hence at least 20.
-    n_warm = max(args.warmup, 20)
+    n_warm = max(args.warmup, int(os.environ.get("US3D_BENCH_MIN_WARMUP", "20")))  # (lowered only for ncu launch lists)
     for _ in range(n_warm):
         step_resident()
         if rank == 0:
@@ -374,8 +374,9 @@ def run_ours(args):
         achieved = dom_flops / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
         roofline = {"bound": "tensor", "kernel": "us3d::mt::k_spconv_mt (tcgen05 sparse-conv forward + input-gradient launches)",
                     "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                    # dram__bytes_read + write of the 200k-voxel 128->96 k3 launch (ncu --set full); its algorithmic bytes: 179.5e6
-                    "traffic": 171988992,
+                    # dram__bytes_read + write of the 200k-voxel 128->96 k3 launch (ncu --set full, profiles/r1_ncu_full_summary.md:
+                    # 369.1 + 64.6 MB with the rows in neighbour-pattern order; 172.0 MB in natural order); algorithmic bytes: 179.5e6
+                    "traffic": 433717248,
                     "peak_source": peak_src,
                     "timing": "CUDA events recorded around each launch inside libus3d, on the launch stream, during normal steps",
                     "launches_per_step": len(dom) // prof_steps, "kernel_ms_per_step": dom_ms / prof_steps,

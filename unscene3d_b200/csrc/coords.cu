@@ -243,16 +243,24 @@ __global__ void k_kernel_map(const int4 *__restrict__ query, int n_q, Offsets of
 // large map are instead grouped by their presence pattern (bit k = neighbour at offset k): sorted by the pattern with
 // the rarest offsets as the most significant bits, a tile's union pattern covers 67 % of the offsets.
 // Pass 1: pattern per row + how often each offset is present.
-__global__ void k_pattern_count(const int32_t *__restrict__ nbr, int n, int kvol, uint32_t *__restrict__ pattern, unsigned *counts) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t pat = 0;
-    for (int k = 0; k < kvol; ++k) {
-        bool hit = j < n && nbr[(size_t)k * n + j] >= 0;
-        pat |= (uint32_t)hit << k;
-        unsigned b = __ballot_sync(0xffffffffu, hit);
-        if (b && (threadIdx.x & 31) == 0) atomicAdd(&counts[k], __popc(b));
+__global__ void __launch_bounds__(256) k_pattern_count(const int32_t *__restrict__ nbr, int n, int kvol, uint32_t *__restrict__ pattern,
+                                                       unsigned *counts) {
+    __shared__ unsigned s_cnt[32];
+    if (threadIdx.x < 32) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    for (int j0 = blockIdx.x * blockDim.x; j0 < n; j0 += gridDim.x * blockDim.x) {
+        const int j = j0 + threadIdx.x;
+        uint32_t pat = 0;
+        for (int k = 0; k < kvol; ++k) {
+            bool hit = j < n && nbr[(size_t)k * n + j] >= 0;
+            pat |= (uint32_t)hit << k;
+            unsigned b = __ballot_sync(0xffffffffu, hit);
+            if (b && (threadIdx.x & 31) == 0) atomicAdd(&s_cnt[k], __popc(b));  // block-local: 27 global atomics per block
+        }
+        if (j < n) pattern[j] = pat;
     }
-    if (j < n) pattern[j] = pat;
+    __syncthreads();
+    if (threadIdx.x < kvol && s_cnt[threadIdx.x]) atomicAdd(&counts[threadIdx.x], s_cnt[threadIdx.x]);
 }
 // Pass 2: sort key = pattern with its bits permuted by presence count (most frequent offset -> bit 0; ties by offset index)
 __global__ void k_pattern_key(const uint32_t *__restrict__ pattern, int n, int kvol, const unsigned *__restrict__ counts,
@@ -411,7 +419,9 @@ int us3d_neighbour_pattern_keys(const int32_t *nbr, int n_rows, int kvol, uint32
     if (n_rows == 0) return 0;
     unsigned *counts = scratch + n_rows;  // scratch: uint32[n_rows + 32] (patterns, then the per-offset counts)
     US3D_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned) * 32, st));
-    k_pattern_count<<<ceil_div(n_rows, 256), 256, 0, st>>>(nbr, n_rows, kvol, scratch, counts);
+    int blocks = ceil_div(n_rows, 256);
+    if (blocks > num_sms() * 4) blocks = num_sms() * 4;
+    k_pattern_count<<<blocks, 256, 0, st>>>(nbr, n_rows, kvol, scratch, counts);
     US3D_LAUNCH_CHECK();
     k_pattern_key<<<ceil_div(n_rows, 256), 256, 0, st>>>(scratch, n_rows, kvol, counts, keys);
     US3D_LAUNCH_CHECK();
