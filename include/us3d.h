@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define US3D_ABI_VERSION 11
+#define US3D_ABI_VERSION 12
 #define US3D_MAX_KVOL 27
 
 int us3d_abi_version(void);
@@ -49,6 +49,12 @@ int us3d_hash_capacity(int n);
 int us3d_coords_unique(const int32_t *coords, int n, int tsx, int tsy, int tsz, uint64_t *keys, int32_t *vals,
                        int cap, int32_t *out_coords, int32_t *out_first, int32_t *inverse, int32_t *scratch,
                        int *out_count_h, void *stream);
+
+/* HOST variant for the data-loader side: the reference calls ME.utils.sparse_quantize on CPU arrays inside forked DataLoader
+ * workers (datasets/utils.py:266-270, 403-408; conf/data/indoor.yaml:24), where no CUDA context may be created.  Host
+ * pointers only: unique rows of coords_h[n, d] (d <= 8) in order of first occurrence; first_h[u] = input row of unique row u,
+ * inverse_h[i] = unique row of input row i.  Returns the number of unique rows (>= 0) or a negative error.            */
+int us3d_coords_unique_h(const int32_t *coords_h, int n, int d, int32_t *first_h, int32_t *inverse_h);
 
 /* Neighbour table ("kernel map", ME KernelGenerator HYPER_CUBE, models/modules/common.py:137-144):
  *   nbr[k*n_q + q] = row r of the hashed map with coords_r == query[q] + offsets_h[k]  (or -1).

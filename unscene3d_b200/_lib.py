@@ -17,6 +17,7 @@ PROTOTYPES = {
     "us3d_reset_launch_count": [],
     "us3d_hash_capacity": [_i],
     "us3d_coords_unique": [_p, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p, _p, ctypes.POINTER(_i), _p],
+    "us3d_coords_unique_h": [_p, _i, _i, _p, _p],
     "us3d_kernel_map": [_p, _i, ctypes.POINTER(ctypes.c_int32), _i, _p, _p, _i, _p, _p, _i, _p],
     "us3d_spconv_gather": [_p, _i, _p, _i, _i, _p, _i, _i, _i, _i, _p, _p, _p, _i, _i, _p, _p],
     "us3d_spconv_tc_supported": [_i, _i],

@@ -440,4 +440,41 @@ int us3d_kernel_map_reorder(const int32_t *nbr, int n_rows, int kvol, const int3
     return 0;
 }
 
+/* HOST function (host pointers, no CUDA context: fork-safe, as ME.utils.sparse_quantize in the reference's DataLoader workers,
+ * datasets/utils.py:266-270, 403-408).  Unique rows of coords_h [n, d] (int32, d <= 8) in order of first occurrence:
+ * first_h[u] = input row of unique row u (ascending), inverse_h[i] = unique row of input row i.  Returns the number of unique
+ * rows, or a negative error. */
+int us3d_coords_unique_h(const int32_t *coords_h, int n, int d, int32_t *first_h, int32_t *inverse_h) {
+    US3D_CHECK_ARG(n >= 0 && d >= 1 && d <= 8, "coords_unique_h: bad shape");
+    if (n == 0) return 0;
+    size_t cap = 1024;
+    while (cap < (size_t)n * 2) cap <<= 1;
+    std::vector<int32_t> slot(cap, -1);  // unique row stored in each slot
+    int count = 0;
+    for (int i = 0; i < n; ++i) {
+        const int32_t *c = coords_h + (size_t)i * d;
+        uint64_t h = 0x9E3779B97F4A7C15ull;
+        for (int a = 0; a < d; ++a) {
+            h ^= (uint64_t)(uint32_t)c[a] + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+            h *= 0xBF58476D1CE4E5B9ull;
+        }
+        size_t p = (size_t)(h ^ (h >> 31)) & (cap - 1);
+        for (;;) {
+            const int32_t u = slot[p];
+            if (u < 0) {
+                slot[p] = count;
+                first_h[count] = i;
+                inverse_h[i] = count++;
+                break;
+            }
+            if (memcmp(coords_h + (size_t)first_h[u] * d, c, sizeof(int32_t) * d) == 0) {
+                inverse_h[i] = u;
+                break;
+            }
+            p = (p + 1) & (cap - 1);
+        }
+    }
+    return count;
+}
+
 }  // extern "C"

@@ -1,21 +1,17 @@
 """ME.utils.sparse_quantize / sparse_collate / batched_coordinates (SURVEY.md Appendix A.13, A.14;
 call sites datasets/utils.py:266-287, 403-432).
 
-The reference runs these on the CPU inside DataLoader workers; here the de-duplication is the same
-hash kernel that builds coordinate maps (csrc/coords.cu), so they need a CUDA context and must be
-called from the main process (documented in DESIGN.md, "out of scope": forked workers).
+The reference runs these on the CPU inside forked DataLoader workers (conf/data/indoor.yaml:24), where a CUDA context
+must not be created: host inputs (numpy arrays, CPU tensors) are de-duplicated by a HOST function of libus3d
+(us3d_coords_unique_h, sequential open-addressing hash — the algorithm of ME's CPU path), CUDA tensors by the hash
+kernels that build coordinate maps (csrc/coords.cu).  Same results either way: unique rows in first-occurrence order.
 Inputs may be numpy arrays or CPU/CUDA torch tensors; results come back in the input's flavour.
 """
 import numpy as np
 import torch
 
+from .._lib import check, lib
 from .coords import unique_coords
-
-
-def _device():
-    if not torch.cuda.is_available():
-        raise RuntimeError("unscene3d_b200.sparse_quantize needs a CUDA device (no CPU fallback)")
-    return torch.device("cuda", torch.cuda.current_device())
 
 
 def sparse_quantize(coordinates, features=None, labels=None, ignore_label=-100, return_index=False,
@@ -24,15 +20,25 @@ def sparse_quantize(coordinates, features=None, labels=None, ignore_label=-100, 
     c = torch.from_numpy(np.ascontiguousarray(coordinates)) if is_np else coordinates
     assert c.ndim == 2, "coordinates must be [N, D]"
     home = c.device
-    dev = home if home.type == "cuda" else _device()
-    c = c.to(dev)
+    dev = home
     if quantization_size is not None:
         c = c.double() / torch.as_tensor(quantization_size, dtype=torch.float64, device=dev)
     if c.dtype.is_floating_point:
         c = torch.floor(c)
-    disc = c.to(torch.int32)
-    rows = torch.cat([torch.zeros((disc.shape[0], 1), dtype=torch.int32, device=dev), disc], 1)
-    cmap, first, inverse = unique_coords(rows, (1, 1, 1))
+    disc = c.to(torch.int32).contiguous()
+    if home.type == "cuda":
+        rows = torch.cat([torch.zeros((disc.shape[0], 1), dtype=torch.int32, device=dev), disc], 1)
+        cmap, first, inverse = unique_coords(rows, (1, 1, 1))
+        unique_rows = cmap.coords[:, 1:].contiguous()
+    else:  # host path: no CUDA context (fork-safe)
+        n, d = disc.shape
+        first = torch.empty(max(n, 1), dtype=torch.int32)
+        inverse = torch.empty(max(n, 1), dtype=torch.int32)
+        m = lib.us3d_coords_unique_h(disc.data_ptr(), n, d, first.data_ptr(), inverse.data_ptr())
+        if m < 0:
+            check(m)
+        first, inverse = first[:m], inverse[:n]
+        unique_rows = disc[first.long()]
     first, inverse = first.long(), inverse.long()
 
     def back(t):
@@ -49,7 +55,7 @@ def sparse_quantize(coordinates, features=None, labels=None, ignore_label=-100, 
         out_labels[bad] = ignore_label
     if return_maps_only:
         return (back(first), back(inverse)) if return_inverse else back(first)
-    ret = [back(cmap.coords[:, 1:].contiguous())]
+    ret = [back(unique_rows)]
     if features is not None:
         if isinstance(features, torch.Tensor):
             ret.append(features[first.to(features.device)])
