@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define US3D_ABI_VERSION 12
+#define US3D_ABI_VERSION 13
 #define US3D_MAX_KVOL 27
 
 int us3d_abi_version(void);
@@ -266,6 +266,13 @@ int us3d_xattn_bwd(const float *q, const float *k, const float *v, const uint8_t
  * prob[q,ncls] softmaxed class probabilities, labels[t] int64 (253 = ignore -> class cost -1).     */
 int us3d_matcher_cost(const float *logits, int s, int q, const float *tgt, int t, const float *prob, int ncls,
                       const int64_t *labels, float w_class, float w_mask, float w_dice, float *cost, void *stream);
+
+/* Attention masks of the decoder rounds (Mask3D.mask_module, models/mask3d.py:407-446: segment logits gathered to the voxels,
+ * MinkowskiAvgPooling x 1..4, `sigmoid < 0.5`) as one sparse product: rowptr[n_rows+1] / col / val = CSR matrix A of the nested
+ * average pooling composed with the voxel -> segment map (int64 indices, fp32 weights), seg[s_total, q] the segment logits;
+ * bits[n_rows, q] (uint8) = sigmoid(A seg) < 0.5.                                                                  */
+int us3d_pooled_mask_bits(const int64_t *rowptr, const int64_t *col, const float *val, int n_rows, const float *seg, int q,
+                          uint8_t *bits, void *stream);
 
 /* Mask losses of the set criterion for the matched pairs of one scene (models/criterion.py:22-73 dice_loss / sigmoid_ce_loss,
  * called from loss_masks :168-216):  logits[s, q] fp32 (pred_masks of the scene), tgt[t_all, s] (float32, or uint8 / bool when

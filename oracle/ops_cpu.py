@@ -150,6 +150,19 @@ def mask_losses(logits_sq, targets_ts, qidx, tidx, weights, n):
     return sigmoid_ce_loss(pred, tgt, n, w), dice_loss(pred, tgt, n, w)
 
 
+def segment_attention_masks(model, mask_features, output_segments, point2segment, num_pooling_steps):
+    """models/mask3d.py:419-446 as the reference runs it: segment logits gathered to the voxels, concatenated into a
+    SparseTensor on mask_features' map, average-pooled `num_pooling_steps` times, `sigmoid < 0.5`."""
+    ST = type(mask_features)
+    output_masks = [seg[p2s] for seg, p2s in zip(output_segments, point2segment)]
+    attn_mask = ST(features=torch.cat(output_masks), coordinate_manager=mask_features.coordinate_manager,
+                   coordinate_map_key=mask_features.coordinate_map_key)
+    for _ in range(num_pooling_steps):
+        attn_mask = model.pooling(attn_mask.float())
+    return ST(features=(attn_mask.F.detach().sigmoid() < 0.5), coordinate_manager=attn_mask.coordinate_manager,
+              coordinate_map_key=attn_mask.coordinate_map_key)
+
+
 def as_module_tree():
     """Module objects `torch_scatter`, `pointnet2`, `pointnet2._ext` exporting the CPU restatements."""
     import types

@@ -83,6 +83,7 @@ def our_models_on_oracle():
     mod = load_package(os.path.join(REPO, "unscene3d_b200", "models"), "oracle_backed_models", oracle_me_modules())
     mod.mask3d.CrossAttentionLayer.attention_core = staticmethod(ops_cpu.multihead_cross_attention)
     mod.criterion.SetCriterion.mask_loss_core = staticmethod(ops_cpu.mask_losses)
+    mod.mask3d.Mask3D.segment_attention_core = staticmethod(ops_cpu.segment_attention_masks)
     return mod
 
 

@@ -67,6 +67,11 @@ def test_sparse_quantize_matches_oracle(eng, ora):
     exp = ora.sparse_quantize(pts, labels=labels, return_index=True, return_inverse=True, quantization_size=0.25)
     for g, e in zip(got, exp):
         assert np.array_equal(np.asarray(g), np.asarray(e))
+    # CUDA tensors go through the hash kernels (host inputs through the host function, tests/test_quantize.py)
+    got = eng.sparse_quantize(torch.from_numpy(pts).cuda(), labels=torch.from_numpy(labels).cuda(), return_index=True, return_inverse=True,
+                              quantization_size=0.25)
+    for g, e in zip(got, exp):
+        assert g.is_cuda and np.array_equal(g.cpu().numpy(), np.asarray(e))
 
 
 def table_to_pairs(nbr):
@@ -542,6 +547,40 @@ def test_mask_losses_match_oracle(eng, S, Q, T_all, T, tgt_dtype, weighted):
         assert rel_err(cu_in.grad, ref_in.grad) < 1e-5
     else:
         assert float(cu_in.grad.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("steps", [1, 2, 4])
+def test_segment_attention_masks_equal_gather_pool_threshold(eng, steps):
+    """Decoder attention masks (models/mask3d.py:419-446): the sparse product sigmoid(A seg) < 0.5 against the reference's
+    sequence run with this engine's own kernels (gather to the voxels, concatenate, MinkowskiAvgPooling x steps, threshold).
+    Both are fp32 sums in different orders: entries whose pooled logit lies within 1e-5 of zero may differ, nothing else."""
+    from unscene3d_b200.engine import functional as Fn
+
+    c = random_scene(6000, 41, batch=3, extent=40)
+    g = torch.Generator().manual_seed(1)
+    x = eng.SparseTensor(torch.zeros(c.shape[0], 1, device="cuda"), torch.from_numpy(c).cuda())
+    Q = 100
+    p2s, seg = [], []
+    for coords_b in x.decomposed_coordinates:
+        S = 37 + len(p2s) * 11
+        ids = torch.randint(0, S, (coords_b.shape[0],), generator=g)
+        ids[:S] = torch.arange(S)
+        p2s.append(ids.cuda())
+        seg.append((torch.randn(S, Q, generator=g) * 2).cuda())
+    key, bits = Fn.segment_attention_masks(x, seg, p2s, steps)
+    t = eng.SparseTensor(torch.cat([s[p] for s, p in zip(seg, p2s)]), coordinate_map_key=x.coordinate_map_key,
+                         coordinate_manager=x.coordinate_manager)
+    pool = eng.MinkowskiAvgPooling(kernel_size=2, stride=2, dimension=3)
+    for _ in range(steps):
+        t = pool(t)
+    assert t.coordinate_map_key == key and bits.shape == t.F.shape and bits.dtype == torch.bool
+    want = t.F.sigmoid() < 0.5
+    differ = want != bits
+    assert int(differ.sum()) <= 1e-4 * bits.numel()
+    assert float(t.F[differ].abs().max()) < 1e-5 if bool(differ.any()) else True
+    # second call re-uses the cached matrix
+    key2, bits2 = Fn.segment_attention_masks(x, seg, p2s, steps)
+    assert key2 == key and torch.equal(bits2, bits)
 
 
 def test_segment_mean(eng):

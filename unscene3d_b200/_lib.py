@@ -70,6 +70,7 @@ PROTOTYPES = {
     "us3d_freemask_row_stats": [_p, _i, _i, _i, _f, _p, _p, _p, _p, _p, _p, _p, _p],
     "us3d_freemask_weighted_inter": [_p, _i, _i, _i, _f, _p, _p, _p],
     "us3d_freemask_separate_h": [_p, _i, _i, _p, _p, _p, _p, _p, _i, _ll],
+    "us3d_pooled_mask_bits": [_p, _p, _p, _i, _p, _i, _p, _p],
     "us3d_mask_loss_fwd": [_p, _i, _i, _p, _i, _p, _p, _i, _p, _f, _p, _p, _p],
     "us3d_mask_loss_bwd": [_p, _i, _i, _p, _i, _p, _p, _i, _p, _f, _p, _p, _p, _p],
     "us3d_matcher_cost": [_p, _i, _i, _p, _i, _p, _i, _p, _f, _f, _f, _p, _p],

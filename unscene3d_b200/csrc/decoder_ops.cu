@@ -339,6 +339,25 @@ k_mask_loss_bwd(const float *__restrict__ logits, int S, int Q, const TT *__rest
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Attention masks of the decoder rounds (models/mask3d.py:407-446) without the point-level detour.  The reference gathers the
+// segment logits to every voxel ([sum N, Q] fp32), wraps them in a SparseTensor, average-pools 1..4 times and thresholds.
+// Nested average pooling is linear, so the pooled logit of a coarse voxel v is sum_s A[v, s] * seglogit[s, :] with a sparse
+// matrix A (CSR, built once per step from the coordinate manager's parent maps, a few entries per row):
+//     bits[v, q] = sigmoid( sum_e val[e] * seg[col[e], q] ) < 0.5
+__global__ void __launch_bounds__(128)
+k_pooled_mask_bits(const int64_t *__restrict__ rowptr, const int64_t *__restrict__ col, const float *__restrict__ val, int n_rows,
+                   const float *__restrict__ seg, int Q, uint8_t *__restrict__ bits) {
+    for (int r = blockIdx.x; r < n_rows; r += gridDim.x) {
+        const long long e0 = rowptr[r], e1 = rowptr[r + 1];
+        for (int q = threadIdx.x; q < Q; q += blockDim.x) {
+            float acc = 0.f;
+            for (long long e = e0; e < e1; ++e) acc = fmaf(val[e], seg[(size_t)col[e] * Q + q], acc);
+            bits[(size_t)r * Q + q] = (1.f / (1.f + expf(-acc))) < 0.5f ? 1 : 0;
+        }
+    }
+}
+
 static inline int flat_grid2(long long work) {
     long long b = (work + 255) / 256;
     long long cap = (long long)num_sms() * 16;
@@ -454,6 +473,16 @@ int us3d_mask_loss_bwd(const float *logits, int s, int q, const void *tgt, int t
         k_mask_loss_bwd<float><<<t, 256, 0, st>>>(logits, s, q, (const float *)tgt, qidx, tidx, stats, weights, n, gout, dlogits);
     else
         k_mask_loss_bwd<uint8_t><<<t, 256, 0, st>>>(logits, s, q, (const uint8_t *)tgt, qidx, tidx, stats, weights, n, gout, dlogits);
+    US3D_LAUNCH_CHECK();
+    return 0;
+}
+
+int us3d_pooled_mask_bits(const int64_t *rowptr, const int64_t *col, const float *val, int n_rows, const float *seg, int q,
+                          uint8_t *bits, void *stream_) {
+    US3D_CHECK_ARG(n_rows >= 0 && q > 0, "pooled_mask_bits: bad shape");
+    if (n_rows == 0) return 0;
+    int grid = n_rows < num_sms() * 16 ? n_rows : num_sms() * 16;
+    k_pooled_mask_bits<<<grid, 128, 0, (cudaStream_t)stream_>>>(rowptr, col, val, n_rows, seg, q, bits);
     US3D_LAUNCH_CHECK();
     return 0;
 }

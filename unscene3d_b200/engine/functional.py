@@ -747,3 +747,81 @@ def mask_losses(logits_sq, targets_ts, qidx, tidx, weights, n):
     """-> (loss_mask, loss_dice) scalars of one scene."""
     out = MaskLossFunction.apply(logits_sq, targets_ts, qidx, tidx, weights, n)
     return out[0], out[1]
+
+
+# ------------------------------------------------------------------------------------------- decoder attention masks
+def _segment_pool_matrix(cm, key0, point2segment, sizes, steps):
+    """CSR matrix A_L [N_L, S_total] with  avgpool^L(seglogit[point2segment])[v, :] = sum_s A_L[v, s] seglogit[s, :]  for the
+    coordinate manager's pyramid below `key0`: A_0[p, seg(p)] = 1, A_{l+1}[v, :] = mean over the present children u of A_l[u, :]
+    (MinkowskiAvgPooling(k2, s2) = mean over present inputs).  Built level by level from the parent maps, once per
+    coordinate manager (i.e. per step) and level; returns (key_L, rowptr, col, val, S_total)."""
+    cache = cm.__dict__.setdefault("_segment_pool", {})
+    sig = (key0, tuple(int(p.data_ptr()) for p in point2segment))
+    entry = cache.get(sig)
+    if entry is None:
+        dev = point2segment[0].device
+        offs, tot = [], 0
+        for s in sizes:
+            offs.append(tot)
+            tot += s
+        cols = torch.cat([p.long() + o for p, o in zip(point2segment, offs)])
+        n0 = cm.size(key0)
+        assert cols.shape[0] == n0, "point2segment does not cover the coordinate map"
+        entry = cache[sig] = {"S": tot, "levels": [(key0, torch.arange(n0, device=dev), cols, torch.ones(n0, dtype=torch.float32, device=dev))]}
+    levels = entry["levels"]
+    while len(levels) <= steps:
+        key, rows, cols, vals = levels[-1]
+        nxt = cm.stride(key, (2, 2, 2))
+        parent = cm._parents[(key, nxt)].long()
+        n_next = cm.size(nxt)
+        count = torch.bincount(parent, minlength=n_next).float()
+        prow = parent[rows]
+        merged, inv = torch.unique(prow * entry["S"] + cols, return_inverse=True)
+        v2 = torch.zeros(merged.shape[0], dtype=torch.float32, device=vals.device).index_add_(0, inv, vals / count[prow])
+        levels.append((nxt, merged // entry["S"], merged % entry["S"], v2))
+    key, rows, cols, vals = levels[steps]
+    csr = entry.setdefault("csr", {})
+    if steps not in csr:
+        n = cm.size(key)
+        rowptr = torch.zeros(n + 1, dtype=torch.int64, device=rows.device)
+        rowptr[1:] = torch.cumsum(torch.bincount(rows, minlength=n), 0)   # rows are sorted (level 0: arange; above: unique keys)
+        csr[steps] = (rowptr, cols.contiguous(), vals.contiguous())
+    return (key, *csr[steps], entry["S"])
+
+
+def prepare_segment_attention(x, point2segment, max_steps):
+    """Builds the pooling matrices of every decoder level ahead of the backbone, on the coordinate stream when one is set
+    (engine.set_coordinate_stream): they depend on coordinates and segment ids only, and de-duplicating their entries hands
+    sizes back to the host — on the compute stream, in the middle of the decoder, each of those synchronisations would wait
+    for the queued backbone kernels and cost the host its run-ahead."""
+    from .coords import get_coordinate_stream
+
+    cm, key0 = x.coordinate_manager, x.coordinate_map_key
+    side = get_coordinate_stream(point2segment[0].device)
+    if side is None:
+        sizes = [int(p.max()) + 1 if p.numel() else 0 for p in point2segment]
+        _segment_pool_matrix(cm, key0, point2segment, sizes, max_steps)
+        return
+    main = torch.cuda.current_stream(point2segment[0].device)
+    with torch.cuda.stream(side):
+        sizes = [int(p.max()) + 1 if p.numel() else 0 for p in point2segment]
+        for steps in range(1, max_steps + 1):
+            for t in _segment_pool_matrix(cm, key0, point2segment, sizes, steps)[1:4]:
+                t.record_stream(main)
+    main.wait_stream(side)
+
+
+def segment_attention_masks(mask_features, seg_logits, point2segment, num_pooling_steps):
+    """Boolean attention mask of one decoder round at the level `num_pooling_steps` strides below `mask_features`
+    (Mask3D.mask_module, models/mask3d.py:419-446): features [N_L, Q] bool = sigmoid(avgpool^L(seg_logits[point2segment])) < 0.5,
+    as a (key, tensor) pair on mask_features' coordinate manager.  One sparse product instead of the point-level gather,
+    the concatenation and L pooling passes over [sum N, Q] floats."""
+    cm = mask_features.coordinate_manager
+    sizes = [int(s.shape[0]) for s in seg_logits]  # rows of scatter_mean's output per scene (index.max() + 1, mask3d.py:223)
+    key, rowptr, col, val, s_total = _segment_pool_matrix(cm, mask_features.coordinate_map_key, point2segment, sizes, num_pooling_steps)
+    seg = torch.cat([s.detach() for s in seg_logits]).float().contiguous()
+    assert seg.shape[0] == s_total, f"{seg.shape[0]} segment rows, point2segment addresses {s_total}"
+    n, q = rowptr.shape[0] - 1, seg.shape[1]
+    bits = torch.empty((n, q), dtype=torch.uint8, device=seg.device)
+    check(lib.us3d_pooled_mask_bits(rowptr.data_ptr(), col.data_ptr(), val.data_ptr(), n, seg.data_ptr(), q, bits.data_ptr(), _stream()))
+    return key, bits.view(torch.bool)

@@ -118,6 +118,19 @@ class HeadSharedMask:
         return self.bkq.repeat_interleave(num_heads, dim=0).permute((0, 2, 1))
 
 
+def _cuda_segment_attention_core(model, mask_features, output_segments, point2segment, num_pooling_steps):
+    from unscene3d_b200.engine import functional as Fn  # CUDA only: there is no CPU path
+
+    key, bits = Fn.segment_attention_masks(mask_features, output_segments, point2segment, num_pooling_steps)
+    return me.SparseTensor(features=bits, coordinate_manager=mask_features.coordinate_manager, coordinate_map_key=key)
+
+
+def _cuda_prepare_segment_attention(x, point2segment, max_steps):
+    from unscene3d_b200.engine import functional as Fn
+
+    Fn.prepare_segment_attention(x, point2segment, max_steps)
+
+
 def _cuda_attention_core(mha, query, key, value, attn_mask=None):
     from unscene3d_b200.engine import functional as Fn  # CUDA only: there is no CPU path
 
@@ -169,6 +182,10 @@ class FFNLayer(_DecoderLayer):
 
 
 class Mask3D(nn.Module):
+    # Attention mask of a decoder round from the SEGMENT logits (train_on_segments): the libus3d sparse product
+    # (engine.functional.segment_attention_masks).  Swappable like the sparse operators: the CPU tests that run this file over
+    # the oracle install the reference's sequence (gather to the voxels, concatenate, pool, threshold) from oracle/ops_cpu.py.
+    segment_attention_core = None
     def __init__(self, config, hidden_dim, num_queries, num_heads, dim_feedforward, sample_sizes, shared_decoder,
                  num_classes, num_decoders, dropout, pre_norm, positional_encoding_type, non_parametric_queries,
                  train_on_segments, normalize_pos_enc, use_level_embed, scatter_type, hlevels, use_np_features,
@@ -242,8 +259,14 @@ class Mask3D(nn.Module):
 
     # ------------------------------------------------------------------------------------------------
     def get_pos_encs(self, coords):
+        """Fourier encodings of the pooled raw coordinates, per level and scene (models/mask3d.py:183-198).  The reference
+        encodes all five levels and reads only those in `hlevels`; the unused ones (the full-resolution level: [N, 128] fp32
+        per scene) are skipped here."""
         out = []
-        for level in coords:
+        for i, level in enumerate(coords):
+            if i not in self.hlevels:
+                out.append([None])
+                continue
             per_scene = []
             for xyz in level.decomposed_features:
                 lo, hi = xyz.min(dim=0)[0][None, ...], xyz.max(dim=0)[0][None, ...]
@@ -254,6 +277,8 @@ class Mask3D(nn.Module):
         return out
 
     def forward(self, x, point2segment=None, raw_coordinates=None, is_eval=False):
+        if self.train_on_segments and point2segment is not None and type(self).segment_attention_core is None:
+            _cuda_prepare_segment_attention(x, point2segment, len(self.sample_sizes) - 1 - min(self.hlevels))  # pooling steps of the coarsest level used
         pcd_features, aux = self.backbone(x)
         n_scenes = len(x.decomposed_coordinates)
 
@@ -373,14 +398,20 @@ class Mask3D(nn.Module):
         if point2segment is not None:
             for i in range(len(mask_segments)):
                 output_segments.append(mask_segments[i] @ mask_embed[i].T)
-                output_masks.append(output_segments[-1][point2segment[i]])
         else:
             per_scene = mask_features.decomposed_features
             for i in range(int(mask_features.C[-1, 0]) + 1):
                 output_masks.append(per_scene[i] @ mask_embed[i].T)
+        if point2segment is not None:
+            if not ret_attn_mask:
+                return outputs_class, output_segments
+            core = type(self).segment_attention_core
+            if core is None:
+                core = _cuda_segment_attention_core
+            return outputs_class, output_segments, core(self, mask_features, output_segments, point2segment, num_pooling_steps)
         outputs_mask = me.SparseTensor(features=torch.cat(output_masks), coordinate_manager=mask_features.coordinate_manager,
                                        coordinate_map_key=mask_features.coordinate_map_key)
-        result_masks = output_segments if point2segment is not None else outputs_mask.decomposed_features
+        result_masks = outputs_mask.decomposed_features
         if not ret_attn_mask:
             return outputs_class, result_masks
         attn_mask = outputs_mask
