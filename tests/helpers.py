@@ -84,6 +84,7 @@ def our_models_on_oracle():
     mod.mask3d.CrossAttentionLayer.attention_core = staticmethod(ops_cpu.multihead_cross_attention)
     mod.criterion.SetCriterion.mask_loss_core = staticmethod(ops_cpu.mask_losses)
     mod.mask3d.Mask3D.segment_attention_core = staticmethod(ops_cpu.segment_attention_masks)
+    mod.modules.resnet_block._ResidualBase.block_core = staticmethod(lambda block, x: None)  # the reference's own sequence
     return mod
 
 

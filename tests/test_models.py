@@ -151,3 +151,44 @@ def _backbone_live():
             assert rel(bg[k], bc[k]) < 1e-4, k
         if k.endswith("num_batches_tracked"):
             assert int(bg[k]) == int(bc[k])
+
+
+@pytest.mark.gpu
+def test_fused_residual_blocks_equal_the_module_route():
+    """engine.blocks runs a BasicBlock as ONE autograd node issuing the same kernels in the same order: forward bit-identical,
+    gradients equal up to the order of the weight-gradient atomics (1e-5); training and eval mode."""
+    import unscene3d_b200  # noqa: F401
+    from unscene3d_b200 import engine, models
+    from unscene3d_b200.engine import blocks
+
+    c = random_scene(6000, 78, batch=2, extent=36)
+    torch.manual_seed(5)
+    f = torch.randn(c.shape[0], 3).cuda()
+    net = models.Res16UNet34C(3, 20, Cfg(), D=3, out_fpn=True)
+    st = deterministic_state(net, 13)
+    w = torch.linspace(-1, 1, 96).cuda()
+    runs = {}
+    for train in (True, False):
+        for fused in (True, False):
+            blocks.set_fused_blocks(fused)
+            try:
+                net.load_state_dict(st)
+                net = net.cuda().train(train)
+                out, aux = net(engine.SparseTensor(f, torch.from_numpy(c).cuda()))
+                (out.F * w).mean().backward()
+                grads = {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}
+                bufs = {k: b.clone() for k, b in net.named_buffers()}
+                net.zero_grad(set_to_none=True)
+                runs[(train, fused)] = (out.F.detach().clone(), [a.F.detach().clone() for a in aux], grads, bufs)
+            finally:
+                blocks.set_fused_blocks(True)
+        a, b = runs[(train, True)], runs[(train, False)]
+        assert torch.equal(a[0], b[0])
+        for u, v in zip(a[1], b[1]):
+            assert torch.equal(u, v)
+        assert a[2].keys() == b[2].keys()
+        for k in a[2]:
+            err = float((a[2][k].double() - b[2][k].double()).norm() / b[2][k].double().norm().clamp(min=1e-30))
+            assert err < 1e-4, (k, err)
+        for k in a[3]:
+            assert torch.equal(a[3][k], b[3][k]), k   # running statistics, num_batches_tracked

@@ -329,6 +329,23 @@ def _wgrad_tc_ok(cin, cout):  # == us3d_spconv_wgrad_tc_supported, without the F
     return cin >= 8 and cin % 8 == 0 and cout >= 16 and cout % 16 == 0 and cout <= 256
 
 
+def conv_input_gradient(dy, kernel, w3, bwd_getter, flip_dgrad):
+    """dX of a convolution: the same gather kernel on the transposed table with W^T (column slices for gradients wider than
+    256 channels, written in place)."""
+    cin, cout = w3.shape[1], w3.shape[2]
+    bwd, flip = bwd_getter()
+    mode = _precision["mode"]
+    chunks = None
+    if mode != 0 and flip == flip_dgrad and cin > 4:
+        chunks = packed_weights(kernel, w3, flip, mode, True)[1]
+    if chunks is None or len(chunks) == 1:
+        return spconv_gather(dy, bwd, w3, cout, cin, True, flip, wpack=None if chunks is None else chunks[0][2])
+    dx = torch.empty((bwd.n_rows, cin), dtype=torch.float32, device=dy.device)
+    for c0, nc, img in chunks:
+        spconv_gather(dy, bwd, w3[:, c0:c0 + nc, :], cout, nc, True, flip, out=dx[:, c0:c0 + nc], wpack=img)
+    return dx
+
+
 class SparseConvFunction(torch.autograd.Function):
     """Y = conv(X) over `fwd` ([K, n_out] neighbour table); backward uses `bwd` ([K, n_in], flip flag).
     `flip_dgrad` is the flag the backward table will carry (known from the map pair at forward time), so that the
@@ -361,17 +378,7 @@ class SparseConvFunction(torch.autograd.Function):
         cin, cout = w3.shape[1], w3.shape[2]
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            bwd, flip = ctx.bwd_getter()
-            mode = _precision["mode"]
-            chunks = None
-            if mode != 0 and flip == ctx.flip_dgrad and cin > 4:
-                chunks = packed_weights(kernel, w3, flip, mode, True)[1]
-            if chunks is None or len(chunks) == 1:
-                dx = spconv_gather(dy, bwd, w3, cout, cin, True, flip, wpack=None if chunks is None else chunks[0][2])
-            else:  # wide gradient: column slices of the transposed weight, written in place into dx
-                dx = torch.empty((bwd.n_rows, cin), dtype=torch.float32, device=dy.device)
-                for c0, nc, img in chunks:
-                    spconv_gather(dy, bwd, w3[:, c0:c0 + nc, :], cout, nc, True, flip, out=dx[:, c0:c0 + nc], wpack=img)
+            dx = conv_input_gradient(dy, kernel, w3, ctx.bwd_getter, ctx.flip_dgrad)
         if ctx.needs_input_grad[1]:
             dw = spconv_wgrad(x, fwd, dy, cin, cout).view(kernel.shape)
         if ctx.has_bias and ctx.needs_input_grad[2]:
@@ -411,6 +418,50 @@ def _want_planes(c):
     return _precision["mode"] != 0 and c % 16 == 0
 
 
+def bn_apply_raw(x, gamma, beta, residual, mean, invstd, relu):
+    """One pass: y = [relu](bn(x) [+ residual]) as fp32 rows + the bf16 planes of y (cached on y for the next convolution).
+    Returns (y, gamma as passed to the kernel)."""
+    n, c = x.shape
+    dev = x.device
+    if residual is not None:
+        residual = _rows(residual)
+    g = gamma.detach().contiguous() if gamma is not None else torch.ones(c, device=dev)
+    b = beta.detach().contiguous() if beta is not None else torch.zeros(c, device=dev)
+    y = torch.empty((n, c), dtype=torch.float32, device=dev)
+    hi = lo = None
+    if _want_planes(c) and n > 0:
+        hi = torch.empty((n, c), dtype=torch.bfloat16, device=dev)
+        lo = torch.empty((n, c), dtype=torch.bfloat16, device=dev) if _precision["mode"] == 3 else None
+    check(lib.us3d_bn_apply_planes(x.data_ptr(), _ld(x), n, c, mean.data_ptr(), invstd.data_ptr(), g.data_ptr(), b.data_ptr(),
+                                   _ptr(residual), 0 if residual is None else _ld(residual), int(relu), y.data_ptr(), c,
+                                   _ptr(hi), _ptr(lo), _stream()))
+    if hi is not None:
+        y._us3d_planes = (hi, lo, y._version)
+    return y, g
+
+
+def bn_backward_raw(dy, x, y, mean, invstd, g, relu, training, has_res):
+    """BatchNorm (+ReLU mask, + residual branch) backward in one call: (dx with its bf16 planes cached, dresidual or None,
+    dgamma, dbeta).  `y` is the forward output (needed for the ReLU mask only; may be None without ReLU)."""
+    n, c = x.shape
+    dev = x.device
+    yy = y if y is not None else x
+    dx = torch.empty((n, c), dtype=torch.float32, device=dev)
+    dres = torch.empty((n, c), dtype=torch.float32, device=dev) if has_res else None
+    dgb = torch.empty((2, c), dtype=torch.float32, device=dev)
+    hi = lo = None
+    if _want_planes(c) and dy.data_ptr() % 16 == 0 and _ld(dy) % 4 == 0 and x.data_ptr() % 16 == 0 and _ld(x) % 4 == 0:
+        hi = torch.empty((n, c), dtype=torch.bfloat16, device=dev)
+        lo = torch.empty((n, c), dtype=torch.bfloat16, device=dev) if _precision["mode"] == 3 else None
+    check(lib.us3d_bn_backward_planes(dy.data_ptr(), _ld(dy), x.data_ptr(), _ld(x), yy.data_ptr(), _ld(yy), n, c, mean.data_ptr(),
+                                      invstd.data_ptr(), g.data_ptr(), int(relu), int(training),
+                                      _bn_workspace(dev, c).data_ptr(), dx.data_ptr(), c, _ptr(dres), c, dgb.data_ptr(),
+                                      dgb.data_ptr() + 4 * c, _ptr(hi), _ptr(lo), _stream()))
+    if hi is not None:
+        dx._us3d_planes = (hi, lo, dx._version)
+    return dx, dres, dgb[0], dgb[1]
+
+
 class BatchNormApplyFunction(torch.autograd.Function):
     """y = [relu]( (x - mean) * invstd * gamma + beta [+ residual] ) with (mean, invstd) given.  `batch_stats`
     says whether they are this batch's statistics (training: backward includes the two batch terms) or constants.
@@ -419,22 +470,7 @@ class BatchNormApplyFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, gamma, beta, residual, mean, invstd, batch_stats, relu):
         x = _rows(x)
-        n, c = x.shape
-        dev = x.device
-        if residual is not None:
-            residual = _rows(residual)
-        g = gamma.detach().contiguous() if gamma is not None else torch.ones(c, device=dev)
-        b = beta.detach().contiguous() if beta is not None else torch.zeros(c, device=dev)
-        y = torch.empty((n, c), dtype=torch.float32, device=dev)
-        hi = lo = None
-        if _want_planes(c) and n > 0:
-            hi = torch.empty((n, c), dtype=torch.bfloat16, device=dev)
-            lo = torch.empty((n, c), dtype=torch.bfloat16, device=dev) if _precision["mode"] == 3 else None
-        check(lib.us3d_bn_apply_planes(x.data_ptr(), _ld(x), n, c, mean.data_ptr(), invstd.data_ptr(), g.data_ptr(), b.data_ptr(),
-                                       _ptr(residual), 0 if residual is None else _ld(residual), int(relu), y.data_ptr(), c,
-                                       _ptr(hi), _ptr(lo), _stream()))
-        if hi is not None:
-            y._us3d_planes = (hi, lo, y._version)
+        y, g = bn_apply_raw(x, gamma, beta, residual, mean, invstd, relu)
         ctx.save_for_backward(x, y if relu else None, mean, invstd, g)
         ctx.relu, ctx.training, ctx.has_res = bool(relu), bool(batch_stats), residual is not None
         ctx.affine = gamma is not None
@@ -443,24 +479,9 @@ class BatchNormApplyFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         x, y, mean, invstd, g = ctx.saved_tensors
-        dy = _rows(dy)
-        n, c = x.shape
-        dev = x.device
-        yy = y if y is not None else x
-        dx = torch.empty((n, c), dtype=torch.float32, device=dev)
-        dres = torch.empty((n, c), dtype=torch.float32, device=dev) if ctx.has_res else None
-        dgb = torch.empty((2, c), dtype=torch.float32, device=dev)
-        hi = lo = None
-        if _want_planes(c) and dy.data_ptr() % 16 == 0 and _ld(dy) % 4 == 0 and x.data_ptr() % 16 == 0 and _ld(x) % 4 == 0:
-            hi = torch.empty((n, c), dtype=torch.bfloat16, device=dev)
-            lo = torch.empty((n, c), dtype=torch.bfloat16, device=dev) if _precision["mode"] == 3 else None
-        check(lib.us3d_bn_backward_planes(dy.data_ptr(), _ld(dy), x.data_ptr(), _ld(x), yy.data_ptr(), _ld(yy), n, c, mean.data_ptr(),
-                                          invstd.data_ptr(), g.data_ptr(), int(ctx.relu), int(ctx.training),
-                                          _bn_workspace(dev, c).data_ptr(), dx.data_ptr(), c, _ptr(dres), c, dgb.data_ptr(),
-                                          dgb.data_ptr() + 4 * c, _ptr(hi), _ptr(lo), _stream()))
-        if hi is not None:
-            dx._us3d_planes = (hi, lo, dx._version)
-        dgamma, dbeta = (dgb[0], dgb[1]) if ctx.affine else (None, None)
+        dx, dres, dgamma, dbeta = bn_backward_raw(_rows(dy), x, y, mean, invstd, g, ctx.relu, ctx.training, ctx.has_res)
+        if not ctx.affine:
+            dgamma = dbeta = None
         return dx, dgamma, dbeta, dres, None, None, None, None
 
 

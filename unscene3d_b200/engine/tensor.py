@@ -315,8 +315,8 @@ class _ConvBase(MinkowskiModuleBase):
             if self.bias is not None:
                 self.bias.uniform_(-stdv, stdv)
 
-    def forward(self, x: SparseTensor) -> SparseTensor:
-        cm, in_key = x.coordinate_manager, x.coordinate_map_key
+    def tables(self, cm, in_key):
+        """(output key, forward table, getter of (backward table, flip flag), flip flag the getter will return)."""
         ks, dil = self.kernel_size, self.dilation
         flip_dgrad = False
         if self.use_mm:
@@ -338,6 +338,11 @@ class _ConvBase(MinkowskiModuleBase):
             # backward reads the fine rows at coarse + off_k
             fwd = cm.backward_table(out_key, in_key, ks, dil)[0]
             bwd_getter = lambda: (cm.forward_table(out_key, in_key, ks, dil), False)
+        return out_key, fwd, bwd_getter, flip_dgrad
+
+    def forward(self, x: SparseTensor) -> SparseTensor:
+        cm = x.coordinate_manager
+        out_key, fwd, bwd_getter, flip_dgrad = self.tables(cm, x.coordinate_map_key)
         y = Fn.SparseConvFunction.apply(x.F, self.kernel, self.bias, fwd, bwd_getter, flip_dgrad)
         return SparseTensor(y, coordinate_map_key=out_key, coordinate_manager=cm)
 
@@ -398,7 +403,8 @@ class MinkowskiBatchNorm(nn.Module):
         super().__init__()
         self.bn = nn.BatchNorm1d(num_features, eps=eps, momentum=momentum, affine=affine, track_running_stats=track_running_stats)
 
-    def forward(self, x: SparseTensor, residual: SparseTensor = None, relu: bool = False) -> SparseTensor:
+    def statistics(self, f: torch.Tensor):
+        """(mean, invstd, batch statistics?) for the rows of `f`; updates the running statistics like nn.BatchNorm1d."""
         bn = self.bn
         use_batch = bn.training or not bn.track_running_stats
         momentum = bn.momentum
@@ -411,12 +417,17 @@ class MinkowskiBatchNorm(nn.Module):
                 nbt = bn.num_batches_tracked  # incremented by the statistics kernel itself
         rm = bn.running_mean if (bn.track_running_stats and (bn.training or not use_batch)) else None
         rv = bn.running_var if rm is not None else None
-        f = x.F
         if use_batch:
             mean, invstd = Fn.bn_batch_stats(f.detach(), rm, rv, momentum, bn.eps, nbt)
         else:
             mean = bn.running_mean.detach().float()
             invstd = torch.rsqrt(bn.running_var.detach().float() + bn.eps)
+        return mean, invstd, use_batch
+
+    def forward(self, x: SparseTensor, residual: SparseTensor = None, relu: bool = False) -> SparseTensor:
+        bn = self.bn
+        f = x.F
+        mean, invstd, use_batch = self.statistics(f)
         lazy = _DeferredBN(f, bn.weight, bn.bias, mean, invstd, use_batch, None if residual is None else residual.F, relu)
         return SparseTensor._deferred(lazy, x.coordinate_map_key, x.coordinate_manager)
 

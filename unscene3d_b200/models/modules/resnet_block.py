@@ -10,7 +10,17 @@ from MinkowskiEngine import MinkowskiReLU
 from .common import ConvType, NormType, conv, get_norm
 
 
+def _cuda_block_core(block, x):
+    from unscene3d_b200.engine.blocks import fused_basic_block
+
+    return fused_basic_block(block, x)
+
+
 class _ResidualBase(nn.Module):
+    # Optional whole-block execution (unscene3d_b200.engine.blocks.fused_basic_block); returns None to fall through to the
+    # reference's module-by-module sequence below.  The CPU tests that run these definitions over the oracle install a core
+    # that always returns None (tests/helpers.py).
+    block_core = None
     expansion = 1
     NORM_TYPE = NormType.BATCH_NORM
     # (attribute suffix, kernel size, uses the block's stride/dilation/conv_type, output multiplier)
@@ -34,6 +44,10 @@ class _ResidualBase(nn.Module):
         self.downsample = downsample
 
     def forward(self, x):
+        core = type(self).block_core or _cuda_block_core
+        fused = core(self, x)  # one autograd node for the whole block where the engine offers it (same kernels, same order)
+        if fused is not None:
+            return fused
         out = x
         last = self.STAGES[-1][0]
         for suffix, _, _, _ in self.STAGES:
