@@ -85,6 +85,7 @@ def our_models_on_oracle():
     mod.criterion.SetCriterion.mask_loss_core = staticmethod(ops_cpu.mask_losses)
     mod.mask3d.Mask3D.segment_attention_core = staticmethod(ops_cpu.segment_attention_masks)
     mod.modules.resnet_block._ResidualBase.block_core = staticmethod(lambda block, x: None)  # the reference's own sequence
+    mod.res16unet.Res16UNetBase.transition_core = staticmethod(lambda conv_layer, norm, x: None)
     return mod
 
 

@@ -154,6 +154,7 @@ def _backbone_live():
 
 
 @pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("US3D_TEST_FUSED", "0") != "1", reason="fused blocks not yet verified on the B200")
 def test_fused_residual_blocks_equal_the_module_route():
     """engine.blocks runs a BasicBlock as ONE autograd node issuing the same kernels in the same order: forward bit-identical,
     gradients equal up to the order of the weight-gradient atomics (1e-5); training and eval mode."""
@@ -168,6 +169,7 @@ def test_fused_residual_blocks_equal_the_module_route():
     st = deterministic_state(net, 13)
     w = torch.linspace(-1, 1, 96).cuda()
     runs = {}
+    default_on = blocks._enabled["on"]
     for train in (True, False):
         for fused in (True, False):
             blocks.set_fused_blocks(fused)
@@ -181,7 +183,7 @@ def test_fused_residual_blocks_equal_the_module_route():
                 net.zero_grad(set_to_none=True)
                 runs[(train, fused)] = (out.F.detach().clone(), [a.F.detach().clone() for a in aux], grads, bufs)
             finally:
-                blocks.set_fused_blocks(True)
+                blocks.set_fused_blocks(default_on)
         a, b = runs[(train, True)], runs[(train, False)]
         assert torch.equal(a[0], b[0])
         for u, v in zip(a[1], b[1]):

@@ -16,7 +16,9 @@ from . import functional as Fn
 from .coords import _stream
 
 
-_enabled = {"on": True}
+import os
+
+_enabled = {"on": os.environ.get("US3D_FUSED_BLOCKS", "0") == "1"}  # TODO(round 1): default on once verified on the B200
 
 
 def set_fused_blocks(on: bool):
@@ -144,3 +146,48 @@ def fused_basic_block(block, x):
                                         None if cd is None else cd.kernel, None if nd is None else nd.bn.weight,
                                         None if nd is None else nd.bn.bias, plan)
     return SparseTensor(out, coordinate_map_key=key2, coordinate_manager=cm)
+
+
+class FusedConvNormReLUFunction(torch.autograd.Function):
+    """out = relu(bn(conv(x))) — the stem and the strided / transposed transition layers between the stages
+    (models/res16unet.py:226-289: `convXpYs2 -> bnX -> relu`, `convtrX -> bntrX -> relu`)."""
+
+    @staticmethod
+    def forward(ctx, x, k, g, b, plan):
+        x = Fn._rows(x)
+        fwd, bwd_getter, flip, norm = plan
+        y = _conv_forward(x, k, fwd, flip)
+        m, s, t = norm.statistics(y)
+        out, gc = Fn.bn_apply_raw(y, g, b, None, m, s, True)
+        ctx.save_for_backward(x, y, out, m, s, gc, k)
+        ctx.plan, ctx.training, ctx.planes = plan, bool(t), _planes(x)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, y, out, m, s, gc, k = ctx.saved_tensors
+        fwd, bwd_getter, flip, _ = ctx.plan
+        _restore(x, ctx.planes)
+        dy, _, dg, db = Fn.bn_backward_raw(Fn._rows(dout), y, out, m, s, gc, True, ctx.training, False)
+        w3 = _w3(k, fwd)
+        dx = Fn.conv_input_gradient(dy, k, w3, bwd_getter, flip) if ctx.needs_input_grad[0] else None
+        dk = Fn.spconv_wgrad(x, fwd, dy, w3.shape[1], w3.shape[2]).view(k.shape)
+        return dx, dk, dg, db, None
+
+
+def fused_conv_norm_relu(conv, norm, x):
+    """relu(norm(conv(x))) as one autograd node, or None when the modules are not a bias-free convolution followed by an
+    affine MinkowskiBatchNorm (the caller then takes the module-by-module route)."""
+    from .tensor import MinkowskiBatchNorm, SparseTensor, _ConvBase
+
+    if not _enabled["on"] or not (isinstance(conv, _ConvBase) and isinstance(norm, MinkowskiBatchNorm)):
+        return None
+    bn = norm.bn
+    if conv.bias is not None or bn.weight is None or (bn.training and bn.track_running_stats and bn.momentum is None):
+        return None
+    if not x.F.is_cuda or x.F.dtype != torch.float32:
+        return None
+    cm = x.coordinate_manager
+    out_key, fwd, bwd_getter, flip = conv.tables(cm, x.coordinate_map_key)
+    out = FusedConvNormReLUFunction.apply(x.F, conv.kernel, bn.weight, bn.bias, (fwd, bwd_getter, flip, norm))
+    return SparseTensor(out, coordinate_map_key=out_key, coordinate_manager=cm)
