@@ -323,6 +323,13 @@ def run_ours(args):
         time.sleep(0.3)  # nvidia-smi fallback: let the subprocess start reporting
         for _ in range(2):
             step_resident()  # and bring the device back under load before the clock starts
+    # Everything alive after the warm-up (model, cached plans, allocator bookkeeping) is long-lived: park it in the permanent
+    # generation so that a cyclic-GC pass inside a timed step only walks that step's own objects (a full collection over the
+    # whole heap is a ~100 ms host stall; training loops do the same with gc.freeze() / scheduled collections).
+    import gc
+
+    gc.collect()
+    gc.freeze()
     _lib.reset_launch_count()
     ms_total, t0, t1 = timed(step_resident, args.steps, sampler if rank == 0 else None)
     launches = _lib.launch_count()

@@ -76,9 +76,13 @@ def train_step(net, crit, weight_dict, batch, world):
 
 
 def timed_steps(fn, steps, warm):
+    import gc
+
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
+    gc.collect()
+    gc.freeze()  # long-lived objects out of the cyclic collector's way (a full pass over the heap is a ~100 ms host stall)
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
     for _ in range(steps):
@@ -91,7 +95,7 @@ def timed_steps(fn, steps, warm):
 def run_c3(dev, rank, world, scenes_per_gpu=4, voxels=200_000, label="C3"):
     net, crit, wd = build_mask3d(dev)
     batch = scene_batch(scenes_per_gpu, voxels, 100 + rank * scenes_per_gpu, dev)
-    ms = timed_steps(lambda: train_step(net, crit, wd, batch, world), steps=5, warm=3)
+    ms = timed_steps(lambda: train_step(net, crit, wd, batch, world), steps=10, warm=4)
     ms = D.max_over_ranks(ms, dev)
     if rank == 0:
         n = scenes_per_gpu * world

@@ -18,7 +18,7 @@ from .coords import _stream
 
 import os
 
-_enabled = {"on": os.environ.get("US3D_FUSED_BLOCKS", "0") == "1"}  # TODO(round 1): default on once verified on the B200
+_enabled = {"on": os.environ.get("US3D_FUSED_BLOCKS", "1") == "1"}
 
 
 def set_fused_blocks(on: bool):
