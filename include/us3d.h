@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define US3D_ABI_VERSION 13
+#define US3D_ABI_VERSION 14
 #define US3D_MAX_KVOL 27
 
 int us3d_abi_version(void);
@@ -131,6 +131,10 @@ int us3d_spconv_wgrad_planes(const void *x_hi, const void *x_lo, const void *dy_
                              int n_rows, int kvol, float *dw, int cin, int cout, int passes, const uint32_t *tile_mask,
                              const int32_t *dy_rows, void *stream);
 /* dy_rows (may be NULL): table column j pairs with dY row dy_rows[j] — the table is in pattern order (below). */
+
+/* bf16 planes [n, c] (c % 8 == 0) re-ordered by rows: out[j] = in[order[j]] (lo / lo_out may both be NULL).  Brings dY into the
+ * row order of a pattern-ordered table so that us3d_spconv_wgrad_planes streams contiguous dY tiles (dy_rows = NULL). */
+int us3d_permute_planes(const void *hi, const void *lo, const int32_t *order, int n, int c, void *hi_out, void *lo_out, void *stream);
 
 /* Rows of a large map ordered by neighbour pattern.  The tcgen05 kernels skip a kernel offset for a 128-row tile only if
  * no row of the tile has a neighbour there; spatially consecutive rows of a voxelised surface leave every offset active,

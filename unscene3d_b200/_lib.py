@@ -31,6 +31,7 @@ PROTOTYPES = {
     "us3d_spconv_wgrad_tc_supported": [_i, _i],
     "us3d_spconv_wgrad_tc": [_p, _i, _p, _i, _i, _p, _i, _p, _p, _i, _i, _i, _p, _p],
     "us3d_spconv_wgrad_planes": [_p, _p, _p, _p, _p, _i, _i, _p, _i, _i, _i, _p, _p, _p],
+    "us3d_permute_planes": [_p, _p, _p, _i, _i, _p, _p, _p],
     "us3d_neighbour_pattern_keys": [_p, _i, _i, _p, _p, _p],
     "us3d_kernel_map_reorder": [_p, _i, _i, _p, _p, _p, _i, _p],
     "us3d_spconv_wgrad": [_p, _i, _p, _i, _i, _p, _i, _p, _p, _i, _i, _p],

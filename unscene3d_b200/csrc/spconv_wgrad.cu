@@ -255,6 +255,21 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad(Params p) {
     if (warp == MMA_WARP) tmem_dealloc(tmem_base, (uint32_t)p.acc_cols);
 }
 
+
+// out[j, :] = in[order[j], :] for both bf16 planes (rows of c channels, c % 8 == 0): dY brought into the row order of a
+// pattern-ordered table, so that the weight-gradient kernel streams its dY tiles instead of gathering scattered rows.
+__global__ void __launch_bounds__(256)
+k_permute_planes(const uint4 *__restrict__ hi, const uint4 *__restrict__ lo, const int32_t *__restrict__ order, int n, int chunks,
+                 uint4 *__restrict__ hi_out, uint4 *__restrict__ lo_out) {
+    const long long total = (long long)n * chunks;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(e / chunks), g = (int)(e - (long long)j * chunks);
+        const size_t src = (size_t)__ldg(order + j) * chunks + g;
+        hi_out[e] = hi[src];
+        if (lo != nullptr) lo_out[e] = lo[src];
+    }
+}
+
 }  // namespace wg
 }  // namespace us3d
 
@@ -315,6 +330,19 @@ int us3d_spconv_wgrad_planes(const void *x_hi, const void *x_lo, const void *dy_
         else
             wg::k_wgrad<1><<<grid, wg::THREADS, smem, st>>>(p);
     }
+    US3D_LAUNCH_CHECK();
+    return 0;
+}
+
+int us3d_permute_planes(const void *hi, const void *lo, const int32_t *order, int n, int c, void *hi_out, void *lo_out, void *stream_) {
+    US3D_CHECK_ARG(n >= 0 && c > 0 && c % 8 == 0, "permute_planes: channels must be a multiple of 8");
+    US3D_CHECK_ARG(hi && hi_out && order && ((lo == nullptr) == (lo_out == nullptr)), "permute_planes: missing plane");
+    if (n == 0) return 0;
+    const int chunks = c / 8;
+    long long blocks = ((long long)n * chunks + 255) / 256;
+    if (blocks > (long long)num_sms() * 16) blocks = (long long)num_sms() * 16;
+    wg::k_permute_planes<<<(int)blocks, 256, 0, (cudaStream_t)stream_>>>((const uint4 *)hi, (const uint4 *)lo, order, n, chunks,
+                                                                        (uint4 *)hi_out, (uint4 *)lo_out);
     US3D_LAUNCH_CHECK();
     return 0;
 }

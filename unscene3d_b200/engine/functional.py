@@ -6,6 +6,8 @@ with its row stride as leading dimension (so column slices of a concatenation ne
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from .._lib import check, lib
@@ -310,7 +312,16 @@ def spconv_wgrad(x, table: NeighbourTable, dy, cin, cout):
             # pattern order pays for the weight gradient only on k2s2 maps (one parent per fine row: 1/8 of the tile x offset
             # products remain); on k3 maps the scattered dY rows cost more than the skipped products save (measured on B200:
             # 200k voxels 96 -> 96, 0.55 -> 0.62 ms ordered, k2s2 0.171 -> 0.125 ms)
-            nbr, mask, order = (table.ordered() if table.kvol <= 8 else None) or (table.nbr, table.mask, None)
+            wgrad_order = _wgrad_order["mode"]
+            nbr, mask, order = (table.ordered() if (table.kvol <= 8 or wgrad_order == "permute") else None) or (table.nbr, table.mask, None)
+            if order is not None and table.kvol > 8:
+                # k3 maps: bring the dY planes into table order with one streaming pass (out[j] = dY[order[j]]) instead of letting
+                # the kernel gather scattered dY rows
+                n, c = dy.shape
+                ph = torch.empty_like(dh)
+                pl = torch.empty_like(dl) if dl is not None else None
+                check(lib.us3d_permute_planes(dh.data_ptr(), _ptr(dl), order.data_ptr(), n, c, ph.data_ptr(), _ptr(pl), st))
+                dh, dl, order = ph, pl, None
             _timed("wgrad", x.shape[0], table.n_rows, table.kvol, cin, cout, lambda: check(
                 lib.us3d_spconv_wgrad_planes(xh.data_ptr(), _ptr(xl), dh.data_ptr(), _ptr(dl), nbr.data_ptr(), table.n_rows,
                                              table.kvol, dw.data_ptr(), cin, cout, mode, _ptr(mask), _ptr(order), st)), table, "wgrad-tc")
@@ -323,6 +334,11 @@ def spconv_wgrad(x, table: NeighbourTable, dy, cin, cout):
         lib.us3d_spconv_wgrad(x.data_ptr(), _ld(x), table.nbr.data_ptr(), table.n_rows, table.kvol, dy.data_ptr(), _ld(dy), 0,
                               dw.data_ptr(), cin, cout, st)), table, "simt")
     return dw
+
+
+# weight gradient on pattern-ordered k3 tables: "natural" = keep the natural table (no pruning), "permute" = ordered table with
+# the dY planes permuted into table order first
+_wgrad_order = {"mode": os.environ.get("US3D_WGRAD_ORDER", "natural")}
 
 
 def _wgrad_tc_ok(cin, cout):  # == us3d_spconv_wgrad_tc_supported, without the FFI round trip
