@@ -334,8 +334,10 @@ def run_ours(args):
     ms_total, t0, t1 = timed(step_resident, args.steps, sampler if rank == 0 else None)
     launches = _lib.launch_count()
     clocks = sampler.stop(t0, t1) if rank == 0 else None
-    for _ in range(6):  # the end-to-end leg has its own allocator pool (copies on the coordinate stream): warm it
+    for _ in range(10):  # the end-to-end leg has its own allocator pool (copies on the coordinate stream): warm it
         step_e2e()
+    gc.collect()
+    gc.freeze()
     ms_e2e, _, _ = timed(step_e2e, args.steps)
 
     if os.environ.get("US3D_BENCH_DEBUG"):
