@@ -267,3 +267,38 @@ def test_cuda_pseudo_masks_match_reference_golden():
     followed = pm.unscene3d(agg, uniq, case["seg_connectivity"].cuda(), affinity_tau=0.65, sign_rule=follow(g["eigvecs"]))
     assert np.array_equal(followed[0], g["masks"][0])
     assert own.dtype == bool and own.shape[1] == len(uniq) and own.sum(0).max() <= 1
+
+
+@pytest.mark.gpu
+def test_cuda_scene_features_3d_equal_kdtree_nearest_voxel():
+    """A17 (pseudo_masks/unscene3d_pseudo_main.py:332-348): every full-resolution voxel takes the features of its nearest
+    res_2 voxel.  The reference asks a scipy KDTree; ours is the parent map.  Same voxel wherever the nearest one is unique,
+    an equally near one otherwise (the KDTree's pick among ties is implementation-defined)."""
+    from scipy.spatial import KDTree
+
+    import unscene3d_b200  # noqa: F401
+    from helpers import Cfg, deterministic_state, random_scene
+    from unscene3d_b200 import engine, models
+    from unscene3d_b200 import pseudo_masks as pm
+
+    c = random_scene(4000, 90, batch=1, extent=30)
+    torch.manual_seed(1)
+    f = torch.randn(c.shape[0], 3)
+    net = models.Res16UNet34CMultiRes(3, 20, Cfg(), D=3, out_fpn=True)
+    net.load_state_dict(deterministic_state(net, 3))
+    net = net.cuda().eval()
+    with torch.no_grad():
+        x = engine.SparseTensor(f.cuda(), torch.from_numpy(c).cuda())
+        out = net(x)                                                    # one forward pass serves both sides
+        got = pm.encode_scene_feats_3d(lambda _: out, x, resolution_scale=2)
+    enc = out[1]["res_2"]
+    lr = enc.C[:, 1:].cpu().numpy()
+    dist, idx = KDTree(lr).query(c[:, 1:], k=2)
+    ref = enc.F[torch.from_numpy(idx[:, 0]).cuda()]
+    unique = dist[:, 0] < dist[:, 1] - 1e-9
+    assert unique.mean() > 0.1  # dense random scene: most voxels have an equally near neighbour of their parent
+    assert got.shape == ref.shape
+    assert torch.equal(got[torch.from_numpy(unique).cuda()], ref[torch.from_numpy(unique).cuda()])
+    # ties: the voxel we picked is exactly as near as the tree's
+    parent_xyz = (c[:, 1:] // 2) * 2
+    assert np.allclose(np.linalg.norm(c[:, 1:] - parent_xyz, axis=1), dist[:, 0])

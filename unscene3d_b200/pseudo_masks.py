@@ -400,3 +400,34 @@ def freemask(keys_F: torch.Tensor, matching_segment_ids: torch.Tensor, seg_conne
     out = torch.zeros((sep.shape[0], ids.shape[0]), dtype=torch.float32, device=dev)
     out[:, member] = sep[:, point_pos[member]]
     return out.cpu(), maskness.cpu()
+
+
+# ------------------------------------------------------------------------------------------- scene features, 3D branch (A17)
+def encode_scene_feats_3d(model, sinput, resolution_scale: int = 2) -> torch.Tensor:
+    """3D branch of encode_scene_feats (pseudo_masks/unscene3d_pseudo_main.py:332-348): forward through the pretrained
+    multi-resolution backbone (models/res16unet.py:428-505), take `res_<resolution_scale>` and hand every full-resolution voxel
+    the features of its nearest low-resolution voxel.
+
+    The reference finds that voxel with a scipy KDTree over the low-resolution coordinates on the host.  The low-resolution
+    map is floor(c / s) * s of the full-resolution one, and the parent p of a voxel c = p + d, d in [0, s)^3, is always a
+    nearest low-resolution voxel (any other one, p + s e, differs from c by |d_i - s e_i| >= |d_i| on every axis), so the
+    lookup is the coordinate manager's parent map composed over the strides — a gather, no tree, no host round trip.  Where
+    several low-resolution voxels are equally near (d_i = s / 2 on an axis with a populated neighbour) the KDTree's choice is
+    implementation-defined; this function returns the parent.  (`whiten=True` is not on the configured path:
+    pseudo_masks/config/default.yaml:76.)"""
+    scale = int(resolution_scale)
+    if scale < 1 or scale & (scale - 1):
+        raise ValueError("resolution_scale must be a power of two")
+    _, feature_maps = model(sinput)
+    enc = feature_maps[f"res_{scale}"]
+    cm = sinput.coordinate_manager
+    key = sinput.coordinate_map_key
+    parent = None
+    while key.tensor_stride[0] < enc.coordinate_map_key.tensor_stride[0]:
+        nxt = cm.stride(key, (2, 2, 2))
+        step = cm._parents[(key, nxt)].long()
+        parent = step if parent is None else step[parent]
+        key = nxt
+    assert key == enc.coordinate_map_key, "the backbone's feature map does not lie on the input's coordinate pyramid"
+    feats = enc.F.detach()
+    return feats if parent is None else feats[parent]
