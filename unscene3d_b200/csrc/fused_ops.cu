@@ -45,7 +45,11 @@ __device__ __forceinline__ void store_planes(const float (&f)[8], uint4 *hi, uin
     }
 }
 
-constexpr int kRows = 256;  // rows per reduction block
+constexpr int kRows = 256;  // rows per reduction block on large maps
+// Small maps (the coarse levels: 513 .. 12k rows) are latency-bound: with 256 rows per block each thread walks 32 dependent-
+// issue rows and the whole launch sits at ~10 us however little data there is (ncu launch list: no k_bn_bwd_reduce launch under
+// 8 us).  Fewer rows per block = more, shorter blocks; large maps keep 256 to bound the number of double atomics per column.
+static inline int reduce_rows(int n) { return n >= 65536 ? kRows : (n >= 16384 ? 128 : (n >= 4096 ? 64 : 32)); }
 
 // ws layout: [0, c) sum, [c, 2c) sum of squares (doubles), then one unsigned ticket counter
 struct StatsArgs {
@@ -55,13 +59,14 @@ struct StatsArgs {
     float *mean, *invstd, *running_mean, *running_var;
     long long *num_batches_tracked;
     double *ws;
+    int rows;  // rows per block
 };
 
 __global__ void __launch_bounds__(256) k_bn_stats_fused(StatsArgs a) {
     __shared__ double s0[8][33], s1[8][33];
     __shared__ bool last;
     const int ch = blockIdx.y * 32 + threadIdx.x;
-    const int r_begin = blockIdx.x * kRows, r_end = min(a.n, r_begin + kRows);
+    const int r_begin = blockIdx.x * a.rows, r_end = min(a.n, r_begin + a.rows);
     float a0 = 0.f, a1 = 0.f;
     if (ch < a.c)
         for (int r = r_begin + threadIdx.y; r < r_end; r += 8) {
@@ -147,10 +152,10 @@ k_bn_apply_planes(const float *__restrict__ x, int ldx, int n, int c, const floa
 // column sums of g and g * xhat (g = dy masked by the ReLU), block = 32 channels x 8 row lanes
 __global__ void __launch_bounds__(256)
 k_bn_bwd_reduce(const float *__restrict__ dy, int lddy, const float *__restrict__ x, int ldx, const float *__restrict__ y, int ldy, int n,
-                int c, const float *__restrict__ mean, const float *__restrict__ invstd, int relu, double *red) {
+                int c, const float *__restrict__ mean, const float *__restrict__ invstd, int relu, double *red, int rows) {
     __shared__ double s0[8][33], s1[8][33];
     const int ch = blockIdx.y * 32 + threadIdx.x;
-    const int r_begin = blockIdx.x * kRows, r_end = min(n, r_begin + kRows);
+    const int r_begin = blockIdx.x * rows, r_end = min(n, r_begin + rows);
     float a0 = 0.f, a1 = 0.f;
     if (ch < c) {
         const float m = mean[ch], is = invstd[ch];
@@ -459,8 +464,9 @@ int us3d_bn_stats_fused(const float *x, int ldx, int n, int c, float eps, float 
                         float *running_mean, float *running_var, long long *num_batches_tracked, double *ws, void *stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     US3D_CHECK_ARG(n > 0 && c > 0 && ldx >= c, "bn_stats_fused: bad shape");
-    fused::StatsArgs a{x, ldx, n, c, eps, momentum, mean, invstd, running_mean, running_var, num_batches_tracked, ws};
-    dim3 grid(ceil_div(n, fused::kRows), ceil_div(c, 32)), block(32, 8);
+    const int rows = fused::reduce_rows(n);
+    fused::StatsArgs a{x, ldx, n, c, eps, momentum, mean, invstd, running_mean, running_var, num_batches_tracked, ws, rows};
+    dim3 grid(ceil_div(n, rows), ceil_div(c, 32)), block(32, 8);
     fused::k_bn_stats_fused<<<grid, block, 0, st>>>(a);
     US3D_LAUNCH_CHECK();
     return 0;
@@ -488,8 +494,9 @@ int us3d_bn_backward_planes(const float *dy, int lddy, const float *x, int ldx, 
                             void *stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     US3D_CHECK_ARG(n > 0 && c > 0 && c <= 4096, "bn_backward_planes: bad shape");
-    dim3 grid(ceil_div(n, fused::kRows), ceil_div(c, 32)), block(32, 8);
-    fused::k_bn_bwd_reduce<<<grid, block, 0, st>>>(dy, lddy, x, ldx, y, ldy, n, c, mean, invstd, relu, ws);
+    const int rows = fused::reduce_rows(n);
+    dim3 grid(ceil_div(n, rows), ceil_div(c, 32)), block(32, 8);
+    fused::k_bn_bwd_reduce<<<grid, block, 0, st>>>(dy, lddy, x, ldx, y, ldy, n, c, mean, invstd, relu, ws, rows);
     US3D_LAUNCH_CHECK();
     const bool vec = c % 8 == 0 && lddy % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && lddx % 4 == 0 && fused::al16(dy) && fused::al16(x) &&
                      fused::al16(y) && fused::al16(dx) && (!dres || (lddres % 4 == 0 && fused::al16(dres)));
