@@ -313,8 +313,9 @@ def run_ours(args):
         sampler.start()
     # The caching allocator needs a handful of steps to stop growing its pools (two streams allocate: compute and
     # coordinate); a cudaMalloc inside the timed region synchronises the device.  Measured: 3 warm-up steps leave the first
-    # timed leg at 22.8 ms/step, the same leg after ~15 steps runs at 19.6; hence at least 20.
-    n_warm = max(args.warmup, int(os.environ.get("US3D_BENCH_MIN_WARMUP", "20")))  # (lowered only for ncu launch lists)
+    # timed leg at 22.8 ms/step, the same leg after ~15 steps runs at 19.6; one second of steps (50) also rides out the
+    # clock / power ramp of a fresh box (one 2-GPU run with 20 warm-up steps measured 20.7 ms, three repeats 19.04).
+    n_warm = max(args.warmup, int(os.environ.get("US3D_BENCH_MIN_WARMUP", "50")))  # (lowered only for ncu launch lists)
     for _ in range(n_warm):
         step_resident()
         if rank == 0:
