@@ -195,7 +195,7 @@ def pack_network(net: torch.nn.Module):
     convs = [m for m in convs if m.kernel.is_cuda and m.kernel.is_contiguous() and m.kernel.dtype == torch.float32 and m.kernel.shape[-2] > 4]
     if not convs:
         return
-    sig = (mode, tuple(m.kernel.data_ptr() for m in convs))
+    sig = (mode, tuple((m.kernel.data_ptr(), tuple(m.kernel.shape), m.kernel_volume) for m in convs))
     plan = _pack_plans.get(id(net))
     if plan is None or plan["sig"] != sig:
         dev = convs[0].kernel.device
