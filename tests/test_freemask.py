@@ -88,6 +88,25 @@ def test_cuda_freemask_matches_oracle(kw):
         _same_masks(got, ref)
 
 
+@pytest.mark.gpu
+def test_cuda_freemask_skips_the_scene_like_the_reference():
+    """Where the reference `continue`s (no candidate survives a filter) both implementations return None."""
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    from make_freemask_golden import make_case
+
+    import unscene3d_b200  # noqa: F401
+    from unscene3d_b200 import pseudo_masks as pm
+
+    case = {k: (v.numpy() if torch.is_tensor(v) else v) for k, v in make_case(side=6, n_objects=3, n_prototypes=3, seed=9).items()}
+    strict = dict(nms_maskness_threshold=1.5)  # maskness is <= 1: nothing passes the final filter (freemask_main.py:412-415)
+    cfg = type(freemask_cpu.DEFAULTS)(**{**vars(freemask_cpu.DEFAULTS), **strict})
+    ref = freemask_cpu.freemask(torch.from_numpy(case["keys_F"]), torch.from_numpy(case["matching_segment_ids"]),
+                                torch.from_numpy(case["seg_connectivity"]), case["lr_coords"], torch.from_numpy(case["coords"]), cfg=cfg)
+    got = pm.freemask(torch.from_numpy(case["keys_F"]).cuda(), torch.from_numpy(case["matching_segment_ids"]).cuda(),
+                      torch.from_numpy(case["seg_connectivity"]).cuda(), case["lr_coords"], torch.from_numpy(case["coords"]).cuda(), **strict)
+    assert ref is None and got is None
+
+
 def test_host_separation_matches_oracle_on_random_graphs():
     """The host set logic of libus3d (a host function of the C ABI: runs without a device) against the oracle's literal
     restatement, including multi-blob merges."""

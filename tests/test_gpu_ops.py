@@ -494,7 +494,7 @@ def test_relu_add_cat_pool(eng, ora):
 # --------------------------------------------------------------------------------------------- decoder helpers
 # n chosen to cover every residency tier of the cluster kernel: one CTA (<= 8192 rows), 2..16 CTAs with all rows in
 # registers (<= 131072), rows in shared memory (<= 327680), rows streamed from L2 beyond that
-@pytest.mark.parametrize("n,m,span", [(1, 1, 8), (5, 3, 8), (31, 10, 8), (100, 100, 8), (777, 100, 8), (5000, 100, 8), (20000, 60, 20),
+@pytest.mark.parametrize("n,m,span", [(1, 1, 8), (3, 7, 8), (5, 3, 8), (31, 10, 8), (100, 100, 8), (777, 100, 8), (5000, 100, 8), (20000, 60, 20),
                                       (131072, 40, 40), (200000, 100, 150), (340000, 30, 60)])
 def test_fps_indices_bit_exact_on_integer_coords(eng, n, m, span):
     from oracle import ops_cpu
