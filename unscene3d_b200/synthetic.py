@@ -94,14 +94,26 @@ def make_scene(n_voxels: int, seed: int = 0, with_masks: bool = True, num_masks:
     rng = np.random.default_rng(seed)
     geo_seed = int(rng.integers(1 << 31))
     scale = (n_voxels / 200_000.0) ** 0.5
-    for _ in range(6):
+    # The room is rescaled until the voxel count lands in [n, 1.03 n]; the count is not a smooth function of the scale (box
+    # sizes saturate), so the search keeps the smallest attempt that reached n and falls back to it (every seed must yield a
+    # scene: ranks of a multi-GPU run use seed = rank).
+    best = chosen = None
+    for attempt in range(24):
         g = np.random.default_rng(geo_seed)
         xyz, seg, adj = _sample(g, _surfaces(g, scale))
         coords, xyzv, segv = _voxelise(xyz, seg)
-        if n_voxels <= coords.shape[0] <= int(n_voxels * 1.03) + 64:
+        cnt = coords.shape[0]
+        if cnt >= n_voxels and (best is None or cnt < best[0].shape[0]):
+            best = (coords, xyzv, segv, adj)
+        if n_voxels <= cnt <= int(n_voxels * 1.03) + 64 or (attempt == 5 and cnt >= n_voxels):
+            chosen = (coords, xyzv, segv, adj)
             break
-        scale *= (n_voxels * 1.015 / coords.shape[0]) ** 0.5
-    assert coords.shape[0] >= n_voxels, "scene generator did not reach the requested voxel count"
+        if attempt >= 5 and best is not None:
+            chosen = best
+            break
+        scale *= (n_voxels * (1.015 if attempt < 6 else 1.06) / cnt) ** 0.5
+    assert chosen is not None, "scene generator did not reach the requested voxel count"
+    coords, xyzv, segv, adj = chosen
     keep = np.sort(rng.permutation(coords.shape[0])[:n_voxels])
     coords, xyzv, segv = coords[keep], xyzv[keep], segv[keep]
     # compact segment ids, remap adjacency
