@@ -315,6 +315,12 @@ def run_ours(args):
     # coordinate); a cudaMalloc inside the timed region synchronises the device.  Measured: 3 warm-up steps leave the first
     # timed leg at 22.8 ms/step, the same leg after ~15 steps runs at 19.6; one second of steps (50) also rides out the
     # clock / power ramp of a fresh box (one 2-GPU run with 20 warm-up steps measured 20.7 ms, three repeats 19.04).
+    if world > 1:
+        # first collectives of the communicator (buffer allocation, proxy threads) well before the timed legs: at 8 ranks the
+        # first timed leg measured 21.3 ms/step against 19.3 for the identical second leg
+        for _ in range(3):
+            barrier()
+            dist.all_reduce(torch.zeros(1, device=dev))
     n_warm = max(args.warmup, int(os.environ.get("US3D_BENCH_MIN_WARMUP", "50")))  # (lowered only for ncu launch lists)
     for _ in range(n_warm):
         step_resident()
@@ -331,6 +337,9 @@ def run_ours(args):
 
     gc.collect()
     gc.freeze()
+    barrier()
+    for _ in range(5):  # ranks leave the barrier at slightly different times: a few more steps before the clock starts
+        step_resident()
     _lib.reset_launch_count()
     ms_total, t0, t1 = timed(step_resident, args.steps, sampler if rank == 0 else None)
     launches = _lib.launch_count()
