@@ -152,3 +152,60 @@ def test_gradcheck_sparse_conv_chain():
     f = torch.randn(c.shape[0], 2, dtype=torch.float64, requires_grad=True)
     args = (f, c3.kernel.detach().requires_grad_(), dn.kernel.detach().requires_grad_(), up.kernel.detach().requires_grad_())
     assert torch.autograd.gradcheck(fn, args, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------
+# SURVEY §8(c) KATs (vi) and (vii): the two host-side solvers the path leans on
+def test_hungarian_assignment_is_the_brute_force_optimum():
+    """(vi) Cost matrices of the matcher's shape ([Q queries, T <= 6 targets], oracle cost function): the assignment
+    scipy.optimize.linear_sum_assignment returns — the solver models/matcher.py:161-163 and our matcher both call — has the
+    cost of the best of all Q!/(Q-T)! injections."""
+    import itertools
+
+    from scipy.optimize import linear_sum_assignment
+
+    from oracle import ops_cpu
+
+    g = torch.Generator().manual_seed(0)
+    for T in range(1, 7):
+        Q, S = 7, 40
+        logits = torch.randn(Q, 3, generator=g)
+        masks = torch.randn(S, Q, generator=g) * 2
+        tgt = torch.rand(T, S, generator=g) < 0.3
+        labels = torch.randint(0, 2, (T,), generator=g)
+        cost = np.asarray(ops_cpu.matcher_cost(logits, masks, tgt, labels, 2.0, 5.0, 2.0), dtype=np.float64)
+        assert cost.shape == (Q, T)
+        i, j = linear_sum_assignment(cost)
+        best = min(sum(cost[q, t] for t, q in enumerate(perm)) for perm in itertools.permutations(range(Q), T))
+        assert abs(cost[i, j].sum() - best) < 1e-9
+        assert sorted(j.tolist()) == list(range(T)) and len(set(i.tolist())) == T
+
+
+def test_fiedler_vector_is_the_second_eigenvector_of_the_normalised_laplacian():
+    """(vii) oracle.ncut_cpu.fiedler (the reference's scipy eigh(D - A, D, subset_by_index=[1, 2]),
+    pseudo_masks/unscene3d_pseudo_main.py:138-146) against numpy.linalg.eigh of D^-1/2 (D - A) D^-1/2: v = D^-1/2 u_2 up to
+    sign and scale, on a thresholded {1, eps} affinity of two loosely coupled blobs."""
+    from oracle import ncut_cpu
+
+    rng = np.random.default_rng(1)
+    n = 60
+    A = np.full((n, n), 1e-5)
+    A[:35, :35] = 1.0
+    A[35:, 35:] = 1.0
+    flip = rng.random((n, n)) < 0.03
+    flip = np.triu(flip, 1)
+    flip = flip | flip.T
+    A[flip] = np.where(A[flip] == 1.0, 1e-5, 1.0)
+    np.fill_diagonal(A, 1.0)
+    D = np.diag(A.sum(1))
+    v = np.asarray(ncut_cpu.fiedler(A, D)).reshape(-1)
+    d = np.diag(D)
+    L = (D - A) / np.sqrt(np.outer(d, d))
+    w, U = np.linalg.eigh(L)
+    assert w[0] < 1e-10 < w[1] < w[2] - 1e-6          # simple second eigenvalue
+    ref = U[:, 1] / np.sqrt(d)
+    cos = abs(v @ ref) / (np.linalg.norm(v) * np.linalg.norm(ref))
+    assert cos > 1 - 1e-10
+    # and it separates the two blobs
+    side = v > v.mean()
+    assert side[:35].all() != side[35:].all() and (side[:35].all() or (~side[:35]).all())
