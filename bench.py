@@ -6,9 +6,11 @@ ScanNet-shaped scenes (BASELINE.json metric, configs[1]) on 1..8 B200s.
 
 One "step" = one scene (batch 1) through the whole hot path: coordinate-manager construction from the
 [N,4] coordinate matrix (hash insert, 4 stride maps, 9 kernel maps), backbone forward, scalar loss,
-backward through every layer.  Scenes are independent, so N GPUs run N scenes per step with no
-data-path collective (weak scaling); the timed region is bracketed by barrier + synchronize, timed
-with CUDA events, and the maximum over ranks is reported by rank 0 as ONE JSON line.
+backward through every layer.  Scenes are independent, so N GPUs run N scenes per step (weak scaling);
+at N > 1 the step is the data-parallel training step of BASELINE configs[4]: the ~151 MB of fp32 gradients
+are averaged over the ranks by bucketed NCCL all-reduces launched from gradient hooks while backward is
+still running (unscene3d_b200/distributed.py).  The timed region is bracketed by barrier + synchronize,
+timed with CUDA events, and the maximum over ranks is reported by rank 0 as ONE JSON line.
 
 Legs:
   value      inputs resident in HBM, device-timed, all ranks
@@ -17,7 +19,8 @@ Legs:
              against its algorithmic bytes and MEASURED_PEAKS.json
   cpu_baseline  the CPU oracle (oracle/me_cpu.py, "port": same gather-GEMM-scatter algorithm as
              MinkowskiEngine's CPU path, which is not installable here) on the host cores, rank 0, N=1
-  --impl reference   the same CPU oracle as the reference arm (MinkowskiEngine is absent)
+  --impl reference   the same CPU oracle as the reference arm, on the SAME 200k-voxel scene and seed (see DESIGN.md:
+             MinkowskiEngine is absent, so the reference's CPU path is its restatement, kind "port")
 """
 import argparse
 import json
@@ -37,7 +40,24 @@ os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
 METRIC = "voxels/sec fwd+bwd Res16UNet34C @200k-voxel scenes"
 UNIT = "voxels/s"
 N_VOXELS = 200_000
-CPU_SAMPLE_VOXELS = 50_000
+# dram__bytes_read.sum + dram__bytes_write.sum of the largest launch of each kernel, from the ncu --set full capture summarised
+# in profiles/ (see there for the command), next to the algorithmic bytes of that launch
+NCU_TRAFFIC = {"mt": {"launch": "200k voxels, k3, 128 -> 96 (pattern order)", "dram_bytes": 433717248, "alg_bytes": 180500000,
+                      "source": "profiles/r1_ncu_full_summary.md"},
+               "wgrad": {"launch": "200k voxels, k3, 128 -> 96", "dram_bytes": 235100000, "alg_bytes": 180500000,
+                         "source": "profiles/r1_ncu_full_summary.md"}}
+DTYPE = "bf16x3"  # tcgen05 bf16 products, three-term split hi*hi + lo*hi + hi*lo (fp32-faithful), fp32 accumulation in TMEM
+PRIME_STEPS = 30  # untimed steps BEFORE the --warmup steps: allocator pools of the two streams, NVML, clock / power ramp
+
+
+def bench_config(voxels, world):
+    """`config` of the JSON line — identical for both arms (the reference arm runs the same workload on the host cores)."""
+    return {"workload": f"Res16UNet34C fwd+bwd, synthetic ScanNet-shaped {voxels}-voxel scene (seed = rank), batch=1 per GPU (BASELINE configs[1])",
+            "parallelism": "dp1 (one scene per GPU)" if world == 1 else
+                           f"dp{world}: one scene per GPU, gradients averaged by bucketed NCCL all-reduce overlapped with backward (BASELINE configs[4])",
+            "l2": "256 MiB buffer written between timed GPU iterations (L2 flush)",
+            "step": "coordinate-manager build (on a high-priority side stream) + forward + loss + backward"
+                    + ("" if world == 1 else " + gradient all-reduce")}
 
 
 def env_int(name, default):
@@ -147,7 +167,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------- CPU arm
-def cpu_oracle_run(steps, warmup, n_voxels, seed=0):
+def cpu_oracle_run(steps, warmup, n_voxels, seed=0, small_warmup=True):
     """Times the CPU oracle (Res16UNet34C fwd+bwd incl. coordinate-manager construction) on all host threads."""
     import torch
 
@@ -169,12 +189,16 @@ def cpu_oracle_run(steps, warmup, n_voxels, seed=0):
         (out.F * w).mean().backward()
         net.zero_grad(set_to_none=True)
 
-    small = make_scene(5000, seed=seed + 1, with_masks=False)
-    c4s = torch.from_numpy(np.concatenate([np.zeros((small.n, 1), np.int32), small.coords], 1))
-    for _ in range(max(warmup, 1)):
-        out, _ = net(me_cpu.SparseTensor(torch.from_numpy(small.colors), c4s))
-        (out.F * w).mean().backward()
-        net.zero_grad(set_to_none=True)
+    if small_warmup:  # cpu_baseline leg of the GPU arm: bounded — warm the thread pool / allocator on a 5k-voxel scene
+        small = make_scene(5000, seed=seed + 1, with_masks=False)
+        c4s = torch.from_numpy(np.concatenate([np.zeros((small.n, 1), np.int32), small.coords], 1))
+        for _ in range(max(warmup, 1)):
+            out, _ = net(me_cpu.SparseTensor(torch.from_numpy(small.colors), c4s))
+            (out.F * w).mean().backward()
+            net.zero_grad(set_to_none=True)
+    else:
+        for _ in range(warmup):
+            step()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
@@ -198,15 +222,17 @@ def run_reference(args):
     if rank != 0:
         return 0
     _load_synthetic_standalone()
-    v, ms, threads = cpu_oracle_run(args.steps, min(args.warmup, 2), CPU_SAMPLE_VOXELS)
+    # same workload as the GPU arm: the full scene, same generator and seed; one step is ~4 s on 16 host threads
+    v, ms, threads = cpu_oracle_run(args.steps, args.warmup, args.voxels, seed=0, small_warmup=False)
+    world = env_int("WORLD_SIZE", 1)
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "Res16UNet34C fwd+bwd, synthetic ScanNet-shaped scene, batch=1 (BASELINE configs[1])",
-                   "sample": f"{CPU_SAMPLE_VOXELS}-voxel scene per step (same generator; voxels/s is size-normalised)"},
+        "config": bench_config(args.voxels, 1 if world == 1 else world),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{args.steps} steps of a {CPU_SAMPLE_VOXELS}-voxel scene, CPU oracle (gather-GEMM-scatter restatement; MinkowskiEngine not installable offline)"},
+                         "sample": f"{args.steps} steps of the full {args.voxels}-voxel scene (seed 0) after {args.warmup} warm-up steps; CPU oracle = "
+                                   "gather-GEMM-scatter restatement of the MinkowskiEngine CPU path (ME is not installable offline)"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -230,6 +256,7 @@ def run_ours(args):
 
     import unscene3d_b200
     from unscene3d_b200 import _lib, engine, models
+    from unscene3d_b200 import distributed as D
     from unscene3d_b200.engine import functional as Fn
     from unscene3d_b200.synthetic import level_sizes, make_scene
     from unscene3d_b200.utils import BackboneConfig, conv_layer_bytes, seeded_state
@@ -246,6 +273,11 @@ def run_ours(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     loss_host = torch.zeros(1).pin_memory()
 
+    # Data-parallel half of the step (N > 1): ~151 MB of fp32 gradients in 32 MB buckets, each all-reduced (NCCL, AVG) as soon
+    # as backward has produced its last gradient; finish() makes the compute stream wait for the collectives.
+    reducer = D.GradientReducer(net.parameters(), bucket_bytes=32 << 20) if world > 1 else None
+    comm_on = {"on": True}
+
     def step(coords, feats):
         # a training step packs the (updated) weights of every convolution once — all images in one launch, as a loop does
         # after its optimizer update; with no optimizer in the metric the cached images would otherwise survive from step
@@ -255,7 +287,12 @@ def run_ours(args):
         out, _ = net(x)
         loss = (out.F * wvec).mean()
         loss.backward()
-        net.zero_grad(set_to_none=True)
+        if reducer is not None:
+            reducer.enabled = comm_on["on"]
+            reducer.finish()
+            reducer.zero_grad()
+        else:
+            net.zero_grad(set_to_none=True)
         return loss
 
     def barrier():
@@ -321,34 +358,64 @@ def run_ours(args):
         for _ in range(3):
             barrier()
             dist.all_reduce(torch.zeros(1, device=dev))
-    n_warm = max(args.warmup, int(os.environ.get("US3D_BENCH_MIN_WARMUP", "50")))  # (lowered only for ncu launch lists)
-    for _ in range(n_warm):
-        step_resident()
-        if rank == 0:
-            sampler.sample()  # absorbs NVML's lazy initialisation (first query: 3 ms); samples outside the timed region are dropped
-    if rank == 0 and sampler.nvml is None:
-        time.sleep(0.3)  # nvidia-smi fallback: let the subprocess start reporting
-        for _ in range(2):
-            step_resident()  # and bring the device back under load before the clock starts
-    # Everything alive after the warm-up (model, cached plans, allocator bookkeeping) is long-lived: park it in the permanent
-    # generation so that a cyclic-GC pass inside a timed step only walks that step's own objects (a full collection over the
-    # whole heap is a ~100 ms host stall; training loops do the same with gc.freeze() / scheduled collections).
+    # PRIME_STEPS untimed steps (allocator pools of the two streams, NVML's lazy initialisation, clock / power ramp of a fresh
+    # box; lowered only for ncu launch lists) — then everything alive is parked in the permanent GC generation (a full
+    # cyclic collection over the whole heap inside a timed step is a ~100 ms host stall; training loops do the same with
+    # gc.freeze()) — then exactly --warmup warm-up steps, then the clock.
     import gc
 
+    n_prime = int(os.environ.get("US3D_BENCH_PRIME", str(PRIME_STEPS)))
+    for _ in range(n_prime):
+        step_resident()
+        if rank == 0:
+            sampler.sample()  # first query: 3 ms; samples outside the timed region are dropped
+    if rank == 0 and sampler.nvml is None:
+        time.sleep(0.3)  # nvidia-smi fallback: let the subprocess start reporting
     gc.collect()
     gc.freeze()
-    barrier()
-    for _ in range(5):  # ranks leave the barrier at slightly different times: a few more steps before the clock starts
+    for _ in range(args.warmup):
         step_resident()
     _lib.reset_launch_count()
     ms_total, t0, t1 = timed(step_resident, args.steps, sampler if rank == 0 else None)
     launches = _lib.launch_count()
     clocks = sampler.stop(t0, t1) if rank == 0 else None
-    for _ in range(10):  # the end-to-end leg has its own allocator pool (copies on the coordinate stream): warm it
+    for _ in range(max(args.warmup, 5)):  # the end-to-end leg has its own allocator pool (copies on the coordinate stream)
         step_e2e()
     gc.collect()
     gc.freeze()
     ms_e2e, _, _ = timed(step_e2e, args.steps)
+
+    # ---- N > 1: what the collective costs.  (a) the same step with the all-reduces switched off (the buckets are still
+    # filled): the difference is the EXPOSED communication per step; (b) the buckets all-reduced back to back with nothing
+    # else running: algorithmic bus bandwidth 2 (N-1)/N * bytes / time.
+    comm = None
+    if reducer is not None:
+        comm_on["on"] = False
+        for _ in range(3):
+            step_resident()
+        ms_nocomm, _, _ = timed(step_resident, args.steps)
+        comm_on["on"] = True
+        for _ in range(2):
+            step_resident()
+        barrier()
+        s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        s_ev.record()
+        for _ in range(reps):
+            for bkt in reducer.buckets:
+                dist.all_reduce(bkt.flat, op=dist.ReduceOp.AVG)
+        e_ev.record()
+        torch.cuda.synchronize()
+        ar_ms = torch.tensor([s_ev.elapsed_time(e_ev) / reps], device=dev, dtype=torch.float64)
+        dist.all_reduce(ar_ms, op=dist.ReduceOp.MAX)
+        ar_ms = float(ar_ms.item())
+        nbytes = reducer.total_bytes
+        comm = {"collective": "all-reduce (NCCL, AVG) of the fp32 gradients, launched per bucket from gradient hooks during backward",
+                "bytes_per_step": int(nbytes), "buckets": len(reducer.buckets),
+                "step_ms_without_collective": ms_nocomm / args.steps,
+                "exposed_ms_per_step": (ms_total - ms_nocomm) / args.steps,
+                "standalone_allreduce_ms": ar_ms,
+                "busbw_gbs": 2.0 * (world - 1) / world * nbytes / (ar_ms * 1e-3) / 1e9}
 
     if os.environ.get("US3D_BENCH_DEBUG"):
         for name, fn in (("resident", step_resident), ("e2e", step_e2e), ("resident", step_resident), ("e2e", step_e2e)):
@@ -358,23 +425,25 @@ def run_ours(args):
     value = world * args.voxels * args.steps / (ms_total * 1e-3)
     e2e_value = world * args.voxels * args.steps / (ms_e2e * 1e-3)
 
-    roofline = cpu_baseline = None
+    roofline = roofline_wgrad = cpu_baseline = None
     if rank == 0:
-        # ---- roofline leg: the dominant kernel is us3d::mt::k_spconv_mt (tcgen05 sparse-conv forward + input gradient,
-        # 45 % of the step in the ncu launch list).  ncu --set full shows it tensor-pipe bound, not HBM bound (tensor pipe
-        # active 80 % of the cycles, DRAM 5 % of peak, DRAM traffic == algorithmic bytes: profiles/r1_ncu_full_summary.md),
-        # so the roof reported is the tensor one; the HBM view of the same launches is kept next to it.
-        #   achieved = ALGORITHMIC FLOPs (2 * kernel-map pairs * Cin * Cout per launch) / launch durations;
-        #   the kernel executes ~7.4x that: three bf16 passes per product (fp32-faithful split) and zero rows for the
-        #   neighbours a 128-row tile does not have.
+        # ---- roofline leg.  The dominant kernel is us3d::mt::k_spconv_mt (tcgen05 sparse-conv forward + input gradient);
+        # the second is us3d::wg::k_wgrad (weight gradient).  north_star judges the HBM roof:
+        #   achieved = ALGORITHMIC bytes of the launches (fp32 X + Y [+ dX] rows + weights, kernel-map
+        #   indices and BN / ReLU / residual traffic count zero) / their summed durations, CUDA events recorded inside libus3d
+        #   around each launch on the launch stream during normal steps;  peak = MEASURED_PEAKS.json hbm_gbs.
+        # The tensor view of the same launches (algorithmic FLOPs = 2 * kernel-map pairs * Cin * Cout against the measured
+        # sustained bf16 GEMM rate) is kept next to it: at Cin, Cout >= 96 the layers are tensor-bound at ideal traffic
+        # (264 FLOP/B against a ridge of 212), and the kernel executes ~7x the algorithmic FLOPs (three bf16
+        # products per fp32 product, zero rows of 128-row tiles).
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
             peaks = json.load(open(peaks_path))
             peak_tf = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
-            peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained: kernels timed inside a long step)"
+            peak_src = "measured (MEASURED_PEAKS.json: hbm_gbs; bf16_tflops_sustained for the tensor view — kernels timed inside a long step)"
             peak_hbm = float(peaks["hbm_gbs"])
         else:
-            peak_tf, peak_src, peak_hbm = 1500.0, "fallback (B200_PROFILING.md)", 6650.0
+            peak_tf, peak_src, peak_hbm = 1400.0, "fallback (B200_PROFILING.md: 6.65 TB/s, ~1.4 PFLOP/s sustained)", 6650.0
         prof_steps = 2
         recs = []
         for _ in range(prof_steps):
@@ -383,29 +452,32 @@ def run_ours(args):
                 step_resident()
             recs += kt.summary()
         # (kind, n_in, n_out, kvol, cin, cout, pairs, path, ms)
-        dom = [r for r in recs if r[0] in ("fwd", "dgrad") and r[7] == "mt"]
-        dom_ms = sum(r[8] for r in dom)
-        dom_flops = sum(2.0 * r[6] * r[4] * r[5] for r in dom)
-        dom_exec_flops = sum(2.0 * r[2] * r[3] * r[4] * r[5] * (3 if Fn.get_precision() == 3 else 1) for r in dom)
-        dom_bytes = sum(conv_layer_bytes(r[1], r[2], r[3], r[4], r[5], r[0]) for r in dom)
-        wg_ms = sum(r[8] for r in recs if r[0] == "wgrad")
-        other_ms = sum(r[8] for r in recs if r[0] != "wgrad" and r not in dom)
-        achieved = dom_flops / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
-        roofline = {"bound": "tensor", "kernel": "us3d::mt::k_spconv_mt (tcgen05 sparse-conv forward + input-gradient launches)",
-                    "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                    # dram__bytes_read + write of the 200k-voxel 128->96 k3 launch (ncu --set full, profiles/r1_ncu_full_summary.md:
-                    # 369.1 + 64.6 MB with the rows in neighbour-pattern order; 172.0 MB in natural order); algorithmic bytes: 179.5e6
-                    "traffic": 433717248,
-                    "peak_source": peak_src,
+        passes = 3 if Fn.get_precision() == 3 else 1
+
+        def view(rows, kinds_label, traffic):
+            ms = sum(r[8] for r in rows)
+            flops = sum(2.0 * r[6] * r[4] * r[5] for r in rows)
+            exec_flops = sum(2.0 * r[2] * r[3] * r[4] * r[5] * passes for r in rows)
+            nbytes = sum(conv_layer_bytes(r[1], r[2], r[3], r[4], r[5], r[0]) for r in rows)
+            gbs = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+            tfs = flops / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+            return {"bound": "hbm", "kernel": kinds_label, "achieved": gbs, "peak": peak_hbm, "unit": "GB/s", "frac": gbs / peak_hbm,
+                    "traffic": traffic["dram_bytes"], "traffic_of": traffic, "peak_source": peak_src,
                     "timing": "CUDA events recorded around each launch inside libus3d, on the launch stream, during normal steps",
-                    "launches_per_step": len(dom) // prof_steps, "kernel_ms_per_step": dom_ms / prof_steps,
-                    "alg_gflop_per_step": dom_flops / prof_steps / 1e9,
-                    "executed_tflops": dom_exec_flops / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0,
-                    "hbm_view": {"achieved_gbs": dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0, "peak_gbs": peak_hbm,
-                                 "frac": (dom_bytes / (dom_ms * 1e-3) / 1e9 / peak_hbm) if dom_ms > 0 else 0.0,
-                                 "alg_bytes_per_step": dom_bytes / prof_steps},
-                    "wgrad_ms_per_step": wg_ms / prof_steps, "other_conv_ms_per_step": other_ms / prof_steps,
-                    "step_ms": ms_total / args.steps, "level_sizes": level_sizes(c4_host.numpy())}
+                    "launches_per_step": len(rows) // prof_steps, "kernel_ms_per_step": ms / prof_steps,
+                    "alg_bytes_per_step": nbytes / prof_steps, "alg_gflop_per_step": flops / prof_steps / 1e9,
+                    "tensor_view": {"achieved_tflops": tfs, "peak_tflops": peak_tf, "frac": tfs / peak_tf,
+                                    "executed_tflops": exec_flops / (ms * 1e-3) / 1e12 if ms > 0 else 0.0}}
+
+        dom = [r for r in recs if r[0] in ("fwd", "dgrad") and r[7] == "mt"]
+        wg = [r for r in recs if r[0] == "wgrad" and r[7] == "wgrad-tc"]
+        # `traffic`: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (ncu --set full, profiles/r2_ncu_full_summary.md)
+        # next to that launch's algorithmic bytes
+        roofline = view(dom, "us3d::mt::k_spconv_mt (tcgen05 sparse-conv forward + input-gradient launches)", NCU_TRAFFIC["mt"])
+        roofline_wgrad = view(wg, "us3d::wg::k_wgrad (tcgen05 weight-gradient launches)", NCU_TRAFFIC["wgrad"])
+        other_ms = sum(r[8] for r in recs if r not in dom and r not in wg)
+        roofline.update({"other_conv_ms_per_step": other_ms / prof_steps, "step_ms": ms_total / args.steps,
+                         "level_sizes": level_sizes(c4_host.numpy())})
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         with open(os.path.join(ROOT, "gpurun_out", "bench_layers.json"), "w") as fh:
             json.dump([{"kind": r[0], "n_in": r[1], "n_out": r[2], "kvol": r[3], "cin": r[4], "cout": r[5], "pairs": r[6], "path": r[7],
@@ -420,16 +492,15 @@ def run_ours(args):
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": n_warm,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"Res16UNet34C fwd+bwd, synthetic ScanNet-shaped {args.voxels}-voxel scene, batch=1 per GPU (BASELINE configs[1])",
-                       "parallelism": f"dp{world} (one scene per GPU, no data-path collective)",
-                       "l2": "256 MiB buffer written between timed iterations (L2 flush)",
-                       "step": "coordinate-manager build (on a high-priority side stream) + forward + loss + backward"},
+            "dtype": DTYPE, "data": "synthetic",
+            "config": bench_config(args.voxels, world),
+            "prime_steps": n_prime,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(c4_host.numel() * 4 + f_host.numel() * 4),
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_wgrad": roofline_wgrad,
+            "cpu_baseline": cpu_baseline, "comm": comm,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

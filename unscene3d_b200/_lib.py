@@ -4,7 +4,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libus3d.so")
+LIB_PATH = os.environ.get("US3D_LIB") or os.path.join(_HERE, "csrc", "libus3d.so")  # US3D_LIB: A/B builds of the same ABI (scripts/)
 
 _i, _ll, _f = ctypes.c_int, ctypes.c_longlong, ctypes.c_float
 _p = ctypes.c_void_p

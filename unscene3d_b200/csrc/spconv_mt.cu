@@ -15,6 +15,18 @@
 //   warp 5     MMA issuer: tcgen05.mma M=128, N=Cout, K=16 (x3 for the split); tcgen05.commit frees slots
 //   warps 6-9  epilogue: tcgen05.ld -> (+bias, +=) -> fp32 rows
 //
+// Round 2:
+//   * warp 10 streams the neighbour indices of the next NIDX (super-tile, offset) pairs into a shared-memory ring with
+//     4-byte cp.async (mbarrier completion): the producers no longer expose one L2 round trip per offset, and no index
+//     lives in a register across an item (a register double buffer was measured 27 % SLOWER: ptxas spilled the prefetched
+//     values, which turns every prefetch into a blocking load);
+//   * LAG == 0: completion by cp.async.mbarrier.arrive.noinc — a producer never waits for its own copies, the whole A
+//     ring can be in flight (the MMA warp crosses generic -> async proxy with fence.proxy.async after its wait);
+//   * FUSE (three-term mode, Cout <= 128): the weight slab [W_hi rows | W_lo rows] is one K-major B operand of
+//     N = 2 Cout rows, so X_hi W_hi and X_hi W_lo are ONE tcgen05.mma (A read from shared memory once, 10 KB of operands
+//     per 96 issue cycles instead of 2 x 7 KB per 2 x 48) landing in column groups [0, Cout) and [Cout, 2 Cout) that the
+//     epilogue adds; X_lo W_hi follows with N = Cout.
+//
 // Replaces MinkowskiConvolution / MinkowskiConvolutionTranspose forward and input gradient
 // (/root/reference/models/modules/common.py:146-155, 179-188).
 #include "common.cuh"
@@ -30,8 +42,10 @@ constexpr int KC = 64;
 constexpr int A_PLANE = M * 128;  // bytes of one plane of one A slot
 constexpr int PROD_WARPS = 4;
 constexpr int B_WARP = PROD_WARPS, MMA_WARP = PROD_WARPS + 1, EPI_WARP0 = PROD_WARPS + 2;
-constexpr int THREADS = (PROD_WARPS + 2 + 4) * 32;
+constexpr int IDX_WARP = PROD_WARPS + 6;
+constexpr int THREADS = (PROD_WARPS + 2 + 4 + 1) * 32;
 constexpr int MAX_A = 8, MAX_B = 3, MAX_T = 4;
+constexpr int NIDX = 4;  // stages of the neighbour-index ring (one stage = the indices of one offset for the T tiles)
 
 struct Params {
     const __nv_bfloat16 *x_hi, *x_lo;  // [n_in, cin] planes
@@ -50,11 +64,14 @@ struct Params {
     long long *prof;  // optional per-CTA wait-cycle counters of the MMA thread (debug)
 };
 
-template <int PASSES, int LAG>
+template <int PASSES, int LAG, bool FUSE>
 __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
+    static_assert(!FUSE || PASSES == 3, "the fused [W_hi | W_lo] operand exists in three-term mode only");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t a_full[MAX_A], a_empty[MAX_A], b_full[MAX_B], b_empty[MAX_B], acc_full, acc_empty;
     __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(8) uint64_t idx_full[NIDX], idx_empty[NIDX];
+    __shared__ int32_t idx_ring[NIDX][MAX_T][M];
     constexpr int NPL = PASSES == 3 ? 2 : 1;
     constexpr int A_SLOT = NPL * A_PLANE;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -67,12 +84,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
 
     if (tid == 0) {
         for (int s = 0; s < p.a_slots; ++s) {
-            mbar_init(smem_u32(&a_full[s]), PROD_WARPS);
+            mbar_init(smem_u32(&a_full[s]), LAG == 0 ? PROD_WARPS * 32 : PROD_WARPS);
             mbar_init(smem_u32(&a_empty[s]), 1);
         }
         for (int s = 0; s < p.b_slots; ++s) {
             mbar_init(smem_u32(&b_full[s]), 1);
             mbar_init(smem_u32(&b_empty[s]), 1);
+        }
+        for (int s = 0; s < NIDX; ++s) {
+            mbar_init(smem_u32(&idx_full[s]), 32);
+            mbar_init(smem_u32(&idx_empty[s]), PROD_WARPS);
         }
         mbar_init(smem_u32(&acc_full), 1);
         mbar_init(smem_u32(&acc_empty), 4);
@@ -91,12 +112,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
 
     if (warp < PROD_WARPS) {
         // ------------------------------------------------------------------ A producers
+        // Neighbour indices come from the index ring in shared memory (filled ahead of time by the index warp): no global
+        // load sits between two gathers, and no index lives in a register across an item.
         constexpr int RPT = 8;       // rows per thread: rbase + 16 i
         const int grp = tid & 7;     // 16-byte chunk within the 128-byte row
         const int rbase = tid >> 3;
         int item = 0, signalled = 0;
         int ps = 0, ss = 0;  // ring positions of `item` and `signalled`
         uint32_t ppar = 0;
+        int is = 0;          // index-ring stage of the current (super-tile, offset)
+        uint32_t ipar = 0;
         for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
             const int st = u / p.ksplit;
             const uint32_t pm = p.part_mask[u - st * p.ksplit];
@@ -108,42 +133,43 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
             }
             for (int k = 0; k < p.kvol; ++k) {
                 if (!((U >> k) & 1u)) continue;
-                int idx[MAX_T][RPT];
-#pragma unroll
-                for (int t = 0; t < MAX_T; ++t) {
-                    if (!((m[t] >> k) & 1u)) continue;
-                    const int tile0 = (st * T + t) * M;
-#pragma unroll
-                    for (int i = 0; i < RPT; ++i) {
-                        const int j = tile0 + rbase + 16 * i;
-                        idx[t][i] = j < p.n_rows ? __ldg(p.nbr + (size_t)k * p.n_rows + j) : -1;
-                    }
-                }
+                mbar_wait(smem_u32(&idx_full[is]), ipar, 6);
                 for (int c = 0; c < p.nchunks; ++c) {
                     const int c0 = c * KC + grp * 8;
                     const bool col_ok = c0 < p.cin;
 #pragma unroll
                     for (int t = 0; t < MAX_T; ++t) {
                         if (!((m[t] >> k) & 1u)) continue;
+                        const int tile0 = (st * T + t) * M;
+                        int idx[RPT];
+#pragma unroll
+                        for (int i = 0; i < RPT; ++i) {
+                            const int r = rbase + 16 * i;
+                            idx[i] = tile0 + r < p.n_rows ? idx_ring[is][t][r] : -1;
+                        }
                         mbar_wait(smem_u32(&a_empty[ps]), ppar ^ 1, 0);
                         const uint32_t slot = a_base + (uint32_t)ps * A_SLOT;
 #pragma unroll
                         for (int i = 0; i < RPT; ++i) {
                             const int r = rbase + 16 * i;
                             const uint32_t dst = slot + (uint32_t)r * 128u + (uint32_t)((grp ^ (r & 7)) << 4);
-                            const bool ok = idx[t][i] >= 0 && col_ok;
-                            const size_t off = ok ? (size_t)idx[t][i] * p.cin + c0 : 0;
+                            const bool ok = idx[i] >= 0 && col_ok;
+                            const size_t off = ok ? (size_t)idx[i] * p.cin + c0 : 0;
                             cp_async16(dst, p.x_hi + off, ok ? 16u : 0u);
                             if (PASSES == 3) cp_async16(dst + A_PLANE, p.x_lo + off, ok ? 16u : 0u);
                         }
-                        cp_async_commit();
-                        if (item - signalled >= LAG) {
-                            cp_async_wait<LAG>();
-                            fence_proxy_async();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(smem_u32(&a_full[ss]));
-                            ++signalled;
-                            if (++ss == p.a_slots) ss = 0;
+                        if (LAG == 0) {
+                            cp_async_arrive_noinc(smem_u32(&a_full[ps]));
+                        } else {
+                            cp_async_commit();
+                            if (item - signalled >= LAG) {
+                                cp_async_wait<(LAG > 0 ? LAG : 1)>();
+                                fence_proxy_async();
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(smem_u32(&a_full[ss]));
+                                ++signalled;
+                                if (++ss == p.a_slots) ss = 0;
+                            }
                         }
                         ++item;
                         if (++ps == p.a_slots) {
@@ -152,15 +178,61 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
                         }
                     }
                 }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&idx_empty[is]));
+                if (++is == NIDX) {
+                    is = 0;
+                    ipar ^= 1u;
+                }
             }
         }
         cp_async_wait<0>();
-        fence_proxy_async();
-        __syncwarp();
-        for (; signalled < item; ++signalled) {
-            if (lane == 0) mbar_arrive(smem_u32(&a_full[ss]));
-            if (++ss == p.a_slots) ss = 0;
+        if (LAG != 0) {
+            fence_proxy_async();
+            __syncwarp();
+            for (; signalled < item; ++signalled) {
+                if (lane == 0) mbar_arrive(smem_u32(&a_full[ss]));
+                if (++ss == p.a_slots) ss = 0;
+            }
         }
+    } else if (warp == IDX_WARP) {
+        // ------------------------------------------------------------------ neighbour indices, NIDX offsets ahead
+        // 4-byte cp.async straight from the kernel map into the index ring; completion by mbarrier (noinc): the warp never
+        // waits for a load.  Rows past the map and tiles without the offset are never read by the producers.
+        int is = 0;
+        uint32_t ipar = 0;
+        for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+            const int st = u / p.ksplit;
+            const uint32_t pm = p.part_mask[u - st * p.ksplit];
+            uint32_t m[MAX_T], U = 0;
+#pragma unroll
+            for (int t = 0; t < MAX_T; ++t) {
+                m[t] = t < T ? tile_kmask(st * T + t, pm) : 0u;
+                U |= m[t];
+            }
+            for (int k = 0; k < p.kvol; ++k) {
+                if (!((U >> k) & 1u)) continue;
+                mbar_wait(smem_u32(&idx_empty[is]), ipar ^ 1, 7);
+                const int32_t *src_k = p.nbr + (size_t)k * p.n_rows;
+#pragma unroll
+                for (int t = 0; t < MAX_T; ++t) {
+                    if (!((m[t] >> k) & 1u)) continue;
+                    const int tile0 = (st * T + t) * M;
+#pragma unroll
+                    for (int q = 0; q < M / 32; ++q) {
+                        const int r = lane + 32 * q;
+                        const bool ok = tile0 + r < p.n_rows;
+                        cp_async4(smem_u32(&idx_ring[is][t][r]), src_k + (ok ? tile0 + r : 0), ok ? 4u : 0u);
+                    }
+                }
+                cp_async_arrive_noinc(smem_u32(&idx_full[is]));
+                if (++is == NIDX) {
+                    is = 0;
+                    ipar ^= 1u;
+                }
+            }
+        }
+        cp_async_wait_all();
     } else if (warp == B_WARP) {
         // ------------------------------------------------------------------ weight slabs
         if (lane == 0) {
@@ -193,6 +265,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
         // uniform registers; one elected lane issues tcgen05.mma / tcgen05.commit.  (A single-lane branch makes
         // ptxas wrap every UTCHMMA in an elect + R2UR.BROADCAST loop: ~80 issue cycles per MMA, measured.)
         const uint32_t idesc = idesc_bf16(p.cout);
+        const uint32_t idesc2 = idesc_bf16(2 * p.cout);  // FUSE: B = [W_hi rows | W_lo rows]
         const uint64_t a_desc0 = desc_k_sw128(a_base), b_desc0 = desc_k_sw128(b_base);
         int as = 0, bs = 0, siter = 0, item = 0, bitem = 0;
         uint32_t apar = 0, bpar = 0;
@@ -227,6 +300,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
                         long long tw2 = clock64();
                         mbar_wait(smem_u32(&a_full[as]), apar, 4);
                         w_a += clock64() - tw2;
+                        if (LAG == 0) fence_proxy_async();  // cp.async writes (generic proxy) -> tcgen05 reads (async proxy)
                         tc_fence_after();
                         const uint64_t da_hi = a_desc0 + (uint64_t)((uint32_t)(as * A_SLOT) >> 4);
                         const uint64_t da_lo = da_hi + (uint64_t)(A_PLANE >> 4);
@@ -235,10 +309,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
                         if (elect_one()) {
                             for (int kk = 0; kk < ksteps; ++kk) {
                                 const uint64_t adv = (uint64_t)(kk * 2);
-                                umma(acc, da_hi + adv, db_hi + adv, idesc, first | (kk != 0));
-                                if (PASSES == 3) {
+                                if (FUSE) {
+                                    umma(acc, da_hi + adv, db_hi + adv, idesc2, first | (kk != 0));
                                     umma(acc, da_lo + adv, db_hi + adv, idesc, 1);
-                                    umma(acc, da_hi + adv, db_lo + adv, idesc, 1);
+                                } else {
+                                    umma(acc, da_hi + adv, db_hi + adv, idesc, first | (kk != 0));
+                                    if (PASSES == 3) {
+                                        umma(acc, da_lo + adv, db_hi + adv, idesc, 1);
+                                        umma(acc, da_hi + adv, db_lo + adv, idesc, 1);
+                                    }
                                 }
                             }
                             umma_commit(smem_u32(&a_empty[as]));
@@ -277,7 +356,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
             o[4] = item;
             o[5] = bitem;
         }
-    } else {
+    } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + 4) {
         // ------------------------------------------------------------------ epilogue
         const int quarter = warp & 3;
         const bool vec = (p.ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
@@ -303,6 +382,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
                     float acc[16];
                     if (has_acc) {
                         tmem_ld16(acc_addr + (uint32_t)col, acc);
+                        if (FUSE) {
+                            float acc2[16];
+                            tmem_ld16(acc_addr + (uint32_t)(p.cout + col), acc2);
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) acc[e] += acc2[e];
+                        }
                     } else {
 #pragma unroll
                         for (int e = 0; e < 16; ++e) acc[e] = 0.f;
@@ -348,14 +433,25 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
     if (warp == MMA_WARP) tmem_dealloc(tmem_base, (uint32_t)(T * p.acc_cols));
 }
 
-template <int PASSES>
-static void launch(int lag, int grid, size_t smem, cudaStream_t st, const Params &p) {
-    if (lag >= 3)
-        k_spconv_mt<PASSES, 3><<<grid, THREADS, smem, st>>>(p);
-    else if (lag == 2)
-        k_spconv_mt<PASSES, 2><<<grid, THREADS, smem, st>>>(p);
-    else
-        k_spconv_mt<PASSES, 1><<<grid, THREADS, smem, st>>>(p);
+template <int PASSES, bool FUSE>
+static cudaError_t launch(int lag, int grid, size_t smem, cudaStream_t st, const Params &p) {
+    // every instantiation needs the opt-in for > 48 KB of dynamic shared memory once per device
+    static bool attr_done[4][64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    auto go = [&](auto kernel, int slot) -> cudaError_t {
+        if (dev >= 0 && dev < 64 && !attr_done[slot][dev]) {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);  // + 9 KB static (index ring, barriers) <= 227 KB
+            if (e != cudaSuccess) return e;
+            attr_done[slot][dev] = true;
+        }
+        kernel<<<grid, THREADS, smem, st>>>(p);
+        return cudaSuccess;
+    };
+    if (lag <= 0) return go(k_spconv_mt<PASSES, 0, FUSE>, 0);
+    if (lag == 1) return go(k_spconv_mt<PASSES, 1, FUSE>, 1);
+    if (lag == 2) return go(k_spconv_mt<PASSES, 2, FUSE>, 2);
+    return go(k_spconv_mt<PASSES, 3, FUSE>, 3);
 }
 
 }  // namespace mt
@@ -364,18 +460,25 @@ static void launch(int lag, int grid, size_t smem, cudaStream_t st, const Params
 using namespace us3d;
 
 static long long *g_prof = nullptr;
+// launcher defaults (set from the measurements in profiles/r2_conv_tuning.md)
+static bool g_default_fuse = true;
+static int g_default_lag = 0;  // 0: completion by cp.async.mbarrier.arrive.noinc (measured best on every level, profiles/r2_conv_tuning.md); -1: wait_group look-ahead 1 (three-term) / 2 (single pass)
 
-static int g_tune_a_slots = 0, g_tune_lag = 0, g_tune_T = 0;
+static int g_tune_a_slots = 0, g_tune_lag = 0, g_tune_T = 0, g_tune_fuse = 0;
 
 extern "C" {
 
 /* debug / tuning hooks (not part of the drop-in surface): per-CTA wait counters of the MMA thread, ring overrides */
 void us3d_debug_set_prof(void *buf) { g_prof = (long long *)buf; }
-void us3d_debug_set_tuning(int a_slots, int lag, int T) {
+/* a_slots / T: 0 = launcher's choice.  lag: 0 = launcher's choice, 1..3 = cp.async.wait_group look-ahead, 9 = completion by
+   cp.async.mbarrier.arrive.noinc (producers never wait).  fuse: 0 = launcher's choice, 1 = off, 2 = on (where eligible). */
+void us3d_debug_set_tuning4(int a_slots, int lag, int T, int fuse) {
     g_tune_a_slots = a_slots;
     g_tune_lag = lag;
     g_tune_T = T;
+    g_tune_fuse = fuse;
 }
+void us3d_debug_set_tuning(int a_slots, int lag, int T) { us3d_debug_set_tuning4(a_slots, lag, T, 0); }
 
 int us3d_spconv_gather_mt(const void *x_hi, const void *x_lo, int n_in, const int32_t *nbr, int n_rows, int kvol,
                           const void *wpack, int cin, int cout, int passes, const float *bias, const int32_t *out_rows,
@@ -395,8 +498,12 @@ int us3d_spconv_gather_mt(const void *x_hi, const void *x_lo, int n_in, const in
     p.wpack = (const uint8_t *)wpack; p.cin = cin; p.cout = cout; p.nchunks = ceil_div(cin, mt::KC);
     p.bias = bias; p.out_rows = out_rows; p.y = y; p.ldy = ldy; p.accumulate = accumulate; p.tile_mask = tile_mask;
     const int npl = passes == 3 ? 2 : 1;
+    // fused [W_hi | W_lo] operand: one N = 2 Cout MMA for the two products that share X_hi (three-term mode, N <= 256)
+    bool fuse = passes == 3 && 2 * cout <= 256 && g_default_fuse;
+    if (g_tune_fuse == 1) fuse = false;
+    if (g_tune_fuse == 2) fuse = passes == 3 && 2 * cout <= 256;
     int cols = 32;
-    while (cols < cout) cols <<= 1;
+    while (cols < (fuse ? 2 * cout : cout)) cols <<= 1;
     p.acc_cols = cols;
     int T = 512 / cols;
     if (T > mt::MAX_T) T = mt::MAX_T;
@@ -431,29 +538,22 @@ int us3d_spconv_gather_mt(const void *x_hi, const void *x_lo, int n_in, const in
     if (p.a_slots == mt::MAX_A && budget - p.a_slots * a_slot - 3 * b_slot >= 0) p.b_slots = 3;
     if (g_tune_a_slots >= 2 && g_tune_a_slots <= p.a_slots) p.a_slots = g_tune_a_slots;
     const size_t smem = (size_t)p.a_slots * a_slot + (size_t)p.b_slots * b_slot + 1024;
-    static bool attr_done = false;
-    if (!attr_done) {
-        US3D_CUDA(cudaFuncSetAttribute(mt::k_spconv_mt<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-        US3D_CUDA(cudaFuncSetAttribute(mt::k_spconv_mt<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-        US3D_CUDA(cudaFuncSetAttribute(mt::k_spconv_mt<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-        US3D_CUDA(cudaFuncSetAttribute(mt::k_spconv_mt<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-        US3D_CUDA(cudaFuncSetAttribute(mt::k_spconv_mt<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-        US3D_CUDA(cudaFuncSetAttribute(mt::k_spconv_mt<3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-        attr_done = true;
-    }
     const int grid = p.n_units < num_sms() ? p.n_units : num_sms();
     // Groups a producer warp keeps in flight before it waits for the oldest.  Measured on B200 (200k voxels, 128 -> 96):
     // three-term mode 0.521 ms at lag 3, 0.472 ms at lag 1 — with 32 KB slots a deep lag leaves the MMA warp no landed
     // slot to run ahead on; single-pass mode is best at lag 2.
-    int lag = passes == 3 ? 1 : 2;
+    int lag = g_default_lag >= 0 ? g_default_lag : (passes == 3 ? 1 : 2);
     if (lag > p.a_slots - 1) lag = p.a_slots - 1;
     if (g_tune_lag >= 1 && g_tune_lag <= p.a_slots - 1) lag = g_tune_lag;
+    if (g_tune_lag == 9) lag = 0;
     {
         ProfScope prof(st, 0, n_in, n_rows, kvol, cin, cout);
+        cudaError_t e;
         if (passes == 3)
-            mt::launch<3>(lag, grid, smem, st, p);
+            e = fuse ? mt::launch<3, true>(lag, grid, smem, st, p) : mt::launch<3, false>(lag, grid, smem, st, p);
         else
-            mt::launch<1>(lag, grid, smem, st, p);
+            e = mt::launch<1, false>(lag, grid, smem, st, p);
+        US3D_CUDA(e);
     }
     US3D_LAUNCH_CHECK();
     return 0;

@@ -65,6 +65,9 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {  // zero-fills 16 - src_bytes
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src, uint32_t src_bytes) {  // zero-fills 4 - src_bytes
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
