@@ -365,8 +365,16 @@ def run_ours(args):
     import gc
 
     n_prime = int(os.environ.get("US3D_BENCH_PRIME", str(PRIME_STEPS)))
-    for _ in range(n_prime):
+    debug = bool(os.environ.get("US3D_BENCH_DEBUG"))
+    if debug:
+        import faulthandler
+
+        faulthandler.dump_traceback_later(int(os.environ.get("US3D_BENCH_DUMP_AFTER", "90")), exit=True)
+    for i in range(n_prime):
         step_resident()
+        if debug:
+            torch.cuda.synchronize()
+            print(f"[debug] rank {rank}: prime step {i} done", file=sys.stderr, flush=True)
         if rank == 0:
             sampler.sample()  # first query: 3 ms; samples outside the timed region are dropped
     if rank == 0 and sampler.nvml is None:
@@ -446,6 +454,7 @@ def run_ours(args):
             peak_tf, peak_src, peak_hbm = 1400.0, "fallback (B200_PROFILING.md: 6.65 TB/s, ~1.4 PFLOP/s sustained)", 6650.0
         prof_steps = 2
         recs = []
+        comm_on["on"] = False  # rank 0 runs these steps alone: no collective may be issued here
         for _ in range(prof_steps):
             with Fn.KernelTimer() as kt:
                 flush.zero_()

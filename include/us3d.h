@@ -278,6 +278,14 @@ int us3d_matcher_cost(const float *logits, int s, int q, const float *tgt, int t
 int us3d_pooled_mask_bits(const int64_t *rowptr, const int64_t *col, const float *val, int n_rows, const float *seg, int q,
                           uint8_t *bits, void *stream);
 
+/* Fourier positional encoding of xyz rows (models/position_embedding.py:128-172 get_fourier_embeddings, called from
+ * models/mask3d.py:183-198, 238-240): xyz[n, >=3] fp32 with leading dimension ld; lo[3] / hi[3] (device, both or neither) = the
+ * input range the rows are normalised to the unit cube with; gauss_b[3, >= d_out] (leading dimension ldb) = the module's
+ * `gauss_B` buffer; out[n, 2 d_out] row-major = [sin(2 pi t . B) | cos(2 pi t . B)] — the transpose of the reference's
+ * [1, 2 d_out, n] result, which every caller permutes into this layout.                                              */
+int us3d_fourier_posenc(const float *xyz, int n, int ld, const float *lo, const float *hi, const float *gauss_b, int ldb,
+                        int d_out, float *out, void *stream);
+
 /* Mask losses of the set criterion for the matched pairs of one scene (models/criterion.py:22-73 dice_loss / sigmoid_ce_loss,
  * called from loss_masks :168-216):  logits[s, q] fp32 (pred_masks of the scene), tgt[t_all, s] (float32, or uint8 / bool when
  * tgt_is_float == 0), qidx[t] / tidx[t] int64 = matched query / target of pair t, weights[t] (may be NULL = 1; the DropLoss

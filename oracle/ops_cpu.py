@@ -163,6 +163,24 @@ def segment_attention_masks(model, mask_features, output_segments, point2segment
               coordinate_map_key=attn_mask.coordinate_map_key)
 
 
+def fourier_posenc(xyz, gauss_b, d_out, lo=None, hi=None):
+    """Rows [N, 2 d_out] of the reference's Fourier features, restated operation by operation from
+    models/position_embedding.py:12-40 (shift_scale_points onto the unit cube) and :128-160 (get_fourier_embeddings):
+    clone, normalise, `xyz *= 2 * np.pi`, `torch.mm(xyz, gauss_B[:, :d_out])`, cat(sin, cos).  The reference returns the
+    transpose [1, 2 d_out, N]; every caller permutes it back (models/mask3d.py:195-196)."""
+    import numpy as np
+
+    t = xyz.clone().float()
+    if lo is not None:
+        lo, hi = lo.reshape(1, -1).float(), hi.reshape(1, -1).float()
+        src_diff = hi - lo                                    # :30  src_diff = src_range[1][:, None, :] - src_range[0][:, None, :]
+        dst_lo, dst_diff = torch.zeros_like(lo), torch.ones_like(lo)  # :18-22 default dst_range = unit cube
+        t = ((t - lo) * dst_diff) / src_diff + dst_lo         # :32-35
+    t *= 2 * np.pi                                            # :149
+    proj = torch.mm(t.view(-1, gauss_b.shape[0]), gauss_b[:, :d_out].float())  # :150-152
+    return torch.cat([proj.sin(), proj.cos()], dim=1)         # :153-156 (before the permute)
+
+
 def as_module_tree():
     """Module objects `torch_scatter`, `pointnet2`, `pointnet2._ext` exporting the CPU restatements."""
     import types

@@ -84,6 +84,7 @@ def our_models_on_oracle():
     mod.mask3d.CrossAttentionLayer.attention_core = staticmethod(ops_cpu.multihead_cross_attention)
     mod.criterion.SetCriterion.mask_loss_core = staticmethod(ops_cpu.mask_losses)
     mod.mask3d.Mask3D.segment_attention_core = staticmethod(ops_cpu.segment_attention_masks)
+    mod.position_embedding.PositionEmbeddingCoordsSine.fourier_core = staticmethod(ops_cpu.fourier_posenc)
     mod.modules.resnet_block._ResidualBase.block_core = staticmethod(lambda block, x: None)  # the reference's own sequence
     mod.res16unet.Res16UNetBase.transition_core = staticmethod(lambda conv_layer, norm, x: None)
     return mod
@@ -172,3 +173,48 @@ def random_scene(n_target: int, seed: int, batch: int = 1, extent: int = 24, neg
         p = p[np.sort(first)][:n_target]
         coords.append(np.concatenate([np.full((p.shape[0], 1), b), p], 1))
     return np.concatenate(coords).astype(np.int32)
+
+
+# ---- ReLU-mask replay -----------------------------------------------------------------------------------------------
+# A parameter gradient is a sum over ~10^6 elements gated by ReLU masks.  Two implementations whose forward passes differ by
+# 1e-6 .. 4e-5 (summation order, the fp32-faithful bf16 split) disagree on the sign of a handful of near-zero
+# pre-activations; each flipped mask entry is a 100 % error on one element, so free-running gradients agree only to
+# ~sqrt(#flips / #elements) (1e-2) however exact the backward kernels are.  To pin the backward path at the north-star
+# tolerance the discrete decisions are taken out: the CUDA run records the mask of every ReLU it executes, in call order, and
+# the oracle replays them (relu(x) := x * mask).  Everything continuous is then compared at 1e-3.  (tests/test_mask3d.py
+# does the same with the decoder's boolean attention masks.)
+@contextlib.contextmanager
+def record_relu_masks(engine):
+    masks = []
+    orig = engine.MinkowskiReLU.forward
+
+    def forward(self, x):
+        out = orig(self, x)
+        masks.append((out.F.detach() > 0).cpu())
+        return out
+
+    engine.MinkowskiReLU.forward = forward
+    try:
+        yield masks
+    finally:
+        engine.MinkowskiReLU.forward = orig
+
+
+@contextlib.contextmanager
+def replay_relu_masks(me_cpu, masks, stats=None):
+    """`stats`, if given, receives (#entries where the oracle's own mask differs, #entries) per ReLU."""
+    it = iter(masks)
+    orig = me_cpu.MinkowskiReLU.forward
+
+    def forward(self, x):
+        m = next(it)
+        assert tuple(m.shape) == tuple(x.F.shape), f"ReLU call order differs: mask {tuple(m.shape)} vs features {tuple(x.F.shape)}"
+        if stats is not None:
+            stats.append((int(((x.F.detach() > 0) != m).sum()), m.numel()))
+        return x._like(x.F * m.to(x.F.dtype))
+
+    me_cpu.MinkowskiReLU.forward = forward
+    try:
+        yield
+    finally:
+        me_cpu.MinkowskiReLU.forward = orig

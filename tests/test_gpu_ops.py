@@ -621,6 +621,76 @@ def test_matcher_cost(eng):
     assert [a.tolist() for a in linear_sum_assignment(got.cpu())] == [a.tolist() for a in linear_sum_assignment(ref)]
 
 
+def test_matcher_cost_rejects_labels_outside_the_class_range_and_takes_cpu_labels(eng):
+    """The reference indexes `out_prob[:, tgt_ids]` (models/matcher.py:122-127): CPU or CUDA labels alike, IndexError for a label
+    outside [0, num_classes).  Here: CPU labels are moved, an invalid label poisons its cost column with NaN (the assignment
+    solver then rejects the matrix) and nothing is read out of bounds."""
+    from unscene3d_b200.engine import functional as Fn
+
+    torch.manual_seed(1)
+    S, Q, T = 300, 100, 6
+    prob = torch.randn(Q, 3).softmax(-1).cuda()
+    masks = (torch.randn(S, Q) * 4).cuda()
+    tgt = (torch.rand(T, S) < 0.2).float().cuda()
+    labels = torch.tensor([1, 0, 2, 253, 1, 2])
+    good = Fn.matcher_cost(masks, tgt, prob, labels, 2.0, 5.0, 2.0)          # CPU labels
+    same = Fn.matcher_cost(masks, tgt, prob, labels.cuda(), 2.0, 5.0, 2.0)
+    assert torch.equal(good, same) and bool(torch.isfinite(good).all())
+    labels[4] = 255                                                           # the ignore value / a mis-set num_classes
+    bad = Fn.matcher_cost(masks, tgt, prob, labels, 2.0, 5.0, 2.0)
+    assert bool(torch.isnan(bad[:, 4]).all()) and bool(torch.isfinite(bad[:, [0, 1, 2, 3, 5]]).all())
+    from scipy.optimize import linear_sum_assignment
+
+    with pytest.raises(ValueError):
+        linear_sum_assignment(bad.cpu())
+
+
+@pytest.mark.parametrize("n,d_out,normalize", [(1, 64, True), (777, 64, True), (20000, 64, True), (500, 16, False)])
+def test_fourier_posenc_matches_oracle(eng, n, d_out, normalize):
+    """us3d_fourier_posenc against the oracle's line-by-line restatement of models/position_embedding.py:12-40, 128-160 (which
+    the Mask3D golden pins to the unmodified reference file).  fp32: the projection is a 3-term dot product of values up to
+    2 pi, sin / cos of arguments up to ~20 -> absolute agreement 2e-6."""
+    from oracle import ops_cpu
+    from unscene3d_b200.engine import functional as Fn
+    from unscene3d_b200.models.position_embedding import PositionEmbeddingCoordsSine
+
+    torch.manual_seed(n)
+    xyz = (torch.rand(n, 3) * torch.tensor([5.0, 4.0, 2.4]) - torch.tensor([2.5, 2.0, 0.1]))
+    xyz = torch.floor(xyz / 0.02) * 0.02
+    mod = PositionEmbeddingCoordsSine(pos_type="fourier", d_pos=128, gauss_scale=1.0, normalize=normalize)
+    lo, hi = (xyz.min(0)[0], xyz.max(0)[0] + (1.0 if n == 1 else 0.0)) if normalize else (None, None)
+    want = ops_cpu.fourier_posenc(xyz, mod.gauss_B, d_out, lo, hi)
+    got = Fn.fourier_posenc(xyz.cuda(), mod.gauss_B.cuda(), d_out, None if lo is None else lo.cuda(), None if hi is None else hi.cuda())
+    assert got.shape == (n, 2 * d_out)
+    assert float((got.cpu() - want).abs().max()) < 2e-6
+    # module surface: [B, d_pos, N] like the reference, rows through encode_rows
+    m = mod.cuda()
+    full = m(xyz.cuda()[None], num_channels=2 * d_out, input_range=None if lo is None else [lo.cuda()[None], hi.cuda()[None]])
+    assert full.shape == (1, 2 * d_out, n) and torch.equal(full[0].permute(1, 0), got)
+
+
+def test_torch_scatter_shim_cpu_tensors_and_dim_size_validation(eng):
+    """torch_scatter.scatter_mean as the reference calls it: CUDA rows on the hot path (models/mask3d.py:223), CPU tensors in
+    the evaluation post-processing (trainer/trainer.py:449); an index tensor on another device is moved; an explicit dim_size
+    that the indices exceed raises like torch_scatter does."""
+    import torch_scatter  # the shim (unscene3d_b200/shims is on sys.path once the package is imported)
+    from oracle import ops_cpu
+
+    assert "unscene3d_b200" in torch_scatter.__file__
+    torch.manual_seed(2)
+    src = torch.randn(5000, 7)
+    idx = torch.randint(0, 40, (5000,))
+    idx[0] = 39
+    want = ops_cpu.scatter_mean(src, idx)
+    assert rel_err(torch_scatter.scatter_mean(src, idx, dim=0), want) < 1e-6          # CPU in, CPU out
+    got = torch_scatter.scatter_mean(src.cuda(), idx, dim=0)                            # CUDA rows, CPU index
+    assert got.is_cuda and rel_err(got, want) < 1e-5
+    big = torch_scatter.scatter_mean(src.cuda(), idx.cuda(), dim=0, dim_size=64)
+    assert big.shape == (64, 7) and float(big[40:].abs().max()) == 0.0
+    with pytest.raises(RuntimeError):
+        torch_scatter.scatter_mean(src.cuda(), idx.cuda(), dim=0, dim_size=10)
+
+
 def test_cpu_tensor_is_rejected_loudly(eng):
     with pytest.raises(RuntimeError):
         eng.SparseTensor(torch.zeros(3, 1), torch.zeros(3, 4, dtype=torch.int32))

@@ -86,7 +86,94 @@ def test_state_dict_and_outputs_identical_to_reference(cls):
         assert torch.equal(u.F, v.F) and torch.equal(u.C, v.C)
 
 
+def _backbone_step(net, me, f, c, w, dtype=torch.float32):
+    out, aux = net(me.SparseTensor(f.to(dtype), c))
+    (out.F * w.to(out.F)).mean().backward()
+    grads = {k: p.grad.detach().double().cpu().clone() for k, p in net.named_parameters() if p.grad is not None}
+    net.zero_grad(set_to_none=True)
+    return out.F.detach().double().cpu(), grads
+
+
+def test_relu_mask_flips_explain_the_gradient_tolerance_fp32_vs_fp64_oracle():
+    """Pins the argument behind the gradient tolerances: the SAME oracle run in fp32 and in fp64 (features agree to 1e-6)
+    disagrees on parameter gradients by far more than that, because a few near-zero pre-activations change sign; with the
+    fp32 run's ReLU masks replayed in the fp64 run the gradients agree at rounding level.  The CUDA tests use the same replay
+    to hold the gradients of the tensor-core path to 1e-3 (test_cuda_backbone_gradients_with_relu_masks_replayed)."""
+    from helpers import record_relu_masks, replay_relu_masks
+    from oracle import me_cpu
+
+    c = torch.from_numpy(random_scene(3000, 21, batch=2, extent=28))
+    torch.manual_seed(4)
+    f = torch.randn(c.shape[0], 3)
+    w = torch.linspace(-1, 1, 96)
+    R = our_models_on_oracle().res16unet
+    net32 = R.Res16UNet34C(3, 20, Cfg(), D=3, out_fpn=True)
+    st = deterministic_state(net32, 13)
+    net32.load_state_dict(st)
+    net64 = R.Res16UNet34C(3, 20, Cfg(), D=3, out_fpn=True).double()
+    net64.load_state_dict(st)
+    rel = lambda a, b: float((a - b).norm() / b.norm().clamp(min=1e-300))
+    with record_relu_masks(me_cpu) as masks:
+        o32, g32 = _backbone_step(net32, me_cpu, f, c, w)
+    net64.load_state_dict(st)
+    o64, g64 = _backbone_step(net64, me_cpu, f, c, w, torch.float64)
+    free = max(rel(g32[k], g64[k]) for k in g64)
+    flips = []
+    net64.load_state_dict(st)
+    with replay_relu_masks(me_cpu, masks, flips):
+        o64r, g64r = _backbone_step(net64, me_cpu, f, c, w, torch.float64)
+    replayed = max(rel(g32[k], g64r[k]) for k in g64r)
+    assert rel(o32, o64) < 1e-5
+    assert replayed < 1e-4, replayed
+    n_flip = sum(a for a, _ in flips)
+    if n_flip:  # the usual case: a handful of flipped decisions cost orders of magnitude in gradient agreement
+        assert free > 5 * replayed, (free, replayed, n_flip)
+
+
 # ------------------------------------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [3, 0])
+def test_cuda_backbone_gradients_with_relu_masks_replayed(mode):
+    """Whole-network backward at the north-star tolerance: the CUDA run (module-by-module route, which exposes every ReLU)
+    records its ReLU masks, the oracle replays them; features, loss and EVERY parameter gradient agree to 1e-3 in the
+    production arithmetic (mode 3, three-term bf16 split on tcgen05) and to 1e-4 with the exact-fp32 kernels (mode 0)."""
+    import unscene3d_b200  # noqa: F401
+    from helpers import record_relu_masks, replay_relu_masks
+    from oracle import me_cpu
+    from unscene3d_b200 import engine, models
+    from unscene3d_b200.engine import blocks
+    from unscene3d_b200.engine import functional as Fn
+
+    c = torch.from_numpy(random_scene(6000, 78, batch=2, extent=36))
+    torch.manual_seed(5)
+    f = torch.randn(c.shape[0], 3)
+    w = torch.linspace(-1, 1, 96)
+    cpu_net = our_models_on_oracle().res16unet.Res16UNet34C(3, 20, Cfg(), D=3, out_fpn=True)
+    st = deterministic_state(cpu_net, 12)
+    cpu_net.load_state_dict(st)
+    gpu_net = models.Res16UNet34C(3, 20, Cfg(), D=3, out_fpn=True)
+    gpu_net.load_state_dict(st)
+    gpu_net.cuda()
+    default_on = blocks._enabled["on"]
+    blocks.set_fused_blocks(False)
+    Fn.set_precision(mode)
+    try:
+        with record_relu_masks(engine) as masks:
+            og, gg = _backbone_step(gpu_net, engine, f.cuda(), c.cuda(), w)
+    finally:
+        blocks.set_fused_blocks(default_on)
+        Fn.set_precision(3)
+    flips = []
+    with replay_relu_masks(me_cpu, masks, flips):
+        oc, gc = _backbone_step(cpu_net, me_cpu, f, c, w)
+    rel = lambda a, b: float((a - b).norm() / b.norm().clamp(min=1e-300))
+    tol = 1e-3 if mode == 3 else 1e-4
+    assert rel(og, oc) < tol
+    assert gg.keys() == gc.keys()
+    worst_k, worst = max(((k, rel(gg[k], gc[k])) for k in gc), key=lambda kv: kv[1])
+    assert worst < tol, f"{worst_k}: {worst:.2e} (mode {mode}, {sum(a for a, _ in flips)} flipped ReLU decisions replayed)"
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", list(CASES))
 def test_cuda_backbone_matches_golden(name):

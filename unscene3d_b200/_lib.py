@@ -74,6 +74,7 @@ PROTOTYPES = {
     "us3d_pooled_mask_bits": [_p, _p, _p, _i, _p, _i, _p, _p],
     "us3d_mask_loss_fwd": [_p, _i, _i, _p, _i, _p, _p, _i, _p, _f, _p, _p, _p],
     "us3d_mask_loss_bwd": [_p, _i, _i, _p, _i, _p, _p, _i, _p, _f, _p, _p, _p, _p],
+    "us3d_fourier_posenc": [_p, _i, _i, _p, _p, _p, _i, _i, _p, _p],
     "us3d_matcher_cost": [_p, _i, _i, _p, _i, _p, _i, _p, _f, _f, _f, _p, _p],
 }
 _RESTYPE = {"us3d_last_error": ctypes.c_char_p, "us3d_launch_count": _ll, "us3d_reset_launch_count": None,

@@ -177,13 +177,45 @@ k_fps_cluster(const float *__restrict__ xyz, int n, int m, int lt, int smem_slot
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Fourier positional encoding (models/position_embedding.py:128-172, get_fourier_embeddings):
+//   t = (xyz - lo) / (hi - lo)   [normalize]     t *= 2 pi     proj = t . B[:, :d]     out = [sin(proj) | cos(proj)]
+// written row-major [n, 2 d] — the layout every consumer of the reference's [1, 2 d, n] tensor permutes it into
+// (models/mask3d.py:195-196, 238-240).  One thread per (row, frequency); same operation order as the reference (shift, scale,
+// divide, 2 pi, three-term dot product), accurate sinf / cosf.
+__global__ void __launch_bounds__(256)
+k_fourier_posenc(const float *__restrict__ xyz, int n, int ld, const float *__restrict__ lo, const float *__restrict__ hi,
+                 const float *__restrict__ gauss_b, int ldb, int d, float *__restrict__ out) {
+    const long long total = (long long)n * d;
+    const float two_pi = 6.283185307179586f;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(e / d), f = (int)(e - (long long)r * d);
+        float proj = 0.f;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            float t = xyz[(size_t)r * ld + a];
+            if (lo != nullptr) t = ((t - lo[a]) * 1.0f) / (hi[a] - lo[a]) + 0.0f;
+            t *= two_pi;
+            proj = fmaf(t, gauss_b[(size_t)a * ldb + f], proj);
+        }
+        float sn, cs;
+        sincosf(proj, &sn, &cs);
+        out[(size_t)r * (2 * d) + f] = sn;
+        out[(size_t)r * (2 * d) + d + f] = cs;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // torch_scatter.scatter_mean over rows
+// (rows whose index lies outside [0, n_seg) are skipped: the host side validates an explicit dim_size, the kernel never
+// writes out of bounds)
 __global__ void __launch_bounds__(256) k_segment_sum(const float *__restrict__ src, const int64_t *__restrict__ index, int n, int c,
-                                                     float *out, float *count) {
+                                                     int n_seg, float *out, float *count) {
     long long total = (long long)n * c;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         int r = (int)(e / c), ch = (int)(e % c);
-        int s = (int)index[r];
+        const int64_t s64 = index[r];
+        if (s64 < 0 || s64 >= n_seg) continue;
+        int s = (int)s64;
         atomicAdd(&out[(size_t)s * c + ch], src[e]);
         if (ch == 0) atomicAdd(&count[s], 1.f);
     }
@@ -201,11 +233,13 @@ __global__ void __launch_bounds__(256) k_segment_div(float *out, const float *__
 // sum is taken in fp64 (order-independent to 2^-53) and rounded to fp32 once — the result does not depend on the
 // order in which the atomics land.
 __global__ void __launch_bounds__(256) k_segment_sum_f64(const float *__restrict__ src, const int64_t *__restrict__ index, int n, int c,
-                                                         double *acc, float *count) {
+                                                         int n_seg, double *acc, float *count) {
     long long total = (long long)n * c;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         int r = (int)(e / c), ch = (int)(e % c);
-        int s = (int)index[r];
+        const int64_t s64 = index[r];
+        if (s64 < 0 || s64 >= n_seg) continue;
+        int s = (int)s64;
         atomicAdd(&acc[(size_t)s * c + ch], (double)src[e]);
         if (ch == 0) atomicAdd(&count[s], 1.f);
     }
@@ -264,7 +298,9 @@ k_matcher_cost(const float *__restrict__ logits, int S, int Q, const float *__re
         float c_mask = a[0] / (float)S;
         float c_dice = 1.f - (2.f * a[1] + 1.f) / (a[2] + a[3] + 1.f);
         int64_t lab = labels[t];
-        float c_class = lab == 253 ? -1.f : -prob[(size_t)q * ncls + (int)lab];
+        // a label outside [0, ncls) (other than the 253 "mask without class" the reference special-cases, models/matcher.py:
+        // 125-127) is an IndexError in the reference; here it poisons the cost so that the assignment solver rejects the matrix
+        float c_class = lab == 253 ? -1.f : ((lab < 0 || lab >= ncls) ? __int_as_float(0x7fc00000) : -prob[(size_t)q * ncls + (int)lab]);
         cost[(size_t)q * T + t] = w_mask * c_mask + w_class * c_class + w_dice * c_dice;
     }
 }
@@ -408,7 +444,7 @@ int us3d_segment_mean_fwd(const float *src, const int64_t *index, int n, int c, 
                           void *stream_) {
     US3D_CHECK_ARG(n >= 0 && c > 0 && s >= 0, "segment_mean: bad shape");
     if (n == 0 || s == 0) return 0;
-    k_segment_sum<<<flat_grid2((long long)n * c), 256, 0, (cudaStream_t)stream_>>>(src, index, n, c, out, count);
+    k_segment_sum<<<flat_grid2((long long)n * c), 256, 0, (cudaStream_t)stream_>>>(src, index, n, c, s, out, count);
     US3D_LAUNCH_CHECK();
     k_segment_div<<<flat_grid2((long long)s * c), 256, 0, (cudaStream_t)stream_>>>(out, count, s, c);
     US3D_LAUNCH_CHECK();
@@ -420,7 +456,7 @@ int us3d_segment_mean_f64(const float *src, const int64_t *index, int n, int c, 
     US3D_CHECK_ARG(n >= 0 && c > 0 && s >= 0, "segment_mean_f64: bad shape");
     if (s == 0) return 0;
     if (n > 0) {
-        k_segment_sum_f64<<<flat_grid2((long long)n * c), 256, 0, (cudaStream_t)stream_>>>(src, index, n, c, acc, count);
+        k_segment_sum_f64<<<flat_grid2((long long)n * c), 256, 0, (cudaStream_t)stream_>>>(src, index, n, c, s, acc, count);
         US3D_LAUNCH_CHECK();
     }
     k_segment_div_f64<<<flat_grid2((long long)s * c), 256, 0, (cudaStream_t)stream_>>>(acc, count, s, c, out);
@@ -433,6 +469,16 @@ int us3d_segment_mean_bwd(const float *dout, const int64_t *index, const float *
     US3D_CHECK_ARG(n >= 0 && c > 0, "segment_mean_bwd: bad shape");
     if (n == 0) return 0;
     k_segment_mean_bwd<<<flat_grid2((long long)n * c), 256, 0, (cudaStream_t)stream_>>>(dout, index, count, n, c, dsrc);
+    US3D_LAUNCH_CHECK();
+    return 0;
+}
+
+int us3d_fourier_posenc(const float *xyz, int n, int ld, const float *lo, const float *hi, const float *gauss_b, int ldb,
+                        int d_out, float *out, void *stream_) {
+    US3D_CHECK_ARG(n >= 0 && ld >= 3 && d_out > 0 && ldb >= d_out, "fourier_posenc: bad shape");
+    US3D_CHECK_ARG((lo == nullptr) == (hi == nullptr), "fourier_posenc: lo and hi come together");
+    if (n == 0) return 0;
+    k_fourier_posenc<<<flat_grid2((long long)n * d_out), 256, 0, (cudaStream_t)stream_>>>(xyz, n, ld, lo, hi, gauss_b, ldb, d_out, out);
     US3D_LAUNCH_CHECK();
     return 0;
 }

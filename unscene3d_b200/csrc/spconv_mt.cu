@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
         const uint64_t a_desc0 = desc_k_sw128(a_base), b_desc0 = desc_k_sw128(b_base);
         int as = 0, bs = 0, siter = 0, item = 0, bitem = 0;
         uint32_t apar = 0, bpar = 0;
-        long long w_acc = 0, w_b = 0, w_a = 0;
+        long long w_acc = 0, w_b = 0, w_a = 0, t_first = 0;
         const long long t_begin = clock64();
         for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++siter) {
             const int st = u / p.ksplit;
@@ -300,6 +300,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
                         long long tw2 = clock64();
                         mbar_wait(smem_u32(&a_full[as]), apar, 4);
                         w_a += clock64() - tw2;
+                        if (item == 0) t_first = clock64() - t_begin;
                         if (LAG == 0) fence_proxy_async();  // cp.async writes (generic proxy) -> tcgen05 reads (async proxy)
                         tc_fence_after();
                         const uint64_t da_hi = a_desc0 + (uint64_t)((uint32_t)(as * A_SLOT) >> 4);
@@ -355,6 +356,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
             o[3] = w_a;
             o[4] = item;
             o[5] = bitem;
+            o[6] = t_first;  // cycles until the first gathered tile has landed (prologue + one index + one gather round trip)
         }
     } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + 4) {
         // ------------------------------------------------------------------ epilogue

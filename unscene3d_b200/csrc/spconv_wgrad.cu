@@ -316,11 +316,13 @@ int us3d_spconv_wgrad_planes(const void *x_hi, const void *x_lo, const void *dy_
     if (p.a_slots > wg::MAX_A) p.a_slots = wg::MAX_A;
     US3D_CHECK_ARG(p.a_slots >= 2, "spconv_wgrad_planes: operand slots do not fit in shared memory (cout %d)", cout);
     const size_t smem = (size_t)p.a_slots * a_slot + (size_t)p.b_slots * b_slot + 1024;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[64] = {};  // the opt-in for > 48 KB of dynamic shared memory is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_done[dev]) {
         US3D_CUDA(cudaFuncSetAttribute(wg::k_wgrad<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
         US3D_CUDA(cudaFuncSetAttribute(wg::k_wgrad<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-        attr_done = true;
+        attr_done[dev] = true;
     }
     const int grid = p.ngroups * p.mblks * p.splits;
     {

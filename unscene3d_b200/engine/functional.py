@@ -605,8 +605,9 @@ class SegmentMeanFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, src, index, num_segments):
         src = _rows(src).contiguous()
-        index = index.contiguous().long()
+        index = index.to(src.device).contiguous().long()
         n, c = src.shape
+        assert index.shape[0] == n, f"scatter_mean: {index.shape[0]} indices for {n} rows"
         out = torch.zeros((num_segments, c), dtype=torch.float32, device=src.device)
         count = torch.zeros(num_segments, dtype=torch.float32, device=src.device)
         check(lib.us3d_segment_mean_fwd(src.data_ptr(), index.data_ptr(), n, c, num_segments, out.data_ptr(), count.data_ptr(), _stream()))
@@ -635,12 +636,27 @@ def furthest_point_sampling(xyz: torch.Tensor, nsamples: int) -> torch.Tensor:
     return idx
 
 
+def fourier_posenc(xyz, gauss_b, d_out, lo=None, hi=None):
+    """[sin | cos](2 pi normalise(xyz) . gauss_B[:, :d_out]) as [n, 2 d_out] rows (models/position_embedding.py:128-172)."""
+    if not xyz.is_cuda:
+        raise RuntimeError("unscene3d_b200 operators run on CUDA tensors only (no CPU fallback)")
+    xyz = _rows(xyz)
+    gb = gauss_b if (gauss_b.dtype == torch.float32 and gauss_b.stride(1) == 1) else gauss_b.float().contiguous()
+    n = xyz.shape[0]
+    out = torch.empty((n, 2 * d_out), dtype=torch.float32, device=xyz.device)
+    if lo is not None:
+        lo, hi = lo.reshape(-1).float().contiguous(), hi.reshape(-1).float().contiguous()
+    check(lib.us3d_fourier_posenc(xyz.data_ptr(), n, _ld(xyz), _ptr(lo), _ptr(hi), gb.data_ptr(), gb.stride(0), int(d_out),
+                                  out.data_ptr(), _stream()))
+    return out
+
+
 def matcher_cost(logits_sq, tgt_ts, prob_qc, labels_t, w_class, w_mask, w_dice):
     """Cost matrix [Q, T] of models/matcher.py:97-168 for one scene."""
     logits_sq = _rows(logits_sq).contiguous()
     tgt_ts = _rows(tgt_ts).contiguous()
     prob_qc = _rows(prob_qc).contiguous()
-    labels_t = labels_t.contiguous().long()
+    labels_t = labels_t.to(logits_sq.device).contiguous().long()  # the reference indexes with CPU or CUDA labels alike
     S, Q = logits_sq.shape
     T = tgt_ts.shape[0]
     cost = torch.empty((Q, T), dtype=torch.float32, device=logits_sq.device)
