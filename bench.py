@@ -309,12 +309,16 @@ def run_ours(args):
         # one GPU and 12 ms/step at two, on this launch-heavy step).  The clocks are therefore sampled once at the middle
         # of the timed steps and twice more right after the closing event has been queued, while the device is still
         # working through the launches the host has queued ahead — inside the timed region, off its critical path.
+        host = []
         for i in range(steps):
+            th = time.perf_counter()
             flush.zero_()
             fn()
             if sampler is not None and i + 1 == max(steps // 2, 1):
                 sampler.sample()
+            host.append((time.perf_counter() - th) * 1e3)
         e.record()
+        host_ms[fn.__name__] = host
         if sampler is not None:
             sampler.sample()
             sampler.sample()
@@ -324,6 +328,8 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), t0, t1
+
+    host_ms = {}  # host-side duration of every timed step (queueing only): an outlier here is a host stall, not device time
 
     def step_resident():
         step(c4_dev, f_dev)
@@ -506,6 +512,8 @@ def run_ours(args):
             "dtype": DTYPE, "data": "synthetic",
             "config": bench_config(args.voxels, world),
             "prime_steps": n_prime,
+            "host_ms_per_step": {k: {"median": float(np.median(v)), "max": float(np.max(v)), "argmax": int(np.argmax(v))}
+                                 for k, v in host_ms.items()},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(c4_host.numel() * 4 + f_host.numel() * 4),
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_wgrad": roofline_wgrad,

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define US3D_ABI_VERSION 14
+#define US3D_ABI_VERSION 15
 #define US3D_MAX_KVOL 27
 
 int us3d_abi_version(void);
@@ -77,53 +77,47 @@ int us3d_spconv_gather(const float *x, int ldx, const int32_t *nbr, int n_rows, 
                        int cout, int transpose_w, int flip_k, const float *bias, const int32_t *out_rows, float *y,
                        int ldy, int accumulate, const uint32_t *tile_mask, void *stream);
 
-/* Tensor-core (tcgen05 + TMEM) variant of us3d_spconv_gather for cin, cout multiples of 16, cout <= 256.
+/* Tensor-core (tcgen05 + TMEM) path for cin, cout multiples of 16, cout <= 256.
  *   passes = 1: bf16 x bf16 -> fp32;  passes = 3: three-term bf16 split (hi·hi + lo·hi + hi·lo), fp32-faithful.
- *   wpack: weights pre-packed by us3d_spconv_pack_weights into bf16 planes laid out as the swizzled
- *   shared-memory image of every (offset, 64-channel chunk) slab; us3d_spconv_packed_bytes gives its size.
+ *   wpack: weights pre-packed into bf16 planes laid out as the swizzled shared-memory image of every (offset,
+ *   64-channel chunk) slab [W_hi rows | W_lo rows]; us3d_spconv_packed_bytes gives its size.
  *   pack_weights(transpose=1, flip_k) produces the slabs of the input-gradient pass (W[kk]^T), in which case
- *   the GEMM runs with cin' = cout, cout' = cin.                                                    */
+ *   the GEMM runs with cin' = cout, cout' = cin.  (us3d_spconv_pack_pair / _pack_many below build the images of one /
+ *   of all convolutions of a network in one launch.)                                               */
 int us3d_spconv_tc_supported(int cin, int cout);
 long long us3d_spconv_packed_bytes(int kvol, int kdim, int ndim, int passes);
 int us3d_spconv_pack_weights(const float *w, int kvol, int cin, int cout, int transpose, int flip_k, int passes,
                              void *out, void *stream);
-int us3d_spconv_gather_tc(const float *x, int ldx, const int32_t *nbr, int n_rows, int kvol, const void *wpack, int cin,
-                          int cout, int passes, const float *bias, const int32_t *out_rows, float *y, int ldy,
-                          int accumulate, const uint32_t *tile_mask, void *stream);
 
 /* Weight gradient of the same map:  dW[k] += sum_j X[nbr[k*n_rows+j]]^T · dY[orow(j)]   ([kvol,cin,cout]).
- * dW must be zero-initialised (or hold the value to accumulate into) by the caller.             */
+ * dW must be zero-initialised (or hold the value to accumulate into) by the caller.  Exact-fp32 SIMT kernel. */
 int us3d_spconv_wgrad(const float *x, int ldx, const int32_t *nbr, int n_rows, int kvol, const float *dy, int ldy,
                       const int32_t *out_rows, float *dw, int cin, int cout, void *stream);
 
-/* TMA-fed variant (the default data path): the activation rows are consumed as bf16 planes — hi, and
- * lo = x - hi for passes == 3 — row-major [n_in, cin], produced by us3d_split_bf16.  One producer warp gathers
- * the neighbour rows with cp.async.bulk.tensor ... tile::gather4 (absent neighbours = row -1 = hardware zero
- * fill) straight into the swizzled operand buffers; persistent CTAs, two TMEM accumulators so a tile's
- * epilogue overlaps the next tile's main loop.  Same contract as us3d_spconv_gather_tc otherwise.           */
+/* fp32 rows -> bf16 planes hi (and lo = x - hi when lo != NULL), row-major [n, c], c % 8 == 0: the operand form of the
+ * tensor-core kernels.  Activations get their planes from the pass that produces them (us3d_bn_apply_planes,
+ * us3d_bn_backward_planes); this entry point is for tensors that come from elsewhere.                       */
 int us3d_split_bf16(const float *x, int ldx, int n, int c, void *hi, void *lo, void *stream);
-int us3d_spconv_gather_tma(const void *x_hi, const void *x_lo, int n_in, const int32_t *nbr, int n_rows, int kvol,
-                           const void *wpack, int cin, int cout, int passes, const float *bias, const int32_t *out_rows,
-                           float *y, int ldy, int accumulate, const uint32_t *tile_mask, void *stream);
-/* Same pipeline with the row gather done by 16-byte cp.async (LDGSTS) from four producer warps; measured an
- * order of magnitude faster than tile::gather4 for 128-byte rows, hence the default.                      */
-int us3d_spconv_gather_cp(const void *x_hi, const void *x_lo, int n_in, const int32_t *nbr, int n_rows, int kvol,
-                          const void *wpack, int cin, int cout, int passes, const float *bias, const int32_t *out_rows,
-                          float *y, int ldy, int accumulate, const uint32_t *tile_mask, void *stream);
 
-/* Production kernel: as us3d_spconv_gather_cp, but T = 512 / acc_cols (<= 4) output tiles share every weight
- * slab (one TMEM accumulator each), which removes the dominant L2 -> SM stream (weights re-read per tile).    */
+/* Production forward / input-gradient kernel (csrc/spconv_mt.cu): the activation rows are consumed as bf16 planes [n_in, cin];
+ * neighbour rows are gathered with 16-byte cp.async into K-major SWIZZLE_128B slots (indices streamed ahead through a
+ * shared-memory ring), up to T = 512 / acc_cols output tiles share every weight slab (one TMEM accumulator each), products
+ * on tcgen05.  Work decomposition: every CTA owns a contiguous range of output tiles — `partition` (may be NULL; int32
+ * [us3d_spconv_partition_size()], from us3d_spconv_partition on the table's tile masks) makes the ranges equal in cost
+ * rather than in count — or, on small maps, the offsets of a tile are dealt to several CTAs whose partial tiles meet in a
+ * caller-provided workspace.  out_rows (may be NULL): table column j writes row out_rows[j] (pattern-ordered tables).      */
 int us3d_spconv_gather_mt(const void *x_hi, const void *x_lo, int n_in, const int32_t *nbr, int n_rows, int kvol,
                           const void *wpack, int cin, int cout, int passes, const float *bias, const int32_t *out_rows,
-                          float *y, int ldy, int accumulate, const uint32_t *tile_mask, void *stream);
+                          float *y, int ldy, int accumulate, const uint32_t *tile_mask, const int32_t *partition,
+                          void *workspace, long long workspace_bytes, void *stream);
+/* workspace (may be NULL; 16-byte aligned, contents irrelevant): room for the partial tiles of the split mode,
+ * [parts][n_rows][cout] fp32, summed in part order by a second launch (no atomics: results are bit-reproducible).
+ * us3d_spconv_gather_mt_workspace_bytes = the most the launcher can use for a map (0: it would not split).             */
+long long us3d_spconv_gather_mt_workspace_bytes(int n_rows, int kvol, int cout);
+int us3d_spconv_partition_size(void);
+int us3d_spconv_partition(const uint32_t *tile_mask, int n_tiles, int kvol, int32_t *partition, void *stream);
 
-/* Tensor-core weight gradient (cin, cout multiples of 8, cout <= 256): D[ci, co] accumulates in TMEM over the rows
- * of one (offset, 128-input-channel block, row split); both operands are MN-major SWIZZLE_128B tiles built from
- * the fp32 rows with the same bf16 split as the forward kernel; partial tiles are reduced into dW with atomics. */
 int us3d_spconv_wgrad_tc_supported(int cin, int cout);
-int us3d_spconv_wgrad_tc(const float *x, int ldx, const int32_t *nbr, int n_rows, int kvol, const float *dy, int ldy,
-                         const int32_t *out_rows, float *dw, int cin, int cout, int passes, const uint32_t *tile_mask,
-                         void *stream);
 
 /* Production weight-gradient kernel: operands from the bf16 planes of X and dY via cp.async; one CTA handles up
  * to 4 kernel offsets per dY tile (one TMEM accumulator each), so dY is streamed ceil(kvol/4) times, not kvol. */

@@ -36,7 +36,7 @@ for nvox in (2000, 200_000):
     from unscene3d_b200._lib import lib, check
     st = Fn._stream()
     bench("raw us3d_spconv_gather_mt", lambda: lib.us3d_spconv_gather_mt(hi.data_ptr(), lo.data_ptr(), s.n, table.nbr.data_ptr(), table.n_rows, 27,
-                                                       wp.data_ptr(), cin, cout, 3, 0, 0, y.data_ptr(), cout, 0, table.mask.data_ptr(), st))
+                                                       wp.data_ptr(), cin, cout, 3, 0, 0, y.data_ptr(), cout, 0, table.mask.data_ptr(), 0, 0, 0, st))
     bench("Fn.spconv_gather", lambda: Fn.spconv_gather(x, table, w, cin, cout, False, False))
     bench("Fn.pack_weights", lambda: Fn.pack_weights(w, False, False, 3))
     bench("Fn.spconv_wgrad", lambda: Fn.spconv_wgrad(x, table, dy, cin, cout))
@@ -68,7 +68,7 @@ st = Fn._stream()
 def call(c):
     hi, lo, n, t, wp, cin, cout, y, x, w = c
     lib.us3d_spconv_gather_mt(hi.data_ptr(), lo.data_ptr(), n, t.nbr.data_ptr(), t.n_rows, 27, wp.data_ptr(), cin, cout, 3, 0, 0,
-                              y.data_ptr(), cout, 0, t.mask.data_ptr(), st)
+                              y.data_ptr(), cout, 0, t.mask.data_ptr(), 0, 0, 0, st)
 
 
 for c in cfgs:

@@ -9,10 +9,11 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, "include", "us3d.h")
+DEBUG_HEADER = os.path.join(ROOT, "include", "us3d_debug.h")
 
 
-def header_functions():
-    src = open(HEADER).read()
+def header_functions(path=HEADER):
+    src = open(path).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(us3d_[a-z0-9_]+)\s*\(", src)))
 
@@ -26,6 +27,21 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(raw, name), f"{name} declared in include/us3d.h but not exported by libus3d.so"
     assert sorted(_lib.PROTOTYPES) == declared, "ctypes prototypes and header disagree"
+
+
+def test_library_exports_nothing_that_is_not_declared():
+    """The converse: every us3d_* symbol the shared library exports is declared — in include/us3d.h (the drop-in surface) or in
+    include/us3d_debug.h (profiling / tuning hooks, which the product's operator path does not call)."""
+    import subprocess
+
+    from unscene3d_b200 import _lib
+
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = sorted({line.split()[-1] for line in out.splitlines() if line.split() and line.split()[-1].startswith("us3d_")})
+    declared = set(header_functions()) | set(header_functions(DEBUG_HEADER))
+    assert not [n for n in exported if n not in declared], [n for n in exported if n not in declared]
+    assert all(n.startswith("us3d_debug_") for n in header_functions(DEBUG_HEADER))
+    assert not [n for n in header_functions(DEBUG_HEADER) if n not in exported]
 
 
 def test_abi_version_matches_header():

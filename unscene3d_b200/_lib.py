@@ -23,13 +23,12 @@ PROTOTYPES = {
     "us3d_spconv_tc_supported": [_i, _i],
     "us3d_spconv_packed_bytes": [_i, _i, _i, _i],
     "us3d_spconv_pack_weights": [_p, _i, _i, _i, _i, _i, _i, _p, _p],
-    "us3d_spconv_gather_tc": [_p, _i, _p, _i, _i, _p, _i, _i, _i, _p, _p, _p, _i, _i, _p, _p],
     "us3d_split_bf16": [_p, _i, _i, _i, _p, _p, _p],
-    "us3d_spconv_gather_tma": [_p, _p, _i, _p, _i, _i, _p, _i, _i, _i, _p, _p, _p, _i, _i, _p, _p],
-    "us3d_spconv_gather_cp": [_p, _p, _i, _p, _i, _i, _p, _i, _i, _i, _p, _p, _p, _i, _i, _p, _p],
-    "us3d_spconv_gather_mt": [_p, _p, _i, _p, _i, _i, _p, _i, _i, _i, _p, _p, _p, _i, _i, _p, _p],
+    "us3d_spconv_gather_mt": [_p, _p, _i, _p, _i, _i, _p, _i, _i, _i, _p, _p, _p, _i, _i, _p, _p, _p, _ll, _p],
+    "us3d_spconv_gather_mt_workspace_bytes": [_i, _i, _i],
+    "us3d_spconv_partition_size": [],
+    "us3d_spconv_partition": [_p, _i, _i, _p, _p],
     "us3d_spconv_wgrad_tc_supported": [_i, _i],
-    "us3d_spconv_wgrad_tc": [_p, _i, _p, _i, _i, _p, _i, _p, _p, _i, _i, _i, _p, _p],
     "us3d_spconv_wgrad_planes": [_p, _p, _p, _p, _p, _i, _i, _p, _i, _i, _i, _p, _p, _p],
     "us3d_permute_planes": [_p, _p, _p, _i, _i, _p, _p, _p],
     "us3d_neighbour_pattern_keys": [_p, _i, _i, _p, _p, _p],
@@ -78,7 +77,8 @@ PROTOTYPES = {
     "us3d_matcher_cost": [_p, _i, _i, _p, _i, _p, _i, _p, _f, _f, _f, _p, _p],
 }
 _RESTYPE = {"us3d_last_error": ctypes.c_char_p, "us3d_launch_count": _ll, "us3d_reset_launch_count": None,
-            "us3d_spconv_packed_bytes": _ll, "us3d_xattn_workspace_bytes": _ll}
+            "us3d_spconv_packed_bytes": _ll, "us3d_xattn_workspace_bytes": _ll,
+            "us3d_spconv_gather_mt_workspace_bytes": _ll}
 
 
 def _load():

@@ -444,6 +444,21 @@ __global__ void __launch_bounds__(256) k_pack_many(const PackItem *__restrict__ 
     }
 }
 
+// fp32 rows -> bf16 hi plane (+ lo plane = x - hi), row-major [n, c], c % 8 == 0 — only for tensors that come from outside the
+// fused passes (network input, loss gradient): activations get their planes from the pass that produces them.
+__global__ void __launch_bounds__(256) k_split_bf16(const float *__restrict__ x, int ldx, int n, int c, uint4 *__restrict__ hi,
+                                                    uint4 *__restrict__ lo) {
+    const int g = c / 8;
+    const long long total = (long long)n * g;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(e / g), q = (int)(e % g);
+        const float4 *src = reinterpret_cast<const float4 *>(x + (size_t)r * ldx + q * 8);
+        const float4 a = __ldg(src), b = __ldg(src + 1);
+        const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        store_planes(f, hi, lo, (size_t)e);
+    }
+}
+
 static inline int flat_grid(long long work) {
     long long b = (work + 255) / 256;
     long long cap = (long long)num_sms() * 16;
@@ -511,6 +526,36 @@ int us3d_bn_backward_planes(const float *dy, int lddy, const float *x, int ldx, 
             nullptr);
     US3D_LAUNCH_CHECK();
     return 0;
+}
+
+long long us3d_spconv_packed_bytes(int kvol, int kdim, int ndim, int passes) {
+    return (long long)kvol * ceil_div(kdim, 64) * (passes == 3 ? 2 : 1) * ndim * 128;
+}
+
+int us3d_spconv_tc_supported(int cin, int cout) {
+    return cin >= 16 && cin % 16 == 0 && cout >= 16 && cout % 16 == 0 && cout <= 256;
+}
+
+int us3d_spconv_wgrad_tc_supported(int cin, int cout) { return cin >= 8 && cin % 8 == 0 && cout >= 16 && cout % 16 == 0 && cout <= 256; }
+
+int us3d_split_bf16(const float *x, int ldx, int n, int c, void *hi, void *lo, void *stream_) {
+    US3D_CHECK_ARG(n >= 0 && c > 0 && c % 8 == 0 && ldx % 4 == 0 && ldx >= c, "split_bf16: need c %% 8 == 0 and ldx %% 4 == 0");
+    US3D_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0, "split_bf16: x must be 16-byte aligned");
+    if (n == 0) return 0;
+    fused::k_split_bf16<<<fused::flat_grid((long long)n * (c / 8)), 256, 0, (cudaStream_t)stream_>>>(x, ldx, n, c, (uint4 *)hi, (uint4 *)lo);
+    US3D_LAUNCH_CHECK();
+    return 0;
+}
+
+/* one image: forward (transpose = 0) or input-gradient (transpose = 1, optionally with the offsets flipped) */
+int us3d_spconv_pack_weights(const float *w, int kvol, int cin, int cout, int transpose, int flip_k, int passes, void *out,
+                             void *stream_) {
+    US3D_CHECK_ARG(kvol >= 1 && kvol <= US3D_MAX_KVOL, "pack_weights: kvol %d out of range", kvol);
+    US3D_CHECK_ARG(passes == 1 || passes == 3, "pack_weights: passes must be 1 or 3");
+    if (transpose)
+        return us3d_spconv_pack_pair(w, kvol, cin, cout, flip_k, passes, nullptr, out, stream_);
+    US3D_CHECK_ARG(flip_k == 0, "pack_weights: flipped offsets belong to the input-gradient image");
+    return us3d_spconv_pack_pair(w, kvol, cin, cout, 0, passes, out, nullptr, stream_);
 }
 
 int us3d_spconv_pack_pair(const float *w, int kvol, int cin, int cout, int flip_dgrad, int passes, void *out_fwd, void *out_dgrad,

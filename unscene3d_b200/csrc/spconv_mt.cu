@@ -59,7 +59,9 @@ struct Params {
     int ldy, accumulate;
     const uint32_t *tile_mask;
     int a_slots, b_slots, b_plane, acc_cols;
-    int ksplit, n_units;                  // small maps: the offsets of a super-tile are dealt to `ksplit` CTAs
+    float *ws;                            // split mode: partial tiles [ksplit][n_rows][cout]
+    const int32_t *part;                  // range mode: tiles [part[b], part[b + 1]) belong to CTA b (NULL: equal counts)
+    int ksplit, n_units;                  // small maps: the offsets of a tile are dealt to `ksplit` CTAs (T == 1)
     uint32_t part_mask[US3D_MAX_KVOL];    // offsets handled by part q (k % ksplit == q)
     long long *prof;  // optional per-CTA wait-cycle counters of the MMA thread (debug)
 };
@@ -81,6 +83,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
     const int b_slot_bytes = NPL * p.b_plane;
     const uint32_t all_k = p.kvol >= 32 ? 0xFFFFFFFFu : ((1u << p.kvol) - 1u);
     const int T = p.T;
+    uint32_t tmem_cols = 32;  // tcgen05.alloc takes a power of two >= 32 (T = 3 accumulators of 128 columns -> 512)
+    while (tmem_cols < (uint32_t)(T * p.acc_cols)) tmem_cols <<= 1;
 
     if (tid == 0) {
         for (int s = 0; s < p.a_slots; ++s) {
@@ -99,7 +103,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
         mbar_init(smem_u32(&acc_empty), 4);
         mbar_fence_init();
     }
-    if (warp == MMA_WARP) tmem_alloc(&tmem_base_s, (uint32_t)(T * p.acc_cols));
+    if (warp == MMA_WARP) tmem_alloc(&tmem_base_s, tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -108,6 +112,36 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
     auto tile_kmask = [&](int tile, uint32_t pm) -> uint32_t {
         if (tile >= p.n_tiles) return 0u;
         return (p.tile_mask ? (p.tile_mask[tile] & all_k) : all_k) & pm;
+    };
+
+    // Work of this CTA.  Range mode (ksplit == 1): a contiguous range of output tiles — equal cost per CTA when the caller
+    // supplies a partition (cost of a tile = its active offsets), equal counts otherwise — walked in groups of up to T tiles
+    // that share every weight slab.  Split mode (small maps): unit u = (tile u / ksplit, offsets k % ksplit == u % ksplit),
+    // dealt round-robin; partial sums meet in y through vector reds.
+    int r_begin = 0, r_end = 0;
+    if (p.ksplit == 1) {
+        if (p.part != nullptr) {
+            r_begin = p.part[blockIdx.x];
+            r_end = p.part[blockIdx.x + 1];
+        } else {
+            r_begin = (int)((long long)blockIdx.x * p.n_tiles / gridDim.x);
+            r_end = (int)((long long)(blockIdx.x + 1) * p.n_tiles / gridDim.x);
+        }
+    }
+    auto unit = [&](int i, int &tile0, int &nt, uint32_t &pm) -> bool {
+        if (p.ksplit == 1) {
+            tile0 = r_begin + i * T;
+            if (tile0 >= r_end) return false;
+            nt = min(T, r_end - tile0);
+            pm = 0xFFFFFFFFu;
+            return true;
+        }
+        const int u = blockIdx.x + i * gridDim.x;
+        if (u >= p.n_units) return false;
+        tile0 = u / p.ksplit;
+        nt = 1;
+        pm = p.part_mask[u - tile0 * p.ksplit];
+        return true;
     };
 
     if (warp < PROD_WARPS) {
@@ -122,13 +156,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
         uint32_t ppar = 0;
         int is = 0;          // index-ring stage of the current (super-tile, offset)
         uint32_t ipar = 0;
-        for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
-            const int st = u / p.ksplit;
-            const uint32_t pm = p.part_mask[u - st * p.ksplit];
+        int tile0, nt;
+        uint32_t pm;
+        for (int ui = 0; unit(ui, tile0, nt, pm); ++ui) {
             uint32_t m[MAX_T], U = 0;
 #pragma unroll
             for (int t = 0; t < MAX_T; ++t) {
-                m[t] = t < T ? tile_kmask(st * T + t, pm) : 0u;
+                m[t] = t < nt ? tile_kmask(tile0 + t, pm) : 0u;
                 U |= m[t];
             }
             for (int k = 0; k < p.kvol; ++k) {
@@ -140,12 +174,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
 #pragma unroll
                     for (int t = 0; t < MAX_T; ++t) {
                         if (!((m[t] >> k) & 1u)) continue;
-                        const int tile0 = (st * T + t) * M;
+                        const int row0 = (tile0 + t) * M;
                         int idx[RPT];
 #pragma unroll
                         for (int i = 0; i < RPT; ++i) {
                             const int r = rbase + 16 * i;
-                            idx[i] = tile0 + r < p.n_rows ? idx_ring[is][t][r] : -1;
+                            idx[i] = row0 + r < p.n_rows ? idx_ring[is][t][r] : -1;
                         }
                         mbar_wait(smem_u32(&a_empty[ps]), ppar ^ 1, 0);
                         const uint32_t slot = a_base + (uint32_t)ps * A_SLOT;
@@ -201,13 +235,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
         // waits for a load.  Rows past the map and tiles without the offset are never read by the producers.
         int is = 0;
         uint32_t ipar = 0;
-        for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
-            const int st = u / p.ksplit;
-            const uint32_t pm = p.part_mask[u - st * p.ksplit];
+        int tile0, nt;
+        uint32_t pm;
+        for (int ui = 0; unit(ui, tile0, nt, pm); ++ui) {
             uint32_t m[MAX_T], U = 0;
 #pragma unroll
             for (int t = 0; t < MAX_T; ++t) {
-                m[t] = t < T ? tile_kmask(st * T + t, pm) : 0u;
+                m[t] = t < nt ? tile_kmask(tile0 + t, pm) : 0u;
                 U |= m[t];
             }
             for (int k = 0; k < p.kvol; ++k) {
@@ -217,12 +251,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
 #pragma unroll
                 for (int t = 0; t < MAX_T; ++t) {
                     if (!((m[t] >> k) & 1u)) continue;
-                    const int tile0 = (st * T + t) * M;
+                    const int row0 = (tile0 + t) * M;
 #pragma unroll
                     for (int q = 0; q < M / 32; ++q) {
                         const int r = lane + 32 * q;
-                        const bool ok = tile0 + r < p.n_rows;
-                        cp_async4(smem_u32(&idx_ring[is][t][r]), src_k + (ok ? tile0 + r : 0), ok ? 4u : 0u);
+                        const bool ok = row0 + r < p.n_rows;
+                        cp_async4(smem_u32(&idx_ring[is][t][r]), src_k + (ok ? row0 + r : 0), ok ? 4u : 0u);
                     }
                 }
                 cp_async_arrive_noinc(smem_u32(&idx_full[is]));
@@ -237,11 +271,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
         // ------------------------------------------------------------------ weight slabs
         if (lane == 0) {
             int bitem = 0;
-            for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
-                const int st = u / p.ksplit;
-                const uint32_t pm = p.part_mask[u - st * p.ksplit];
+            int tile0, nt;
+            uint32_t pm;
+            for (int ui = 0; unit(ui, tile0, nt, pm); ++ui) {
                 uint32_t U = 0;
-                for (int t = 0; t < T; ++t) U |= tile_kmask(st * T + t, pm);
+                for (int t = 0; t < nt; ++t) U |= tile_kmask(tile0 + t, pm);
                 for (int k = 0; k < p.kvol; ++k) {
                     if (!((U >> k) & 1u)) continue;
                     for (int c = 0; c < p.nchunks; ++c, ++bitem) {
@@ -271,13 +305,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
         uint32_t apar = 0, bpar = 0;
         long long w_acc = 0, w_b = 0, w_a = 0, t_first = 0;
         const long long t_begin = clock64();
-        for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++siter) {
-            const int st = u / p.ksplit;
-            const uint32_t pm = p.part_mask[u - st * p.ksplit];
+        int tile0, nt;
+        uint32_t pm;
+        for (int ui = 0; unit(ui, tile0, nt, pm); ++ui, ++siter) {
             uint32_t m[MAX_T], U = 0;
 #pragma unroll
             for (int t = 0; t < MAX_T; ++t) {
-                m[t] = t < T ? tile_kmask(st * T + t, pm) : 0u;
+                m[t] = t < nt ? tile_kmask(tile0 + t, pm) : 0u;
                 U |= m[t];
             }
             long long tw0 = clock64();
@@ -363,22 +397,23 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
         const int quarter = warp & 3;
         const bool vec = (p.ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
         int siter = 0;
-        const bool split = p.ksplit > 1;  // partial sums of the offset parts meet in y through vector reds (y pre-zeroed)
-        for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++siter) {
-            const int st = u / p.ksplit;
-            const int part = u - st * p.ksplit;
-            const uint32_t pm = p.part_mask[part];
+        const bool split = p.ksplit > 1;  // the offset parts write partial tiles to the workspace; k_reduce_parts sums them
+        int tile0, nt;
+        uint32_t pm;
+        for (int ui = 0; unit(ui, tile0, nt, pm); ++ui, ++siter) {
+            const int part = p.ksplit == 1 ? 0 : (blockIdx.x + ui * gridDim.x) % p.ksplit;
             mbar_wait(smem_u32(&acc_full), siter & 1, 5);
             tc_fence_after();
-            for (int t = 0; t < T; ++t) {
-                const int tile = st * T + t;
+            for (int t = 0; t < nt; ++t) {
+                const int tile = tile0 + t;
                 if (tile >= p.n_tiles) break;
                 const bool has_acc = tile_kmask(tile, pm) != 0;
-                if (split && !has_acc && !(p.bias && part == 0)) continue;
                 const int j = tile * M + quarter * 32 + lane;
                 const bool row_ok = j < p.n_rows;
                 float *yrow = nullptr;
-                if (row_ok) yrow = p.y + (size_t)(p.out_rows ? p.out_rows[j] : j) * p.ldy;
+                if (row_ok)
+                    yrow = split ? p.ws + ((size_t)part * p.n_rows + j) * p.cout
+                                 : p.y + (size_t)(p.out_rows ? p.out_rows[j] : j) * p.ldy;
                 const uint32_t acc_addr = tmem_base + (uint32_t)(t * p.acc_cols) + ((uint32_t)(quarter * 32) << 16);
                 for (int col = 0; col < p.cout; col += 16) {
                     float acc[16];
@@ -395,19 +430,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
                         for (int e = 0; e < 16; ++e) acc[e] = 0.f;
                     }
                     if (!row_ok) continue;
-                    if (p.bias && part == 0)
+                    if (split) {  // plain stores of the partial tile (cout % 16 == 0, workspace 16-byte aligned)
+#pragma unroll
+                        for (int e = 0; e < 16; e += 4)
+                            *reinterpret_cast<float4 *>(yrow + col + e) = make_float4(acc[e], acc[e + 1], acc[e + 2], acc[e + 3]);
+                        continue;
+                    }
+                    if (p.bias)
 #pragma unroll
                         for (int e = 0; e < 16; ++e) acc[e] += __ldg(p.bias + col + e);
-                    if (split) {
-                        if (vec) {
-#pragma unroll
-                            for (int e = 0; e < 16; e += 4)
-                                atomicAdd(reinterpret_cast<float4 *>(yrow + col + e), make_float4(acc[e], acc[e + 1], acc[e + 2], acc[e + 3]));
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < 16; ++e) atomicAdd(yrow + col + e, acc[e]);
-                        }
-                    } else if (vec) {
+                    if (vec) {
 #pragma unroll
                         for (int e = 0; e < 16; e += 4) {
                             float4 o = make_float4(acc[e], acc[e + 1], acc[e + 2], acc[e + 3]);
@@ -432,7 +464,84 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
 
     tc_fence_before();
     __syncthreads();
-    if (warp == MMA_WARP) tmem_dealloc(tmem_base, (uint32_t)(T * p.acc_cols));
+    if (warp == MMA_WARP) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// Cost-weighted partition of the output tiles over G CTAs: tile i costs (active offsets of its mask) + 2 (index / epilogue
+// overhead); part[b] = first tile of CTA b, chosen so that every CTA's range carries ~1/G of the total.  One block.
+__global__ void __launch_bounds__(1024) k_partition(const uint32_t *__restrict__ tile_mask, int n_tiles, int kvol, int G,
+                                                    int32_t *__restrict__ part) {
+    __shared__ long long wsum[32];
+    __shared__ long long carry_s, total_s;
+    const uint32_t all_k = kvol >= 32 ? 0xFFFFFFFFu : ((1u << kvol) - 1u);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    auto cost = [&](int i) -> long long { return i < n_tiles ? (long long)__popc(tile_mask[i] & all_k) + 2 : 0; };
+    // pass 1: total
+    long long acc = 0;
+    for (int i = tid; i < n_tiles; i += blockDim.x) acc += cost(i);
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if (lane == 0) wsum[warp] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        long long t = 0;
+        for (int w = 0; w < 32; ++w) t += wsum[w];
+        total_s = t;
+        carry_s = 0;
+    }
+    __syncthreads();
+    const long long total = total_s;
+    if (tid <= G) {
+        if (tid == 0) part[0] = 0;
+        if (tid == G) part[G] = n_tiles;
+    }
+    // pass 2: running prefix, chunk by chunk; tile i opens CTA b's range when the prefix BEFORE it crosses b * total / G
+    for (int base = 0; base < n_tiles; base += blockDim.x) {
+        const int i = base + tid;
+        long long c = cost(i), incl = c;
+        for (int o = 1; o < 32; o <<= 1) {
+            long long v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        long long woff = 0;
+        for (int w = 0; w < warp; ++w) woff += wsum[w];
+        const long long before = carry_s + woff + incl - c;  // cost of tiles [0, i)
+        if (i < n_tiles && total > 0) {
+            // boundaries b with  before < b * total / G <= before + c   start AFTER tile i (tile i closes CTA b - 1's range)
+            long long b_lo = (before * G) / total + 1, b_hi = ((before + c) * G) / total;
+            for (long long b = b_lo; b <= b_hi && b < G; ++b)
+                if (b >= 1) part[b] = i + 1;
+        }
+        __syncthreads();
+        if (tid == blockDim.x - 1) carry_s = carry_s + woff + incl;
+        __syncthreads();
+    }
+}
+
+// Split mode, second half: y[row] (=|+=) bias + sum_q ws[q][row], parts added in index order (bit-reproducible; the vector
+// reds this replaces cost ~25 us per 128-row tile on the B200: ~76 G fp32 atomics/s chip-wide).
+__global__ void __launch_bounds__(256) k_reduce_parts(const float *__restrict__ ws, int ksplit, int n_rows, int cout,
+                                                      const float *__restrict__ bias, float *__restrict__ y, int ldy, int accumulate) {
+    const int g = cout / 4;
+    const long long total = (long long)n_rows * g;
+    const size_t plane = (size_t)n_rows * cout;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(e / g), c = (int)(e - (long long)r * g) * 4;
+        float4 acc = *reinterpret_cast<const float4 *>(ws + (size_t)r * cout + c);
+        for (int q = 1; q < ksplit; ++q) {
+            const float4 v = *reinterpret_cast<const float4 *>(ws + q * plane + (size_t)r * cout + c);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        if (bias != nullptr) {
+            acc.x += bias[c]; acc.y += bias[c + 1]; acc.z += bias[c + 2]; acc.w += bias[c + 3];
+        }
+        float *dst = y + (size_t)r * ldy + c;
+        if (accumulate) {
+            acc.x += dst[0]; acc.y += dst[1]; acc.z += dst[2]; acc.w += dst[3];
+        }
+        dst[0] = acc.x; dst[1] = acc.y; dst[2] = acc.z; dst[3] = acc.w;
+    }
 }
 
 template <int PASSES, bool FUSE>
@@ -482,9 +591,19 @@ void us3d_debug_set_tuning4(int a_slots, int lag, int T, int fuse) {
 }
 void us3d_debug_set_tuning(int a_slots, int lag, int T) { us3d_debug_set_tuning4(a_slots, lag, T, 0); }
 
+int us3d_spconv_partition(const uint32_t *tile_mask, int n_tiles, int kvol, int32_t *partition, void *stream_) {
+    US3D_CHECK_ARG(tile_mask != nullptr && partition != nullptr && n_tiles >= 0 && kvol >= 1 && kvol <= US3D_MAX_KVOL, "spconv_partition: bad arguments");
+    mt::k_partition<<<1, 1024, 0, (cudaStream_t)stream_>>>(tile_mask, n_tiles, kvol, num_sms(), partition);
+    US3D_LAUNCH_CHECK();
+    return 0;
+}
+
+int us3d_spconv_partition_size(void) { return num_sms() + 1; }
+
 int us3d_spconv_gather_mt(const void *x_hi, const void *x_lo, int n_in, const int32_t *nbr, int n_rows, int kvol,
                           const void *wpack, int cin, int cout, int passes, const float *bias, const int32_t *out_rows,
-                          float *y, int ldy, int accumulate, const uint32_t *tile_mask, void *stream_) {
+                          float *y, int ldy, int accumulate, const uint32_t *tile_mask, const int32_t *partition, void *workspace,
+                          long long workspace_bytes, void *stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     US3D_CHECK_ARG(kvol >= 1 && kvol <= US3D_MAX_KVOL, "spconv_gather_mt: kvol %d out of range", kvol);
     US3D_CHECK_ARG(passes == 1 || passes == 3, "spconv_gather_mt: passes must be 1 or 3");
@@ -507,29 +626,46 @@ int us3d_spconv_gather_mt(const void *x_hi, const void *x_lo, int n_in, const in
     int cols = 32;
     while (cols < (fuse ? 2 * cout : cout)) cols <<= 1;
     p.acc_cols = cols;
+    const int sms = num_sms();
     int T = 512 / cols;
     if (T > mt::MAX_T) T = mt::MAX_T;
-    // small maps: do not starve SMs of work for the sake of weight reuse
-    while (T > 1 && ceil_div(p.n_tiles, T) < num_sms()) T >>= 1;
+    p.prof = g_prof;
+    // Work decomposition.  The kernel's cost is ~ the (tile, offset) products on the busiest CTA plus ~2 of them per tile for the
+    // epilogue.  With the offsets of a tile dealt to `ks` CTAs (each writes a partial tile to the workspace, k_reduce_parts sums
+    // them in a second launch) the busiest CTA runs ceil(tiles * ks / SMs) units of ceil(kvol / ks) offsets.  ks = 1 needs no
+    // second pass and shares weight slabs between the tiles of a CTA, so a split has to win by 25 %.  Without a workspace the
+    // map is never split.  (Round 1 split with vector reds into y: measured ~25 us per 128-row tile on the B200.)
+    int ksplit = 1;
+    if (out_rows == nullptr && kvol > 1 && workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0) {
+        long long best = (long long)ceil_div(p.n_tiles, sms) * (kvol + 2) * 100;
+        for (int ks = 2; ks <= kvol; ++ks) {
+            if ((long long)ks * n_rows * cout * (long long)sizeof(float) > workspace_bytes) break;
+            const long long c = (long long)ceil_div((long long)p.n_tiles * ks, sms) * (ceil_div(kvol, ks) + 2) * 125;
+            if (c < best) {
+                best = c;
+                ksplit = ks;
+            }
+        }
+    }
+    p.ws = (float *)workspace;
+    if (ksplit > 1) T = 1;
+    // range mode: every CTA owns a contiguous range of tiles; no more accumulators than its share of the tiles
+    if (ksplit == 1) {
+        const int per_cta = ceil_div(p.n_tiles, sms);
+        if (T > per_cta) T = per_cta;
+    }
     if (g_tune_T > 0 && g_tune_T <= T) T = g_tune_T;
     p.T = T;
-    p.prof = g_prof;
     p.n_super = ceil_div(p.n_tiles, T);
-    // small maps (coarse levels): deal the kernel offsets of a super-tile to several CTAs; partial sums meet in y
-    int ksplit = 1;
-    if (out_rows == nullptr && kvol > 1 && p.n_super * 2 <= num_sms()) {
-        ksplit = num_sms() / p.n_super;
-        if (ksplit > kvol) ksplit = kvol;
-    }
     p.ksplit = ksplit;
-    p.n_units = p.n_super * ksplit;
+    p.n_units = ksplit == 1 ? p.n_tiles : p.n_tiles * ksplit;
+    // the cost-weighted partition (us3d_spconv_partition) is laid out for one CTA per SM
+    p.part = (ksplit == 1 && partition != nullptr && p.n_tiles >= 2 * sms) ? partition : nullptr;
     for (int q = 0; q < US3D_MAX_KVOL; ++q) {
         uint32_t pmask = 0;
         for (int k = q; k < kvol && q < ksplit; k += ksplit) pmask |= 1u << k;
         p.part_mask[q] = ksplit == 1 ? 0xFFFFFFFFu : pmask;
     }
-    if (ksplit > 1 && !accumulate)
-        US3D_CUDA(cudaMemset2DAsync(y, (size_t)ldy * sizeof(float), 0, (size_t)cout * sizeof(float), (size_t)n_rows, st));
     p.b_plane = cout * 128;
     const int a_slot = npl * mt::A_PLANE, b_slot = npl * p.b_plane;
     const int budget = 208 * 1024;
@@ -540,7 +676,7 @@ int us3d_spconv_gather_mt(const void *x_hi, const void *x_lo, int n_in, const in
     if (p.a_slots == mt::MAX_A && budget - p.a_slots * a_slot - 3 * b_slot >= 0) p.b_slots = 3;
     if (g_tune_a_slots >= 2 && g_tune_a_slots <= p.a_slots) p.a_slots = g_tune_a_slots;
     const size_t smem = (size_t)p.a_slots * a_slot + (size_t)p.b_slots * b_slot + 1024;
-    const int grid = p.n_units < num_sms() ? p.n_units : num_sms();
+    const int grid = p.n_units < sms ? p.n_units : sms;
     // Groups a producer warp keeps in flight before it waits for the oldest.  Measured on B200 (200k voxels, 128 -> 96):
     // three-term mode 0.521 ms at lag 3, 0.472 ms at lag 1 — with 32 KB slots a deep lag leaves the MMA warp no landed
     // slot to run ahead on; single-pass mode is best at lag 2.
@@ -556,9 +692,22 @@ int us3d_spconv_gather_mt(const void *x_hi, const void *x_lo, int n_in, const in
         else
             e = mt::launch<1, false>(lag, grid, smem, st, p);
         US3D_CUDA(e);
+        US3D_LAUNCH_CHECK();
+        if (ksplit > 1) {
+            long long blocks = ((long long)n_rows * (cout / 4) + 255) / 256;
+            if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
+            mt::k_reduce_parts<<<(int)blocks, 256, 0, st>>>(p.ws, ksplit, n_rows, cout, bias, y, ldy, accumulate);
+            US3D_LAUNCH_CHECK();
+        }
     }
-    US3D_LAUNCH_CHECK();
     return 0;
+}
+
+/* bytes of workspace that let us3d_spconv_gather_mt split a small map's offsets over all SMs (0: the map is never split) */
+long long us3d_spconv_gather_mt_workspace_bytes(int n_rows, int kvol, int cout) {
+    const int n_tiles = ceil_div(n_rows, mt::M);
+    if (kvol <= 1 || n_tiles >= 2 * num_sms()) return 0;
+    return (long long)kvol * n_rows * cout * (long long)sizeof(float);
 }
 
 }  // extern "C"

@@ -103,10 +103,26 @@ def set_row_ordering(min_rows: int):
 
 
 class NeighbourTable:
-    __slots__ = ("nbr", "mask", "n_rows", "kvol", "_pairs", "_ordered")
+    __slots__ = ("nbr", "mask", "n_rows", "kvol", "_pairs", "_ordered", "_part")
 
     def __init__(self, nbr: torch.Tensor, mask: torch.Tensor, n_rows: int, kvol: int):
-        self.nbr, self.mask, self.n_rows, self.kvol, self._pairs, self._ordered = nbr, mask, n_rows, kvol, None, None
+        self.nbr, self.mask, self.n_rows, self.kvol, self._pairs, self._ordered, self._part = nbr, mask, n_rows, kvol, None, None, None
+
+    def partition(self):
+        """Cost-weighted split of the (pattern-ordered) table's 128-row tiles over the SMs: int32 [SMs + 1] tile boundaries such
+        that every CTA's contiguous range carries the same number of active (tile, offset) products.  Tiles of a pattern-ordered
+        table differ by up to 27x in cost (the rarest patterns sort first), so equal COUNTS leave the CTAs unbalanced.  One tiny
+        kernel, built with the order and cached."""
+        if self._part is None:
+            o = self.ordered()
+            if not o:
+                self._part = False
+            else:
+                part = torch.empty(int(lib.us3d_spconv_partition_size()), dtype=torch.int32, device=self.nbr.device)
+                n_tiles = (self.n_rows + TILE_ROWS - 1) // TILE_ROWS
+                check(lib.us3d_spconv_partition(o[1].data_ptr(), n_tiles, self.kvol, part.data_ptr(), _stream()))
+                self._part = part
+        return None if self._part is False else self._part
 
     def ordered(self):
         """(nbr, tile mask, order) with the table's rows grouped by neighbour pattern, or None for small tables.

@@ -227,13 +227,6 @@ def pack_network(net: torch.nn.Module):
         k._us3d_packs = ((k._version, epoch, mode, flip, k.data_ptr()), fwd, bwd)
 
 
-# forward / input-gradient tensor-core kernel: "cp" = cp.async row gather, persistent, double-buffered TMEM (default);
-# "tma" = same pipeline with TMA tile::gather4 (slower: ~80 cycles per gather4); "ldg" = register-staged gather
-# "mt" = "cp" + up to 4 output tiles sharing each weight slab (production).  Weight gradient: "planes" = cp.async
-# from the bf16 planes, up to 4 offsets per dY tile (production); "ldg" = register-staged, one offset per CTA
-_tc_kernel = {"fwd": "mt", "wgrad": "planes"}
-
-
 def bf16_planes(x: torch.Tensor, need_lo: bool):
     """bf16 hi plane (+ lo = x - hi) of a row-major fp32 tensor, cached on the tensor object while its
     version counter is unchanged (an activation feeds the forward conv, a shortcut conv and the weight gradient)."""
@@ -249,6 +242,23 @@ def bf16_planes(x: torch.Tensor, need_lo: bool):
     except Exception:  # pragma: no cover - tensors normally accept attributes
         pass
     return hi, lo
+
+
+_conv_ws = {}
+_SMALL_MAP_ROWS = 148 * 2 * 128  # == the bound inside us3d_spconv_gather_mt_workspace_bytes, without the FFI round trip
+
+
+def _conv_workspace(dev, n_rows, kvol, cout):
+    """Per-device scratch for the split mode of small maps (partial tiles [parts][n_rows][cout] fp32).  Kernels of one stream are
+    ordered, so one buffer per device serves the single-stream execution of the module surface; it only grows."""
+    if kvol <= 1 or n_rows >= _SMALL_MAP_ROWS:
+        return None, 0
+    need = kvol * n_rows * cout * 4
+    ws = _conv_ws.get(dev.index)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(max(need, 32 << 20), dtype=torch.uint8, device=dev)
+        _conv_ws[dev.index] = ws
+    return ws, ws.numel()
 
 
 def _tc_ok(cin, cout):  # == us3d_spconv_tc_supported, without the FFI round trip
@@ -274,18 +284,13 @@ def spconv_gather(x, table: NeighbourTable, w3, cin, cout, transpose_w, flip_k, 
         if wpack is None:
             wpack = pack_weights(w3, transpose_w, flip_k, mode)
         hi, lo = bf16_planes(x, mode == 3)
-        kname = _tc_kernel["fwd"]
-        if kname in ("tma", "cp", "mt"):
-            fn = lib.us3d_spconv_gather_mt if kname == "mt" else (lib.us3d_spconv_gather_tma if kname == "tma" else lib.us3d_spconv_gather_cp)
-            nbr, mask, order = (table.ordered() if kname == "mt" else None) or (table.nbr, table.mask, None)
-            _timed(kind, x.shape[0], table.n_rows, table.kvol, cin, cout, lambda: check(
-                fn(hi.data_ptr(), _ptr(lo), x.shape[0], nbr.data_ptr(), table.n_rows, table.kvol, wpack.data_ptr(), cin, cout,
-                   mode, _ptr(bias), _ptr(order), y.data_ptr(), _ld(y), int(accumulate), _ptr(mask), st)), table, kname)
-            return y
+        nbr, mask, order = table.ordered() or (table.nbr, table.mask, None)
+        part = table.partition() if order is not None else None
+        ws, ws_bytes = _conv_workspace(x.device, table.n_rows, table.kvol, cout) if order is None else (None, 0)
         _timed(kind, x.shape[0], table.n_rows, table.kvol, cin, cout, lambda: check(
-            lib.us3d_spconv_gather_tc(x.data_ptr(), _ld(x), table.nbr.data_ptr(), table.n_rows, table.kvol, wpack.data_ptr(),
-                                      cin, cout, mode, _ptr(bias), 0, y.data_ptr(), _ld(y), int(accumulate),
-                                      _ptr(table.mask), st)), table, "tc")
+            lib.us3d_spconv_gather_mt(hi.data_ptr(), _ptr(lo), x.shape[0], nbr.data_ptr(), table.n_rows, table.kvol, wpack.data_ptr(),
+                                      cin, cout, mode, _ptr(bias), _ptr(order), y.data_ptr(), _ld(y), int(accumulate), _ptr(mask),
+                                      _ptr(part), _ptr(ws), ws_bytes, st)), table, "mt")
         return y
     _timed(kind, x.shape[0], table.n_rows, table.kvol, cin, cout, lambda: check(
         lib.us3d_spconv_gather(x.data_ptr(), _ld(x), table.nbr.data_ptr(), table.n_rows, table.kvol, w3.data_ptr(), cin, cout,
@@ -306,29 +311,24 @@ def spconv_wgrad(x, table: NeighbourTable, dy, cin, cout):
         return dw
     if (mode != 0 and _wgrad_tc_ok(cin, cout) and x.data_ptr() % 16 == 0 and dy.data_ptr() % 16 == 0
             and _ld(x) % 4 == 0 and _ld(dy) % 4 == 0):
-        if _tc_kernel["wgrad"] == "planes":
-            xh, xl = bf16_planes(x, mode == 3)
-            dh, dl = bf16_planes(dy, mode == 3)
-            # pattern order pays for the weight gradient only on k2s2 maps (one parent per fine row: 1/8 of the tile x offset
-            # products remain); on k3 maps the scattered dY rows cost more than the skipped products save (measured on B200:
-            # 200k voxels 96 -> 96, 0.55 -> 0.62 ms ordered, k2s2 0.171 -> 0.125 ms)
-            wgrad_order = _wgrad_order["mode"]
-            nbr, mask, order = (table.ordered() if (table.kvol <= 8 or wgrad_order == "permute") else None) or (table.nbr, table.mask, None)
-            if order is not None and table.kvol > 8:
-                # k3 maps: bring the dY planes into table order with one streaming pass (out[j] = dY[order[j]]) instead of letting
-                # the kernel gather scattered dY rows
-                n, c = dy.shape
-                ph = torch.empty_like(dh)
-                pl = torch.empty_like(dl) if dl is not None else None
-                check(lib.us3d_permute_planes(dh.data_ptr(), _ptr(dl), order.data_ptr(), n, c, ph.data_ptr(), _ptr(pl), st))
-                dh, dl, order = ph, pl, None
-            _timed("wgrad", x.shape[0], table.n_rows, table.kvol, cin, cout, lambda: check(
-                lib.us3d_spconv_wgrad_planes(xh.data_ptr(), _ptr(xl), dh.data_ptr(), _ptr(dl), nbr.data_ptr(), table.n_rows,
-                                             table.kvol, dw.data_ptr(), cin, cout, mode, _ptr(mask), _ptr(order), st)), table, "wgrad-tc")
-            return dw
+        xh, xl = bf16_planes(x, mode == 3)
+        dh, dl = bf16_planes(dy, mode == 3)
+        # pattern order pays for the weight gradient only on k2s2 maps (one parent per fine row: 1/8 of the tile x offset
+        # products remain); on k3 maps the scattered dY rows cost more than the skipped products save (measured on B200:
+        # 200k voxels 96 -> 96, 0.55 -> 0.62 ms ordered, k2s2 0.171 -> 0.125 ms)
+        wgrad_order = _wgrad_order["mode"]
+        nbr, mask, order = (table.ordered() if (table.kvol <= 8 or wgrad_order == "permute") else None) or (table.nbr, table.mask, None)
+        if order is not None and table.kvol > 8:
+            # k3 maps: bring the dY planes into table order with one streaming pass (out[j] = dY[order[j]]) instead of letting
+            # the kernel gather scattered dY rows
+            n, c = dy.shape
+            ph = torch.empty_like(dh)
+            pl = torch.empty_like(dl) if dl is not None else None
+            check(lib.us3d_permute_planes(dh.data_ptr(), _ptr(dl), order.data_ptr(), n, c, ph.data_ptr(), _ptr(pl), st))
+            dh, dl, order = ph, pl, None
         _timed("wgrad", x.shape[0], table.n_rows, table.kvol, cin, cout, lambda: check(
-            lib.us3d_spconv_wgrad_tc(x.data_ptr(), _ld(x), table.nbr.data_ptr(), table.n_rows, table.kvol, dy.data_ptr(), _ld(dy),
-                                     0, dw.data_ptr(), cin, cout, mode, _ptr(table.mask), st)), table, "wgrad-tc")
+            lib.us3d_spconv_wgrad_planes(xh.data_ptr(), _ptr(xl), dh.data_ptr(), _ptr(dl), nbr.data_ptr(), table.n_rows,
+                                         table.kvol, dw.data_ptr(), cin, cout, mode, _ptr(mask), _ptr(order), st)), table, "wgrad-tc")
         return dw
     _timed("wgrad", x.shape[0], table.n_rows, table.kvol, cin, cout, lambda: check(
         lib.us3d_spconv_wgrad(x.data_ptr(), _ld(x), table.nbr.data_ptr(), table.n_rows, table.kvol, dy.data_ptr(), _ld(dy), 0,
