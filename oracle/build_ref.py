@@ -1,0 +1,78 @@
+"""Builds oracle/_ref/ — the reference's OWN code, compiled / staged where it lies under /root/reference (build container
+only; the outputs are git-ignored and travel to the GPU box with the snapshot).  TEST INFRASTRUCTURE, never the product.
+
+* `libfps_ref.so`: the reference's furthest-point-sampling kernel, third_party/pointnet2/_ext_src/src/sampling_gpu.cu
+  (:72-176 kernel, :178-215 host wrapper), compiled for sm_100a straight from the reference tree together with
+  oracle/fps_ref_shim.cu (an extern "C" entry around the reference's own host wrapper).  It needs ATen only for
+  `at::cuda::getCurrentCUDAStream()`, so it links against the torch libraries of this image.
+* `reference/`: the UNMODIFIED reference Python files of the hot path (models/, pointnet2_utils.py, the pseudo-mask
+  functions, the trainer and its entry point) staged so that the `-m gpu` tests can execute them on the CUDA shim on the GPU
+  box, where /root/reference does not exist.  Nothing here is committed: the reference's sources stay out of the history.
+
+    python oracle/build_ref.py [--verbose]
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(HERE, "_ref")
+REFERENCE = "/root/reference"
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+
+STAGED = [
+    "models", "third_party/pointnet2/pointnet2_utils.py", "third_party/pointnet2/pytorch_utils.py",
+    "pseudo_masks/unscene3d_pseudo_main.py", "pseudo_masks/freemask_main.py", "utils/freemask_utils.py", "utils/pc_utils.py",
+    "utils/utils.py", "utils/kfold.py", "utils/votenet_utils", "datasets/utils.py", "trainer/trainer.py", "trainer/__init__.py",
+    "main_instance_segmentation.py", "conf", "utils/cuda_utils/cuda_utils.py", "utils/cuda_utils/raycast_image.py",
+    "models/noise_robust_loss.py",
+]
+
+
+def build_fps(verbose=False):
+    import torch  # noqa: F401  (locates the headers / libraries)
+    from torch.utils import cpp_extension as ce
+
+    src = os.path.join(REFERENCE, "third_party/pointnet2/_ext_src/src/sampling_gpu.cu")
+    inc = os.path.join(REFERENCE, "third_party/pointnet2/_ext_src/include")
+    shim = os.path.join(HERE, "fps_ref_shim.cu")
+    lib = os.path.join(OUT, "libfps_ref.so")
+    if os.path.exists(lib) and os.path.getmtime(lib) > os.path.getmtime(shim):
+        return lib
+    tlib = ce.library_paths(device_type="cuda")[0]
+    cmd = [NVCC, "-shared", "-Xcompiler", "-fPIC", "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-I", inc]
+    for p in ce.include_paths(device_type="cuda"):
+        cmd += ["-I", p]
+    cmd += [src, shim, "-o", lib, "-L", tlib, "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-Xlinker", "-rpath," + tlib]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    subprocess.run(cmd, check=True)
+    return lib
+
+
+def stage_reference():
+    dst_root = os.path.join(OUT, "reference")
+    for rel in STAGED:
+        src = os.path.join(REFERENCE, rel)
+        dst = os.path.join(dst_root, rel)
+        if not os.path.exists(src):
+            continue
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        if os.path.isdir(src):
+            shutil.copytree(src, dst, dirs_exist_ok=True, ignore=shutil.ignore_patterns("__pycache__", "*.pyc"), copy_function=shutil.copyfile)
+        else:
+            shutil.copyfile(src, dst)
+    return dst_root
+
+
+def build(verbose=False):
+    """Returns None where /root/reference is absent — the GPU box uses what was built here."""
+    if not os.path.isdir(REFERENCE):
+        return None
+    os.makedirs(OUT, exist_ok=True)
+    return build_fps(verbose), stage_reference()
+
+
+if __name__ == "__main__":
+    print(build(verbose="--verbose" in sys.argv))

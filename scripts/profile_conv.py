@@ -9,7 +9,6 @@ from unscene3d_b200.engine import functional as Fn
 from unscene3d_b200.synthetic import make_scene
 
 mode = int(os.environ.get("US3D_MODE", "3"))
-Fn._tc_kernel["fwd"] = os.environ.get("US3D_TC_KERNEL", "mt")
 dev = torch.device("cuda")
 s = make_scene(200_000, seed=0, with_masks=False)
 c4 = torch.from_numpy(np.concatenate([np.zeros((s.n, 1), np.int32), s.coords], 1)).to(dev)

@@ -94,6 +94,51 @@ def have_reference() -> bool:
     return os.path.isdir(os.path.join(REFERENCE, "models"))
 
 
+def staged_reference_root():
+    """Where the UNMODIFIED reference Python files can be imported from: /root/reference in the build container, the copy
+    staged by oracle/build_ref.py (git-ignored oracle/_ref/reference, shipped with the snapshot) on the GPU box."""
+    for root in (REFERENCE, os.path.join(REPO, "oracle", "_ref", "reference")):
+        if os.path.isdir(os.path.join(root, "models")):
+            return root
+    return None
+
+
+def reference_models_on_shim():
+    """The UNMODIFIED reference `models` package over the CUDA drop-in modules (unscene3d_b200/shims): `import MinkowskiEngine`,
+    `torch_scatter`, `pointnet2._ext`, `detectron2`, `custom_cuda_utils` inside the reference files resolve to libus3d."""
+    root = staged_reference_root()
+    assert root is not None
+    collections.Set = collections.abc.Set
+    cur = sys.modules.get("models")
+    if cur is not None and getattr(cur, "_us3d_backend", None) == "shim":
+        return cur
+    import unscene3d_b200  # noqa: F401  (shims first on sys.path)
+
+    for k in [k for k in sys.modules if k == "models" or k.startswith("models.") or k.startswith("third_party")]:
+        del sys.modules[k]
+    for k in _ME_KEYS:  # a CPU test of the same process may have left the oracle's modules under these names
+        m = sys.modules.get(k)
+        if m is not None and "shims" not in (getattr(m, "__file__", "") or ""):
+            del sys.modules[k]
+    saved = {k: sys.modules.get(k) for k in _stub_modules()}
+    sys.modules.update({k: v for k, v in _stub_modules().items() if k not in sys.modules})
+    sys.path.insert(0, root)
+    try:
+        mod = importlib.import_module("models")
+        for sub in ("res16unet", "mask3d", "matcher", "criterion"):
+            importlib.import_module("models." + sub)
+    finally:
+        sys.path.remove(root)
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+    mod._us3d_backend = "shim"
+    import MinkowskiEngine
+
+    assert "shims" in MinkowskiEngine.__file__, MinkowskiEngine.__file__
+    return mod
+
+
 def reference_models_on_oracle():
     """The UNMODIFIED reference `models` package over the oracle (build container only).
     The reference uses absolute imports (`from models.resnet import ...`), so it has to be imported
