@@ -15,6 +15,7 @@ using namespace us3d::tcx;
 __global__ void __launch_bounds__(256, 1) k_probe(int n, int iters, int mode, int writers, long long *out, const uint8_t *src, int wmode) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t done;
+    __shared__ __align__(8) uint64_t ring[8];
     __shared__ uint32_t tmem_base_s;
     __shared__ volatile int stop;
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -23,6 +24,7 @@ __global__ void __launch_bounds__(256, 1) k_probe(int n, int iters, int mode, in
     for (int i = tid; i < (16 + 32) * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0x3c003c00u;
     if (tid == 0) {
         mbar_init(smem_u32(&done), 1);
+        for (int i = 0; i < 8; ++i) mbar_init(smem_u32(&ring[i]), 1);
         mbar_fence_init();
         stop = 0;
     }
@@ -37,7 +39,17 @@ __global__ void __launch_bounds__(256, 1) k_probe(int n, int iters, int mode, in
         const uint32_t idesc = idesc_bf16(n);
         const uint64_t da = desc_k_sw128(a_base), db = desc_k_sw128(b_base);
         long long t0 = clock64();
-        if (elect_one()) {
+        if (wmode == 4) {
+            // mode = MMAs per commit (0: commits only, no MMA at all)
+            const int g = mode;
+            if (elect_one()) {
+                for (int i = 0; i < iters; ++i) {
+                    if (g > 0) umma(tmem_base, da + (uint64_t)((i & 3) * 2), db + (uint64_t)((i & 3) * 2), idesc, i >= 2);
+                    if (g == 0 || (i % g) == g - 1) umma_commit(smem_u32(&ring[(i / (g ? g : 1)) & 7]));
+                }
+                umma_commit(smem_u32(&done));
+            }
+        } else if (elect_one()) {
             for (int i = 0; i < iters; ++i) {
                 const uint64_t adv = mode == 2 ? (uint64_t)((i & 3) * 2) : 0;
                 const uint32_t acc = tmem_base + ((mode == 1 && (i & 1)) ? 256u : 0u);
@@ -54,7 +66,7 @@ __global__ void __launch_bounds__(256, 1) k_probe(int n, int iters, int mode, in
             out[blockIdx.x * 2] = t1 - t0;
             out[blockIdx.x * 2 + 1] = t2 - t0;
         }
-    } else if (warp <= writers) {
+    } else if (wmode < 2 && warp <= writers) {
         uint32_t dst = scratch + (uint32_t)(warp - 1) * 4096u + (uint32_t)(tid & 31) * 16u;
         int k = 0;
         long long bytes = 0;
@@ -85,6 +97,16 @@ __global__ void __launch_bounds__(256, 1) k_probe(int n, int iters, int mode, in
             if (lane == 0) atomicAdd((unsigned long long *)&out[296 + blockIdx.x], (unsigned long long)bytes);
         }
     }
+    else if (wmode >= 2 && warp >= 1) {
+        // wmode 2: all 32 lanes of 7 warps poll an mbarrier that never completes (what the conv kernel's waiting roles do);
+        // wmode 3: one lane polls, the others park at __syncwarp
+        __shared__ __align__(8) uint64_t never;
+        if (tid == 32) mbar_init(smem_u32(&never), 1);
+        __syncwarp();
+        if (wmode == 2 || (tid & 31) == 0)
+            while (!stop) mbar_try_wait(smem_u32(&never), 0);
+        __syncwarp();
+    }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base, 512);
@@ -99,11 +121,13 @@ int main() {
     cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     const int iters = 4096;
     long long h[444];
-    for (int wmode = 0; wmode < 2; ++wmode)
-    for (int writers = (wmode ? 2 : 0); writers <= (wmode ? 7 : 4); writers += (wmode ? 1 : 4))
-        for (int mode = (wmode ? 2 : 0); mode < 3; ++mode)
+    for (int wmode = 0; wmode < 5; ++wmode)
+    for (int writers = (wmode == 1 ? 2 : 0); writers <= (wmode == 1 ? 7 : wmode == 0 ? 4 : 0); writers += (wmode == 1 ? 1 : 4))
+        for (int mode = ((wmode && wmode < 4) ? 2 : 0); mode < (wmode == 4 ? 9 : 3); ++mode)
             for (int n : {32, 64, 96, 128, 192, 256}) {
                 if (wmode && n != 96 && n != 192 && n != 256) continue;
+                if (wmode == 4 && n != 96) continue;
+                if (wmode == 4 && !(mode == 0 || mode == 1 || mode == 2 || mode == 4 || mode == 8)) continue;
                 cudaMemset(out, 0, 148 * 3 * sizeof(long long));
                 k_probe<<<148, 256, 200 * 1024>>>(n, iters, mode, writers, out, src, wmode);
                 cudaError_t e = cudaDeviceSynchronize();
@@ -112,7 +136,7 @@ int main() {
                 double issue = 0, total = 0, wb = 0;
                 for (int b = 0; b < 148; ++b) { issue += h[2 * b]; total += h[2 * b + 1]; wb += h[296 + b]; }
                 printf("%s writers %d mode %d N %3d: %.1f cyc/MMA issue, %.1f cyc/MMA complete (floor 128*N/256 = %d), gather %.1f B/clk/SM\n",
-                       wmode ? "cp.async" : "st.shared", writers, mode, n, issue / 148 / iters, total / 148 / iters, n / 2, wb / total);
+                       wmode == 0 ? "st.shared" : wmode == 1 ? "cp.async" : wmode == 2 ? "7 warps x 32 lanes polling" : wmode == 3 ? "7 warps x 1 lane polling" : "commit every <mode> MMAs", writers, mode, n, issue / 148 / iters, total / 148 / iters, n / 2, wb / total);
             }
     return 0;
 }
