@@ -42,10 +42,10 @@ UNIT = "voxels/s"
 N_VOXELS = 200_000
 # dram__bytes_read.sum + dram__bytes_write.sum of the largest launch of each kernel, from the ncu --set full capture summarised
 # in profiles/ (see there for the command), next to the algorithmic bytes of that launch
-NCU_TRAFFIC = {"mt": {"launch": "200k voxels, k3, 128 -> 96 (pattern order)", "dram_bytes": 433717248, "alg_bytes": 180500000,
-                      "source": "profiles/r1_ncu_full_summary.md"},
-               "wgrad": {"launch": "200k voxels, k3, 128 -> 96", "dram_bytes": 235100000, "alg_bytes": 180500000,
-                         "source": "profiles/r1_ncu_full_summary.md"}}
+NCU_TRAFFIC = {"mt": {"launch": "200k voxels, k3, 128 -> 96 (pattern order)", "dram_bytes": 502625792, "alg_bytes": 180500000,
+                      "source": "profiles/r2_ncu_full_summary.md"},
+               "wgrad": {"launch": "200k voxels, k3, 128 -> 96", "dram_bytes": 242054656, "alg_bytes": 180500000,
+                         "source": "profiles/r2_ncu_full_summary.md"}}
 DTYPE = "bf16x3"  # tcgen05 bf16 products, three-term split hi*hi + lo*hi + hi*lo (fp32-faithful), fp32 accumulation in TMEM
 PRIME_STEPS = 30  # untimed steps BEFORE the --warmup steps: allocator pools of the two streams, NVML, clock / power ramp
 

@@ -303,6 +303,16 @@ int us3d_ncut_gram(const float *f, int s, int d, float *inv_norm, float *A, uint
 int us3d_ncut_threshold(const float *Aa, const float *Ab, int s, const uint32_t *stats_a, const uint32_t *stats_b, float tau,
                         double eps, const uint8_t *painted, uint32_t *bits, double *degree, void *stream);
 int us3d_ncut_matvec(const uint32_t *bits, int s, double eps, const double *x, const double *xsum, double *y, void *stream);
+/*   lanczos:   the spectral step of second_smallest_eigenvector (:138-146) as ONE cooperative launch: Lanczos steps [j0, j1) of
+ *              M = D^-1/2 W D^-1/2 with two Gram-Schmidt passes per step against every earlier basis vector, entirely on the
+ *              device (bit matrix, basis slices in shared memory, three grid barriers per step).  Q: double[(m + 2), s], row 0 =
+ *              the deflated vector D^1/2 1 / |.|, row 1 = the unit start vector, rows 2.. are written (unit vectors on return);
+ *              dinv = D^-1/2; alpha / beta: double[m]; *steps_done (device int) = steps completed so far — < j1 when the
+ *              recurrence broke down (beta < breakdown).  The workspace is zeroed by the call with j0 == 0 and carries the
+ *              state of later calls (j0 = previous *steps_done).  s <= 32 x (number of SMs).                              */
+long long us3d_ncut_lanczos_workspace_bytes(int m);
+int us3d_ncut_lanczos(const uint32_t *bits, int s, double eps, const double *dinv, double *Q, double *alpha, double *beta, int j0,
+                      int j1, int m, double breakdown, void *workspace, long long workspace_bytes, int *steps_done, void *stream);
 
 /* ---------------------------------------------------------------- FreeMask-style pseudo masks (A22)
  * Segment branch of the scene loop of pseudo_masks/freemask_main.py:203-417.

@@ -63,6 +63,8 @@ PROTOTYPES = {
     "us3d_ncut_gram": [_p, _i, _i, _p, _p, _p, _p],
     "us3d_ncut_threshold": [_p, _p, _i, _p, _p, _f, ctypes.c_double, _p, _p, _p, _p],
     "us3d_ncut_matvec": [_p, _i, ctypes.c_double, _p, _p, _p, _p],
+    "us3d_ncut_lanczos_workspace_bytes": [_i],
+    "us3d_ncut_lanczos": [_p, _i, ctypes.c_double, _p, _p, _p, _p, _i, _i, _i, ctypes.c_double, _p, _ll, _p, _p],
     "us3d_xattn_workspace_bytes": [_i, _i, _i, _i, _i],
     "us3d_xattn_fwd": [_p, _p, _p, _p, _ll, _ll, _ll, _ll, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p],
     "us3d_xattn_bwd": [_p, _p, _p, _p, _ll, _ll, _ll, _ll, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p],
@@ -78,7 +80,7 @@ PROTOTYPES = {
 }
 _RESTYPE = {"us3d_last_error": ctypes.c_char_p, "us3d_launch_count": _ll, "us3d_reset_launch_count": None,
             "us3d_spconv_packed_bytes": _ll, "us3d_xattn_workspace_bytes": _ll,
-            "us3d_spconv_gather_mt_workspace_bytes": _ll}
+            "us3d_spconv_gather_mt_workspace_bytes": _ll, "us3d_ncut_lanczos_workspace_bytes": _ll}
 
 
 def _load():

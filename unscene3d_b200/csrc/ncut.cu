@@ -185,3 +185,249 @@ int us3d_ncut_matvec(const uint32_t *bits, int s, double eps, const double *x, c
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Device-resident spectral step: ALL Lanczos steps of a solve in one cooperative launch (us3d_ncut_lanczos).
+//
+// Replaces the host-driven loop (one matvec launch + ~7 fp64 library kernels + a host decision per step, >= 512 steps per
+// solve, <= 20 solves per scene) behind second_smallest_eigenvector (pseudo_masks/unscene3d_pseudo_main.py:138-146).
+//
+// Layout: the S elements are dealt to G = ceil(S / EPB) CTAs (EPB = 32 elements each).  A CTA keeps ITS SLICE of every
+// basis vector in shared memory ([cap][EPB + 1] doubles; rows past `cap` fall back to the L2-resident global copy), so the
+// two classical Gram-Schmidt passes of a step are local work: partial dots over the slice -> fp64 atomics on a global
+// coefficient vector -> grid barrier -> every CTA subtracts the projection from its slice.  Per step: bit-matrix matvec of the
+// CTA's rows (x = D^-1/2 q broadcast in shared memory), 3 grid barriers (after dots 1, after dots 2, after the norm).  The
+// new basis row is published unnormalised together with its squared norm; readers scale on load, the owner normalises its
+// global slice one phase later (no reader is left by then), so no extra barrier is needed.
+namespace us3d {
+namespace lz {
+
+constexpr int THREADS = 256;
+constexpr int EPB = 32;
+
+struct Params {
+    const uint32_t *bits;
+    int S, words;
+    double eps;
+    const double *dinv;
+    double *Q;
+    double *alpha, *beta;
+    int j0, j1, m2, cap;
+    double breakdown;
+    double *cA, *cB, *nrm;
+    unsigned *bar;
+    int *steps_done;
+};
+
+__device__ __forceinline__ double ldcg_d(const double *p) { return __ldcg(p); }
+
+// all CTAs of the (cooperative, co-resident) grid; `gen` is the caller's count of barriers passed
+__device__ __forceinline__ void grid_sync(unsigned *bar, unsigned G, unsigned &gen) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&bar[0], 1u) == G - 1) {
+            atomicExch(&bar[0], 0u);
+            __threadfence();
+            atomicExch(&bar[1], gen + 1);
+        } else {
+            while (*((volatile unsigned *)&bar[1]) == gen) {
+            }
+        }
+        __threadfence();
+    }
+    ++gen;
+    __syncthreads();
+}
+
+__device__ __forceinline__ double block_sum(double v, double *red) {  // red: >= 8 doubles of shared memory; all threads get the sum
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0;
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; ++w) s += red[w];
+    return s;
+}
+
+__global__ void __launch_bounds__(THREADS, 1) k_lanczos(Params p) {
+    extern __shared__ __align__(16) double sm[];
+    const int S = p.S, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned G = gridDim.x;
+    const int e0 = blockIdx.x * EPB;
+    const int ne = min(EPB, S - e0);  // valid elements of this slice
+    double *x_s = sm;                          // [S]
+    double *c_s = x_s + S;                     // [m2]
+    double *w_s = c_s + p.m2;                  // [EPB]
+    double *last_s = w_s + EPB;                // [EPB] normalised slice of the newest basis row
+    double *red = last_s + EPB;                // [8][EPB] partial projections (>= 8 doubles for block_sum)
+    double *Bs = red + 8 * EPB;                // [cap][EPB + 1]
+    constexpr int LD = EPB + 1;
+    unsigned gen = *((volatile unsigned *)&p.bar[1]);
+
+    // basis rows 0 .. j0 + 1 are complete and normalised in global memory (host / previous launch): load the slice
+    for (int idx = tid; idx < min(p.j0 + 2, p.cap) * EPB; idx += THREADS) {
+        const int i = idx / EPB, e = idx - i * EPB;
+        Bs[i * LD + e] = e < ne ? ldcg_d(p.Q + (size_t)i * S + e0 + e) : 0.0;
+    }
+    __syncthreads();
+
+    auto basis = [&](int i, int e, int newest) -> double {  // element e of this CTA's slice of basis row i
+        if (i < p.cap) return Bs[i * LD + e];
+        if (i == newest) return last_s[e];
+        return e < ne ? ldcg_d(p.Q + (size_t)i * S + e0 + e) : 0.0;
+    };
+    auto project = [&](int rows, int newest) {  // w_s[e] -= sum_i c_s[i] basis(i, e), i < rows
+        const int e = tid & (EPB - 1), ig = tid / EPB;  // 8 groups of rows
+        double acc = 0;
+        for (int i = ig; i < rows; i += THREADS / EPB) acc += c_s[i] * basis(i, e, newest);
+        red[ig * EPB + e] = acc;
+        __syncthreads();
+        if (tid < EPB) {
+            double s = 0;
+#pragma unroll
+            for (int q = 0; q < THREADS / EPB; ++q) s += red[q * EPB + tid];
+            w_s[tid] -= s;
+        }
+        __syncthreads();
+    };
+    auto dots = [&](int rows, int newest, double *dst) {  // dst[i] += <basis row i, w> over this slice
+        for (int i = tid; i < rows; i += THREADS) {
+            double s = 0;
+#pragma unroll 8
+            for (int e = 0; e < EPB; ++e) s += basis(i, e, newest) * w_s[e];
+            atomicAdd(dst + i, s);
+        }
+    };
+
+    double beta_prev = 1.0;
+    int steps = p.j0;
+    for (int j = p.j0; j < p.j1; ++j) {
+        const int newest = j + 1, rows = j + 2;
+        const double scale = j == p.j0 ? 1.0 : 1.0 / beta_prev;
+        // ---- A: x = D^-1/2 q_j for ALL elements (row `newest`: normalised at j0, else as published: raw, scaled on load)
+        double xs = 0;
+        for (int e = tid; e < S; e += THREADS) {
+            const double v = ldcg_d(p.Q + (size_t)newest * S + e) * scale * p.dinv[e];
+            x_s[e] = v;
+            xs += v;
+        }
+        if (j > p.j0 && tid < EPB) {  // this CTA's copy of the newest row was stored raw
+            const double v = w_s[tid] * scale;
+            last_s[tid] = v;
+            if (newest < p.cap) Bs[newest * LD + tid] = v;
+        } else if (j == p.j0 && tid < EPB) {
+            last_s[tid] = tid < ne ? ldcg_d(p.Q + (size_t)newest * S + e0 + tid) : 0.0;
+        }
+        const double xsum = block_sum(xs, red);
+        __syncthreads();
+        // ---- matvec of this CTA's rows: y = eps * sum(x) + (1 - eps) * (B x); w = D^-1/2 y
+        for (int r = warp; r < EPB; r += THREADS / 32) {
+            double acc = 0;
+            if (r < ne) {
+                const uint32_t *brow = p.bits + (size_t)(e0 + r) * p.words;
+                for (int w = lane; w < p.words; w += 32) {
+                    unsigned word = brow[w];
+                    const double *xv = x_s + w * 32;
+                    while (word) {
+                        const int b = __ffs(word) - 1;
+                        word &= word - 1;
+                        acc += xv[b];
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) w_s[r] = r < ne ? p.dinv[e0 + r] * (p.eps * xsum + (1.0 - p.eps) * acc) : 0.0;
+        }
+        if (blockIdx.x == 0)
+            for (int i = tid; i < rows + 1 && i < p.m2; i += THREADS) p.cB[i] = 0.0;  // last read before barrier 3 of step j - 1
+        __syncthreads();
+        // ---- B: first Gram-Schmidt pass, partial coefficients
+        dots(rows, newest, p.cA);
+        grid_sync(p.bar, G, gen);  // #1
+        // ---- C
+        for (int i = tid; i < rows; i += THREADS) c_s[i] = ldcg_d(p.cA + i);
+        if (j > p.j0 && tid < ne) p.Q[(size_t)newest * S + e0 + tid] = last_s[tid];  // normalise the published row (no reader left)
+        if (blockIdx.x == 0 && tid == 0) p.nrm[j & 1] = 0.0;
+        __syncthreads();
+        if (blockIdx.x == 0 && tid == 0) p.alpha[j] = c_s[newest];  // alpha_j = <M q_j, q_j>, taken before the orthogonalisation
+        project(rows, newest);
+        dots(rows, newest, p.cB);
+        grid_sync(p.bar, G, gen);  // #2
+        // ---- D: second pass, norm, publish the raw row
+        for (int i = tid; i < rows; i += THREADS) c_s[i] = ldcg_d(p.cB + i);
+        if (blockIdx.x == 0)
+            for (int i = tid; i < rows + 1 && i < p.m2; i += THREADS) p.cA[i] = 0.0;  // every CTA read it before barrier 2
+        __syncthreads();
+        project(rows, newest);
+        {
+            const double v = tid < EPB ? w_s[tid] : 0.0;
+            const double n2 = block_sum(v * v, red);
+            if (tid == 0) atomicAdd(&p.nrm[j & 1], n2);
+            if (tid < ne) p.Q[(size_t)(j + 2) * S + e0 + tid] = w_s[tid];
+        }
+        grid_sync(p.bar, G, gen);  // #3
+        // ---- E
+        const double beta = sqrt(ldcg_d(&p.nrm[j & 1]));
+        if (blockIdx.x == 0 && tid == 0) p.beta[j] = beta;
+        beta_prev = beta;
+        steps = j + 1;
+        if (beta < p.breakdown) break;  // Krylov space exhausted (the same value on every CTA)
+    }
+    // the last published row is still raw: normalise this CTA's slice (nobody reads it inside this launch)
+    if (steps > p.j0 && beta_prev >= p.breakdown && tid < ne) p.Q[(size_t)(steps + 1) * S + e0 + tid] = w_s[tid] / beta_prev;
+    if (blockIdx.x == 0 && tid == 0) *p.steps_done = steps;
+}
+
+}  // namespace lz
+}  // namespace us3d
+
+extern "C" {
+
+/* shared-memory capacity in basis rows for a problem of s segments and at most m steps (rows past it are read from L2) */
+static int lanczos_cap(int s, int m2, size_t *smem_out) {
+    const size_t fixed = sizeof(double) * ((size_t)s + m2 + 2 * lz::EPB + 8 * lz::EPB);
+    const size_t budget = 200 * 1024;
+    int cap = fixed + sizeof(double) * (lz::EPB + 1) < budget ? (int)((budget - fixed) / (sizeof(double) * (lz::EPB + 1))) : 0;
+    if (cap > m2) cap = m2;
+    *smem_out = fixed + sizeof(double) * (size_t)cap * (lz::EPB + 1);
+    return cap;
+}
+
+long long us3d_ncut_lanczos_workspace_bytes(int m) { return (long long)sizeof(double) * (2 * ((long long)m + 2) + 2) + 16; }
+
+int us3d_ncut_lanczos(const uint32_t *bits, int s, double eps, const double *dinv, double *Q, double *alpha, double *beta, int j0,
+                      int j1, int m, double breakdown, void *workspace, long long workspace_bytes, int *steps_done, void *stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    US3D_CHECK_ARG(s >= 3 && m >= 1 && j0 >= 0 && j0 <= j1 && j1 <= m, "ncut_lanczos: bad step range [%d, %d) of %d", j0, j1, m);
+    US3D_CHECK_ARG(workspace != nullptr && workspace_bytes >= us3d_ncut_lanczos_workspace_bytes(m), "ncut_lanczos: workspace too small");
+    const int G = ceil_div(s, lz::EPB);
+    US3D_CHECK_ARG(G <= num_sms(), "ncut_lanczos: %d segments need %d co-resident CTAs, the device has %d SMs", s, G, num_sms());
+    lz::Params p;
+    p.bits = bits; p.S = s; p.words = ceil_div(s, 32); p.eps = eps; p.dinv = dinv; p.Q = Q; p.alpha = alpha; p.beta = beta;
+    p.j0 = j0; p.j1 = j1; p.m2 = m + 2; p.breakdown = breakdown;
+    double *ws = (double *)workspace;
+    p.cA = ws; p.cB = ws + p.m2; p.nrm = ws + 2 * (size_t)p.m2; p.bar = (unsigned *)(p.nrm + 2);
+    p.steps_done = steps_done;
+    size_t smem = 0;
+    p.cap = lanczos_cap(s, p.m2, &smem);
+    US3D_CHECK_ARG(p.cap >= 2, "ncut_lanczos: %d segments do not fit the shared-memory layout", s);
+    if (j0 == 0) US3D_CUDA(cudaMemsetAsync(workspace, 0, (size_t)us3d_ncut_lanczos_workspace_bytes(m), st));
+    static bool attr_done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_done[dev]) {
+        US3D_CUDA(cudaFuncSetAttribute(lz::k_lanczos, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+        attr_done[dev] = true;
+    }
+    if (j0 == j1) return 0;
+    void *args[] = {&p};
+    US3D_CUDA(cudaLaunchCooperativeKernel((void *)lz::k_lanczos, dim3(G), dim3(lz::THREADS), args, smem, st));
+    US3D_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

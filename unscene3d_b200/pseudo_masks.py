@@ -156,6 +156,60 @@ def _lanczos_top_deflated(matvec, u1: torch.Tensor, max_steps: int, tol: float, 
     return u / u.norm()
 
 
+def _lanczos_device(graph: NCutGraph, dinv: torch.Tensor, u1: torch.Tensor, max_steps: int, tol: float, seed: int,
+                    min_steps: int = 512, segment: int = 32, breakdown: float = 1e-10, info: Optional[dict] = None) -> torch.Tensor:
+    """The recurrence of `_lanczos_top_deflated` with every step on the device (us3d_ncut_lanczos, one cooperative launch per
+    segment): the first launch runs `min_steps` steps (or to breakdown), later ones `segment` steps each; the host is touched
+    once per launch — the completed-step count — plus the small tridiagonal eigen-solves of the convergence test."""
+    S, dev = graph.n, graph.bits.device
+    st = _stream()
+    m = min(max_steps, S - 1)
+    Q = torch.zeros((m + 2, S), dtype=torch.float64, device=dev)
+    Q[0] = u1
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    q0 = torch.randn(S, generator=g, dtype=torch.float64).to(dev)
+    q0 = q0 - u1 * (u1 @ q0)
+    q0 = q0 - u1 * (u1 @ q0)
+    Q[1] = q0 / q0.norm()
+    alpha = torch.zeros(m, dtype=torch.float64, device=dev)
+    beta = torch.zeros(m, dtype=torch.float64, device=dev)
+    ws_bytes = int(lib.us3d_ncut_lanczos_workspace_bytes(m))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    done = torch.zeros(1, dtype=torch.int32, device=dev)
+    dinv = dinv.contiguous()
+    steps, launches = 0, 0
+    while steps < m:
+        j1 = min(m, min_steps if steps == 0 else steps + segment)
+        check(lib.us3d_ncut_lanczos(graph.bits.data_ptr(), S, float(graph.eps), dinv.data_ptr(), Q.data_ptr(), alpha.data_ptr(),
+                                    beta.data_ptr(), steps, j1, m, float(breakdown), ws.data_ptr(), ws_bytes, done.data_ptr(), st))
+        launches += 1
+        steps = int(done.item())
+        if steps < j1:  # the Krylov space is exhausted
+            break
+        if steps >= min_steps and steps < m:
+            a, b = alpha[:steps].cpu(), beta[:steps].cpu()
+            T = torch.diag(a) + torch.diag(b[: steps - 1], 1) + torch.diag(b[: steps - 1], -1)
+            evecs = torch.linalg.eigh(T)[1]
+            if float(b[steps - 1]) * float(evecs[-1, -3:].abs().max()) < tol:
+                break
+    a, b = alpha[:steps].cpu(), beta[:steps].cpu()
+    T = torch.diag(a) + torch.diag(b[: steps - 1], 1) + torch.diag(b[: steps - 1], -1)
+    evals, evecs = torch.linalg.eigh(T)
+    ritz = evecs[:, -1]
+    if info is not None:
+        info.update(steps=steps, beta=b.tolist(), ritz_values=evals[-4:].tolist(), launches=launches)
+    u = Q[1: steps + 1].T @ ritz.to(dev)
+    return u / u.norm()
+
+
+_fused_lanczos = {"on": True}
+
+
+def set_fused_lanczos(on: bool):
+    """Debugging switch: False drives the same recurrence from the host, one matvec launch per step."""
+    _fused_lanczos["on"] = bool(on)
+
+
 def second_smallest_eigenvector(graph: NCutGraph, max_steps: int = 4096, tol: float = 1e-10, seed: int = 0, info: Optional[dict] = None) -> torch.Tensor:
     """Eigenvector of the second smallest eigenvalue of (D - W) v = lambda D v, normalised v^T D v = 1 like
     scipy.linalg.eigh(D - A, D): Lanczos for the largest eigenpair of M = D^-1/2 W D^-1/2 (W x from the bit matrix on
@@ -163,6 +217,10 @@ def second_smallest_eigenvector(graph: NCutGraph, max_steps: int = 4096, tol: fl
     S, dev = graph.n, graph.bits.device
     st = _stream()
     dinv = graph.degree.rsqrt()
+    if _fused_lanczos["on"]:
+        u1 = graph.degree.sqrt()
+        u1 = u1 / u1.norm()
+        return dinv * _lanczos_device(graph, dinv, u1, max_steps, tol, seed, info=info)
     y = torch.empty(S, dtype=torch.float64, device=dev)
 
     def matvec(u):
