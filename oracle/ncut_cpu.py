@@ -34,6 +34,28 @@ def affinity(feats_a: torch.Tensor, feats_b: torch.Tensor, tau: float, eps: floa
     return A, np.diag(np.sum(A, axis=0))
 
 
+def cosine_sim(feats_k: torch.Tensor, feats_q: torch.Tensor):
+    """utils/freemask_utils.py:8-18 — NOT symmetric: every query row has its own minimum subtracted and its own maximum divided out."""
+    eps = 10e-10
+    key_feats = feats_k / (feats_k.norm(dim=1, keepdim=True) + eps)
+    queries = feats_q / (feats_q.norm(dim=1, keepdim=True) + eps)
+    attn = queries @ key_feats.T
+    attn = attn - attn.min(-1, keepdim=True)[0]
+    attn = attn / (attn.max(-1, keepdim=True)[0] + eps)
+    return attn
+
+
+def affinity_single(feats: torch.Tensor, tau: float, eps: float = 1e-5):
+    """Single-modality branch of get_affinity_matrix (:92-98): row-normalised cosine_sim of the L2-normalised features, then
+    normalize_mat, threshold; D = COLUMN sums of the (asymmetric) thresholded matrix.  scipy's eigh(D - A, D) reads the lower
+    triangle of A only."""
+    f = F.normalize(feats, p=2, dim=-1)
+    A = normalize_mat(cosine_sim(f, f).cpu().numpy())
+    A = A > tau
+    A = np.where(A.astype(float) == 0, eps, A)
+    return A, np.diag(np.sum(A, axis=0))
+
+
 def fiedler(A, D):
     _, vecs = eigh(D - A, D, subset_by_index=[1, 2])
     return vecs[:, 0].copy()
@@ -53,10 +75,15 @@ def connected_component_of(seed_id, fg_ids, connectivity):
 
 
 def separate_segments_max(bipartition, vec, unique_segments, seg_connectivity):
-    """Mode 'max' (:181-233), restated literally: foreground segments are visited in id order; a segment joins every
+    return separate_segments(bipartition, vec, unique_segments, seg_connectivity, "max")
+
+
+def separate_segments(bipartition, vec, unique_segments, seg_connectivity, mode="max"):
+    """:181-250, restated literally: foreground segments are visited in id order; a segment joins every
     existing blob that contains one of ITS listed neighbours (rows [c, *] of seg_connectivity, as stored — directed),
     blobs bridged by it are merged (the scan index still advances after a merge, as in the reference), otherwise
-    it opens a new blob; the blob containing the segment of argmax(vec) is returned."""
+    it opens a new blob.  'max': the blob containing the segment of argmax(vec); 'avg': the blob with the highest mean of vec;
+    'largest': the blob with most segments (first one on ties, np.argmax); 'all': every foreground segment."""
     ids = unique_segments.cpu().numpy()
     conn = seg_connectivity.cpu().numpy()
     nbrs = {int(s): set(conn[conn[:, 0] == s, 1].tolist()) for s in ids}
@@ -77,8 +104,17 @@ def separate_segments_max(bipartition, vec, unique_segments, seg_connectivity):
             pos += 1
         if not merged:
             blobs.append({c})
-    seed_id = int(ids[int(np.argmax(vec))])
-    return next(b for b in blobs if seed_id in b)
+    if mode == "max":
+        seed_id = int(ids[int(np.argmax(vec))])
+        return next(b for b in blobs if seed_id in b)
+    if mode == "avg":
+        means = [np.mean(vec[np.isin(ids, list(b))]) for b in blobs]
+        return blobs[int(np.argmax(means))]
+    if mode == "largest":
+        return blobs[int(np.argmax(np.array([len(b) for b in blobs])))]
+    if mode == "all":
+        return set(int(c) for c in ids[bipartition])
+    raise NotImplementedError(mode)
 
 
 def aggregate_features(encoded, segment_ids, seg_connectivity, mode="mean"):
@@ -104,8 +140,8 @@ def aggregate_features(encoded, segment_ids, seg_connectivity, mode="mean"):
 
 
 def unscene3d(feats_a, feats_b, unique_segments, seg_connectivity, affinity_tau=0.65, max_number_of_instances=20,
-              max_extent_ratio=0.8, eps=1e-5, min_segment_size=4, sign_hook=None, trace=None):
-    """Greedy NCut mask extraction over segments; returns bool [n_masks, S]."""
+              max_extent_ratio=0.8, eps=1e-5, min_segment_size=4, sign_hook=None, trace=None, separation_mode="max"):
+    """Greedy NCut mask extraction over segments; returns bool [n_masks, S].  feats_b = None: single-modality affinity."""
     S = len(unique_segments)
     if S < 3:
         return np.ones((1, S), dtype=bool)
@@ -113,13 +149,13 @@ def unscene3d(feats_a, feats_b, unique_segments, seg_connectivity, affinity_tau=
     masks, foreground = [], set()
     painting = torch.zeros(S)
     current = None
-    fa, fb = feats_a.clone(), feats_b.clone()
+    fa, fb = feats_a.clone(), (None if feats_b is None else feats_b.clone())
     for it in range(max_number_of_instances):
         if it > 0:
             painting = ((painting.view(S, 1) + current.view(S, 1).float()) > 0).float()
-            fa, fb = (1 - painting) * fa, (1 - painting) * fb
+            fa, fb = (1 - painting) * fa, (None if fb is None else (1 - painting) * fb)
             painting = painting.squeeze()
-        A, D = affinity(fa, fb, affinity_tau, eps)
+        A, D = affinity(fa, fb, affinity_tau, eps) if fb is not None else affinity_single(fa, affinity_tau, eps)
         pm = painting.bool().numpy()
         A[pm] = eps
         A[:, pm] = eps
@@ -131,7 +167,8 @@ def unscene3d(feats_a, feats_b, unique_segments, seg_connectivity, affinity_tau=
         bip = vec > vec.sum() / len(vec)
         if bip.sum() / len(bip) > max_extent_ratio:
             bip, vec = np.logical_not(bip), -vec
-        part = separate_segments_max(bip, vec, unique_segments, seg_connectivity)
+        part = (separate_segments_max(bip, vec, unique_segments, seg_connectivity) if separation_mode == "max"
+                else separate_segments(bip, vec, unique_segments, seg_connectivity, separation_mode))
         current = torch.from_numpy(np.isin(ids, list(part)))
         iou = len(part & foreground) / len(part)
         if iou > 0.5 or len(part) < min_segment_size:

@@ -30,6 +30,12 @@ def reference_functions(trace=None):
     body = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in WANTED]
     assert len(body) == len(WANTED), "reference file layout changed"
     ns = {"np": np, "torch": torch, "F": F, "eigh": eigh}
+    # cosine_sim / l2_sim of the single-modality branch live in utils/freemask_utils.py (which imports open3d, hdbscan, ME)
+    utils_file = os.path.join(os.path.dirname(os.path.dirname(REFERENCE_FILE)), "utils", "freemask_utils.py")
+    utree = ast.parse(open(utils_file).read(), utils_file)
+    ubody = [n for n in utree.body if isinstance(n, ast.FunctionDef) and n.name in ("cosine_sim", "l2_sim")]
+    assert len(ubody) == 2, "utils/freemask_utils.py layout changed"
+    exec(compile(ast.Module(body=ubody, type_ignores=[]), utils_file, "exec"), ns)
     exec(compile(ast.Module(body=body, type_ignores=[]), REFERENCE_FILE, "exec"), ns)
     if trace is not None:
         inner = ns["second_smallest_eigenvector"]
@@ -83,15 +89,16 @@ def make_case(n_segments=240, n_objects=8, noise=0.8, seed=7, points_per_segment
     return dict(segment_ids=segment_ids, feats_a=fa, feats_b=fb, seg_connectivity=conn, coords=coords)
 
 
-def run_reference(case, tau=0.65):
+def run_reference(case, tau=0.65, aggregation_mode="mean", separation_mode="max", single=False):
     trace = []
     ref = reference_functions(trace)
-    cfg = types.SimpleNamespace(freemask=types.SimpleNamespace(aggregation_mode="mean"))
+    cfg = types.SimpleNamespace(freemask=types.SimpleNamespace(aggregation_mode=aggregation_mode))
     agg_a, uniq = ref.aggregate_features(case["feats_a"], case["segment_ids"], case["seg_connectivity"], cfg)
     agg_b, _ = ref.aggregate_features(case["feats_b"], case["segment_ids"], case["seg_connectivity"], cfg)
-    A, D = ref.get_affinity_matrix((agg_a, agg_b), tau=tau, eps=1e-5)
-    masks = ref.unscene3d((agg_a, agg_b), uniq, case["seg_connectivity"], case["segment_ids"], case["coords"],
-                          torch.zeros_like(case["coords"]), affinity_tau=tau)
+    feats = agg_a if single else (agg_a, agg_b)
+    A, D = ref.get_affinity_matrix(feats, tau=tau, eps=1e-5)
+    masks = ref.unscene3d(feats, uniq, case["seg_connectivity"], case["segment_ids"], case["coords"],
+                          torch.zeros_like(case["coords"]), affinity_tau=tau, separation_mode=separation_mode)
     return dict(agg_a=agg_a.numpy(), agg_b=agg_b.numpy(), unique_segments=uniq.numpy(), affinity_on=(A == 1.0),
                 degree=np.diag(D).copy(), eigvecs=np.stack(trace), masks=masks)
 

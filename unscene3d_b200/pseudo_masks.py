@@ -34,8 +34,11 @@ from .engine.coords import _stream
 class NCutGraph:
     """Thresholded affinity W = eps 11^T + (1 - eps) B as a bit matrix, plus the degrees of the unpainted graph."""
 
-    def __init__(self, bits: torch.Tensor, degree: torch.Tensor, n: int, eps: float):
+    def __init__(self, bits: torch.Tensor, degree: torch.Tensor, n: int, eps: float, trivial_known: bool = True):
         self.bits, self.degree, self.n, self.eps = bits, degree, n, eps
+        # D = row sums of W: D^1/2 1 is the leading eigenvector of D^-1/2 W D^-1/2 and can be deflated.  False for the
+        # single-modality graph (degrees of the asymmetric thresholded matrix): the solver then takes the second Ritz pair.
+        self.trivial_known = trivial_known
 
     def dense(self) -> torch.Tensor:
         """float64 [S, S] (tests / debugging)."""
@@ -49,18 +52,24 @@ class NCutGraph:
 def aggregate_features(encoded_features: torch.Tensor, segment_ids: torch.Tensor, seg_connectivity: torch.Tensor, aggregation_mode: str = "mean"):
     """Per-segment mean of the rows that are not all-zero; segments without a valid row take the mean of the
     non-zero neighbours listed for the FIRST such segment (reference quirk, :387), else the global mean."""
-    if aggregation_mode != "mean":
-        raise NotImplementedError("only aggregation_mode='mean' is on the hot path (pseudo_masks/config/default.yaml)")
+    if aggregation_mode not in ("mean", "max"):
+        raise ValueError(f"aggregation_mode {aggregation_mode!r}: the reference knows 'mean' and 'max' (:366)")
     unique_segments, index = torch.unique(segment_ids, return_inverse=True)
     valid = torch.any(encoded_features != 0, dim=-1)
     S = unique_segments.shape[0]
     src, idx = encoded_features[valid].float().contiguous(), index[valid].contiguous().long()
-    agg = torch.empty((S, src.shape[1]), dtype=torch.float32, device=src.device)
-    acc = torch.zeros((S, src.shape[1]), dtype=torch.float64, device=src.device)
-    count = torch.zeros(S, dtype=torch.float32, device=src.device)
-    # fp64 sums, rounded once: the affinity threshold downstream must not see the order of the atomics
-    check(lib.us3d_segment_mean_f64(src.data_ptr(), idx.data_ptr(), src.shape[0], src.shape[1], S, acc.data_ptr(), agg.data_ptr(),
-                                    count.data_ptr(), _stream()))
+    if aggregation_mode == "max":
+        # per-segment maximum over the valid rows (order-independent, exact); segments without a valid row stay zero
+        agg = torch.full((S, src.shape[1]), float("-inf"), dtype=torch.float32, device=src.device)
+        agg.scatter_reduce_(0, idx[:, None].expand(-1, src.shape[1]), src, "amax", include_self=True)
+        agg[torch.isinf(agg)] = 0.0
+    else:
+        agg = torch.empty((S, src.shape[1]), dtype=torch.float32, device=src.device)
+        acc = torch.zeros((S, src.shape[1]), dtype=torch.float64, device=src.device)
+        count = torch.zeros(S, dtype=torch.float32, device=src.device)
+        # fp64 sums, rounded once: the affinity threshold downstream must not see the order of the atomics
+        check(lib.us3d_segment_mean_f64(src.data_ptr(), idx.data_ptr(), src.shape[0], src.shape[1], S, acc.data_ptr(), agg.data_ptr(),
+                                        count.data_ptr(), _stream()))
     zero = torch.all(agg == 0, dim=-1)
     if bool(zero.any()):
         first_zero = unique_segments[zero][0]
@@ -75,9 +84,10 @@ def aggregate_features(encoded_features: torch.Tensor, segment_ids: torch.Tensor
 
 
 def get_affinity_matrix(feats, tau: float = 0.15, eps: float = 1e-5, painted: Optional[torch.Tensor] = None) -> NCutGraph:
-    """Two-modality affinity (feats = (feats_a [S, Da], feats_b [S, Db]) fp32 CUDA) -> thresholded bit graph."""
+    """Affinity -> thresholded bit graph.  feats = (feats_a [S, Da], feats_b [S, Db]) fp32 CUDA: the configured two-modality
+    path (fused kernels); a single tensor: the reference's single-modality branch."""
     if not isinstance(feats, tuple):
-        raise NotImplementedError("single-modality affinity (row-normalised cosine_sim) is not on the configured path")
+        return _affinity_single(feats, tau, eps, painted)
     fa, fb = [f.float().contiguous() for f in feats]
     S = fa.shape[0]
     dev = fa.device
@@ -99,8 +109,38 @@ def get_affinity_matrix(feats, tau: float = 0.15, eps: float = 1e-5, painted: Op
     return NCutGraph(bits, degree, S, eps)
 
 
+def _affinity_single(feats: torch.Tensor, tau: float, eps: float, painted: Optional[torch.Tensor]) -> NCutGraph:
+    """Single-modality branch of get_affinity_matrix (:92-98; off the configured path, device tensor ops): the row-normalised
+    cosine_sim (utils/freemask_utils.py:8-18) of the L2-normalised features is NOT symmetric; the reference thresholds it as
+    it is, takes D from the COLUMN sums, and scipy's eigh(D - A, D) then reads the lower triangle of A only — so the graph is
+    the lower triangle mirrored, with the degrees of the full asymmetric matrix."""
+    f = torch.nn.functional.normalize(feats.float(), p=2, dim=-1)
+    k = f / (f.norm(dim=1, keepdim=True) + 10e-10)
+    A = k @ k.T
+    A = A - A.min(-1, keepdim=True)[0]
+    A = A / (A.max(-1, keepdim=True)[0] + 10e-10)
+    if bool((A > 0).any()):
+        A = A - A[A != 0].min()
+    A = A.clamp_min(0.0)
+    A = A / (A.max() + 1e-5)
+    on = A > tau
+    S = on.shape[0]
+    degree = torch.where(on, 1.0, float(eps)).double().sum(0)
+    low = torch.tril(on)
+    sym = low | low.T
+    if painted is not None:
+        pb = painted.bool()
+        sym = sym & ~pb[:, None] & ~pb[None, :]
+    words = (S + 31) // 32
+    pad = torch.zeros((S, words * 32), dtype=torch.int64, device=on.device)
+    pad[:, :S] = sym
+    bits = (pad.view(S, words, 32) << torch.arange(32, device=on.device)).sum(-1)
+    bits = torch.where(bits >= 2 ** 31, bits - 2 ** 32, bits).to(torch.int32).contiguous()
+    return NCutGraph(bits, degree.contiguous(), S, eps, trivial_known=False)
+
+
 def _lanczos_top_deflated(matvec, u1: torch.Tensor, max_steps: int, tol: float, seed: int, check_every: int = 20,
-                          min_steps: int = 512, breakdown: float = 1e-10, info: Optional[dict] = None) -> torch.Tensor:
+                          min_steps: int = 512, breakdown: float = 1e-10, info: Optional[dict] = None, pick: int = -1) -> torch.Tensor:
     """Unit eigenvector of the LARGEST eigenvalue of the symmetric operator `matvec` restricted to the complement of the
     known unit eigenvector `u1` (fp64, full re-orthogonalisation twice per step, u1 included in the basis).
 
@@ -149,7 +189,7 @@ def _lanczos_top_deflated(matvec, u1: torch.Tensor, max_steps: int, tol: float, 
     a, b = alpha[:steps].cpu(), beta[:steps].cpu()
     T = torch.diag(a) + torch.diag(b[: steps - 1], 1) + torch.diag(b[: steps - 1], -1)
     evals, evecs = torch.linalg.eigh(T)
-    ritz = evecs[:, -1]
+    ritz = evecs[:, pick]
     if info is not None:
         info.update(steps=steps, beta=b.tolist(), ritz_values=evals[-4:].tolist())
     u = Q[1: steps + 1].T @ ritz.to(dev)
@@ -157,7 +197,7 @@ def _lanczos_top_deflated(matvec, u1: torch.Tensor, max_steps: int, tol: float, 
 
 
 def _lanczos_device(graph: NCutGraph, dinv: torch.Tensor, u1: torch.Tensor, max_steps: int, tol: float, seed: int,
-                    min_steps: int = 512, segment: int = 32, breakdown: float = 1e-10, info: Optional[dict] = None) -> torch.Tensor:
+                    min_steps: int = 512, segment: int = 32, breakdown: float = 1e-10, info: Optional[dict] = None, pick: int = -1) -> torch.Tensor:
     """The recurrence of `_lanczos_top_deflated` with every step on the device (us3d_ncut_lanczos, one cooperative launch per
     segment): the first launch runs `min_steps` steps (or to breakdown), later ones `segment` steps each; the host is touched
     once per launch — the completed-step count — plus the small tridiagonal eigen-solves of the convergence test."""
@@ -195,7 +235,7 @@ def _lanczos_device(graph: NCutGraph, dinv: torch.Tensor, u1: torch.Tensor, max_
     a, b = alpha[:steps].cpu(), beta[:steps].cpu()
     T = torch.diag(a) + torch.diag(b[: steps - 1], 1) + torch.diag(b[: steps - 1], -1)
     evals, evecs = torch.linalg.eigh(T)
-    ritz = evecs[:, -1]
+    ritz = evecs[:, pick]
     if info is not None:
         info.update(steps=steps, beta=b.tolist(), ritz_values=evals[-4:].tolist(), launches=launches)
     u = Q[1: steps + 1].T @ ritz.to(dev)
@@ -217,10 +257,13 @@ def second_smallest_eigenvector(graph: NCutGraph, max_steps: int = 4096, tol: fl
     S, dev = graph.n, graph.bits.device
     st = _stream()
     dinv = graph.degree.rsqrt()
+    # with the leading eigenvector known it is deflated and the largest remaining Ritz pair is the answer; otherwise nothing is
+    # deflated (a zero row takes its place in the basis) and the second largest pair is taken
+    pick = -1 if graph.trivial_known else -2
     if _fused_lanczos["on"]:
         u1 = graph.degree.sqrt()
-        u1 = u1 / u1.norm()
-        return dinv * _lanczos_device(graph, dinv, u1, max_steps, tol, seed, info=info)
+        u1 = u1 / u1.norm() if graph.trivial_known else torch.zeros_like(u1)
+        return dinv * _lanczos_device(graph, dinv, u1, max_steps, tol, seed, info=info, pick=pick)
     y = torch.empty(S, dtype=torch.float64, device=dev)
 
     def matvec(u):
@@ -230,16 +273,19 @@ def second_smallest_eigenvector(graph: NCutGraph, max_steps: int = 4096, tol: fl
         return dinv * y
 
     u1 = graph.degree.sqrt()
-    u1 = u1 / u1.norm()
-    return dinv * _lanczos_top_deflated(matvec, u1, max_steps, tol, seed, info=info)
+    u1 = u1 / u1.norm() if graph.trivial_known else torch.zeros_like(u1)
+    return dinv * _lanczos_top_deflated(matvec, u1, max_steps, tol, seed, info=info, pick=pick)
 
 
 def separate_segments(bipartition: np.ndarray, vec: np.ndarray, unique_segments: torch.Tensor, seg_connectivity: torch.Tensor, mode: str = "max"):
-    """Blob of connected foreground segments containing argmax(vec) — the reference's incremental blob growing
-    (:181-233) including its scan-index behaviour after a merge, on the host like the reference."""
-    if mode != "max":
-        raise NotImplementedError("separation_mode='max' is the configured mode (pseudo_masks/config/default.yaml:64-74)")
+    """The reference's incremental blob growing (:181-233) including its scan-index behaviour after a merge, on the host like
+    the reference; 'max' (configured, pseudo_masks/config/default.yaml:64-74): the blob containing argmax(vec); 'avg': the blob
+    with the highest mean of vec; 'largest': the blob with most segments; 'all': every foreground segment (:234-250)."""
+    if mode not in ("max", "avg", "largest", "all"):
+        raise NotImplementedError(mode)
     ids = unique_segments.cpu().numpy()
+    if mode == "all":
+        return set(int(c) for c in ids[bipartition])
     conn = seg_connectivity.cpu().numpy()
     order = np.argsort(conn[:, 0], kind="stable")
     starts = np.searchsorted(conn[order, 0], ids, side="left")
@@ -261,6 +307,10 @@ def separate_segments(bipartition: np.ndarray, vec: np.ndarray, unique_segments:
             pos += 1
         if not merged:
             blobs.append({c})
+    if mode == "avg":
+        return blobs[int(np.argmax([np.mean(vec[np.isin(ids, list(b))]) for b in blobs]))]
+    if mode == "largest":
+        return blobs[int(np.argmax(np.array([len(b) for b in blobs])))]
     seed_id = int(ids[int(np.argmax(vec))])
     return next(b for b in blobs if seed_id in b)
 
@@ -268,8 +318,10 @@ def separate_segments(bipartition: np.ndarray, vec: np.ndarray, unique_segments:
 def unscene3d(aggregated_features, unique_segments, seg_connectivity, affinity_tau=0.65, max_number_of_instances=20,
               max_extent_ratio=0.8, eps=1e-5, min_segment_size=4, separation_mode="max",
               sign_rule: Union[str, Callable[[np.ndarray], float]] = "minority", trace=None) -> np.ndarray:
-    """Greedy NCut extraction; aggregated_features = (feats_a, feats_b) per segment (CUDA).  Returns bool [M, S]."""
-    fa, fb = aggregated_features
+    """Greedy NCut extraction; aggregated_features = (feats_a, feats_b) per segment (CUDA), or one tensor for the
+    single-modality affinity.  Returns bool [M, S]."""
+    single = not isinstance(aggregated_features, tuple)
+    fa, fb = (aggregated_features, aggregated_features) if single else aggregated_features
     S = len(unique_segments)
     if S < 3:
         return np.ones((1, S), dtype=bool)
@@ -284,7 +336,7 @@ def unscene3d(aggregated_features, unique_segments, seg_connectivity, affinity_t
             painting = painting | current
             keep = (~painting).float()[:, None]
             fa, fb = keep * fa, keep * fb
-        graph = get_affinity_matrix((fa, fb), tau=affinity_tau, eps=eps, painted=painting)
+        graph = get_affinity_matrix(fa if single else (fa, fb), tau=affinity_tau, eps=eps, painted=painting)
         vec = second_smallest_eigenvector(graph).cpu().numpy()
         if callable(sign_rule):
             vec = vec * sign_rule(vec)
