@@ -16,33 +16,6 @@ import numpy as np
 import torch
 
 
-def make_c4_scene(n_points=300_000, n_segments=2048, seed=0):
-    """SURVEY §8(d) C4: per-segment random centres (sigma_within = 0.3) so that the thresholded affinity at tau = 0.6 is non-trivial;
-    segments are grouped into ~40 'objects' whose centres are correlated, adjacency = ring + random chords inside an object."""
-    rng = np.random.default_rng(seed)
-    n_obj = 40
-    obj_of = rng.integers(0, n_obj, n_segments)
-    ca = rng.normal(size=(n_obj, 384)).astype(np.float32)[obj_of] + 0.35 * rng.normal(size=(n_segments, 384)).astype(np.float32)
-    cb = rng.normal(size=(n_obj, 96)).astype(np.float32)[obj_of] + 0.35 * rng.normal(size=(n_segments, 96)).astype(np.float32)
-    seg = rng.integers(0, n_segments, n_points)
-    seg[:n_segments] = np.arange(n_segments)
-    fa = ca[seg] + 0.3 * rng.normal(size=(n_points, 384)).astype(np.float32)
-    fb = cb[seg] + 0.3 * rng.normal(size=(n_points, 96)).astype(np.float32)
-    edges = []
-    for o in range(n_obj):
-        members = np.nonzero(obj_of == o)[0]
-        if len(members) < 2:
-            continue
-        nxt = np.roll(members, -1)
-        edges.append(np.stack([members, nxt], 1))
-        extra = rng.integers(0, len(members), (len(members), 2))
-        edges.append(members[extra])
-    e = np.concatenate(edges)
-    e = e[e[:, 0] != e[:, 1]]
-    e = np.unique(np.concatenate([e, e[:, ::-1]]), axis=0)
-    return seg.astype(np.int64), fa, fb, e.astype(np.int64)
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--points", type=int, default=300_000)
@@ -54,6 +27,7 @@ def main():
     args = ap.parse_args()
     import unscene3d_b200  # noqa: F401
     from unscene3d_b200 import pseudo_masks as pm
+    from unscene3d_b200.synthetic import make_ncut_scene as make_c4_scene
 
     seg, fa, fb, conn = make_c4_scene(args.points, args.segments)
     dev = torch.device("cuda")

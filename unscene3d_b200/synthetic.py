@@ -182,3 +182,30 @@ def level_sizes(coords: np.ndarray, levels: int = 5):
         key = (q[:, 0] << 54) | ((q[:, 1] + (1 << 17)) << 36) | ((q[:, 2] + (1 << 17)) << 18) | (q[:, 3] + (1 << 17))
         out.append(int(np.unique(key).shape[0]))
     return out
+
+
+def make_ncut_scene(n_points=300_000, n_segments=2048, seed=0):
+    """SURVEY §8(d) C4: per-segment random centres (sigma_within = 0.3) so that the thresholded affinity at tau = 0.6 is non-trivial;
+    segments are grouped into ~40 'objects' whose centres are correlated, adjacency = ring + random chords inside an object."""
+    rng = np.random.default_rng(seed)
+    n_obj = 40
+    obj_of = rng.integers(0, n_obj, n_segments)
+    ca = rng.normal(size=(n_obj, 384)).astype(np.float32)[obj_of] + 0.35 * rng.normal(size=(n_segments, 384)).astype(np.float32)
+    cb = rng.normal(size=(n_obj, 96)).astype(np.float32)[obj_of] + 0.35 * rng.normal(size=(n_segments, 96)).astype(np.float32)
+    seg = rng.integers(0, n_segments, n_points)
+    seg[:n_segments] = np.arange(n_segments)
+    fa = ca[seg] + 0.3 * rng.normal(size=(n_points, 384)).astype(np.float32)
+    fb = cb[seg] + 0.3 * rng.normal(size=(n_points, 96)).astype(np.float32)
+    edges = []
+    for o in range(n_obj):
+        members = np.nonzero(obj_of == o)[0]
+        if len(members) < 2:
+            continue
+        nxt = np.roll(members, -1)
+        edges.append(np.stack([members, nxt], 1))
+        extra = rng.integers(0, len(members), (len(members), 2))
+        edges.append(members[extra])
+    e = np.concatenate(edges)
+    e = e[e[:, 0] != e[:, 1]]
+    e = np.unique(np.concatenate([e, e[:, ::-1]]), axis=0)
+    return seg.astype(np.int64), fa, fb, e.astype(np.int64)
