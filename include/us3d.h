@@ -314,6 +314,19 @@ long long us3d_ncut_lanczos_workspace_bytes(int m);
 int us3d_ncut_lanczos(const uint32_t *bits, int s, double eps, const double *dinv, double *Q, double *alpha, double *beta, int j0,
                       int j1, int m, double breakdown, void *workspace, long long workspace_bytes, int *steps_done, void *stream);
 
+/* ---------------------------------------------------------------- tri-plane projection (noise-robust loss)
+ * custom_cuda_utils.project_sparse_voxels_to_planes[_backward] (utils/cuda_utils/cuda_utils.cpp:26-53, kernels
+ * cuda_utils_kernel.cu:371-433, 496-556; callers models/noise_robust_loss.py:28-31, 67-69).  coords int32 [n, 4] (batch, x, y, z)
+ * centred at zero; pred / tgt float [n, inst]; planes float [x_dim, y_dim, inst], [x_dim, z_dim, inst], [y_dim, z_dim, inst]
+ * and int32 counts [x_dim, y_dim] ... are ACCUMULATED into (the caller zero-fills, as the reference's Python does).  Voxels
+ * with a coordinate >= its dim are skipped (the reference sizes the planes by the maximum coordinate).  Backward: grad[n, inst]
+ * = mean of the non-zero plane gradients at the voxel's three cells; skipped voxels are left untouched.                  */
+int us3d_project_voxels_to_planes(const int32_t *coords, const float *pred, const float *tgt, int n, int inst, int x_dim, int y_dim,
+                                  int z_dim, float *pred_xy, float *pred_xz, float *pred_yz, float *tgt_xy, float *tgt_xz,
+                                  float *tgt_yz, int32_t *num_xy, int32_t *num_xz, int32_t *num_yz, void *stream);
+int us3d_project_voxels_to_planes_bwd(const int32_t *coords, int n, int inst, int x_dim, int y_dim, int z_dim, const float *grad_xy,
+                                      const float *grad_xz, const float *grad_yz, float *grad, void *stream);
+
 /* ---------------------------------------------------------------- FreeMask-style pseudo masks (A22)
  * Segment branch of the scene loop of pseudo_masks/freemask_main.py:203-417.
  *   soft_masks:     soft[s,s] = cosine_sim(f, f) (utils/freemask_utils.py:8-18: rows L2-normalised with eps 1e-9, Gram matrix,

@@ -5,6 +5,8 @@ only; the outputs are git-ignored and travel to the GPU box with the snapshot). 
   (:72-176 kernel, :178-215 host wrapper), compiled for sm_100a straight from the reference tree together with
   oracle/fps_ref_shim.cu (an extern "C" entry around the reference's own host wrapper).  It needs ATen only for
   `at::cuda::getCurrentCUDAStream()`, so it links against the torch libraries of this image.
+* `libplanes_ref.so`: the reference's tri-plane projection functions, utils/cuda_utils/cuda_utils_kernel.cu (:371-600), compiled
+  the same way with oracle/planes_ref_shim.cu (needs --expt-relaxed-constexpr: the file calls std::sqrt in a kernel; ~2 min).
 * `reference/`: the UNMODIFIED reference Python files of the hot path (models/, pointnet2_utils.py, the pseudo-mask
   functions, the trainer and its entry point) staged so that the `-m gpu` tests can execute them on the CUDA shim on the GPU
   box, where /root/reference does not exist.  Nothing here is committed: the reference's sources stay out of the history.
@@ -51,6 +53,29 @@ def build_fps(verbose=False):
     return lib
 
 
+def build_planes(verbose=False):
+    import sysconfig
+
+    import torch  # noqa: F401
+    from torch.utils import cpp_extension as ce
+
+    src = os.path.join(REFERENCE, "utils/cuda_utils/cuda_utils_kernel.cu")
+    shim = os.path.join(HERE, "planes_ref_shim.cu")
+    lib = os.path.join(OUT, "libplanes_ref.so")
+    if os.path.exists(lib) and os.path.getmtime(lib) > os.path.getmtime(shim):
+        return lib
+    tlib = ce.library_paths(device_type="cuda")[0]
+    cmd = [NVCC, "-shared", "-Xcompiler", "-fPIC", "-O2", "-std=c++17", "--expt-relaxed-constexpr", "-w", "-gencode",
+           "arch=compute_100a,code=sm_100a", "-I", os.path.join(REFERENCE, "utils/cuda_utils"), "-I", sysconfig.get_paths()["include"]]
+    for p in ce.include_paths(device_type="cuda"):
+        cmd += ["-I", p]
+    cmd += [src, shim, "-o", lib, "-L", tlib, "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch", "-Xlinker", "-rpath," + tlib]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    subprocess.run(cmd, check=True)
+    return lib
+
+
 def stage_reference():
     dst_root = os.path.join(OUT, "reference")
     for rel in STAGED:
@@ -71,7 +96,12 @@ def build(verbose=False):
     if not os.path.isdir(REFERENCE):
         return None
     os.makedirs(OUT, exist_ok=True)
-    return build_fps(verbose), stage_reference()
+    out = [build_fps(verbose), stage_reference()]
+    try:  # ~5 minutes of nvcc (torch/extension.h); the GPU tests skip the reference-kernel comparison when it is absent
+        out.append(build_planes(verbose))
+    except Exception as e:  # noqa: BLE001
+        print(f"oracle/_ref: libplanes_ref.so not built ({e})", file=sys.stderr)
+    return tuple(out)
 
 
 if __name__ == "__main__":

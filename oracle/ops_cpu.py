@@ -195,3 +195,44 @@ def as_module_tree():
     ext.furthest_point_sampling = _fps_tensor
     pn._ext = ext
     return {"torch_scatter": ts, "pointnet2": pn, "pointnet2._ext": ext}
+
+
+def project_voxels_to_planes(coords, pred, tgt, dims):
+    """utils/cuda_utils/cuda_utils_kernel.cu:371-433 restated with numpy: sums of predictions / targets and voxel counts per cell of
+    the xy, xz and yz planes.  coords int [n, 4] (batch, x, y, z) centred at zero; dims = (x_dim, y_dim, z_dim) = the MAXIMUM
+    coordinates (models/noise_robust_loss.py:84): voxels with a coordinate >= its dim are skipped (:392)."""
+    import numpy as np
+
+    c = np.asarray(coords)[:, 1:].astype(np.int64)
+    p, t = np.asarray(pred, dtype=np.float64), np.asarray(tgt, dtype=np.float64)
+    xd, yd, zd = (int(d) for d in dims)
+    inst = p.shape[1]
+    ok = (c >= 0).all(1) & (c[:, 0] < xd) & (c[:, 1] < yd) & (c[:, 2] < zd)
+    c, p, t = c[ok], p[ok], t[ok]
+    out = {}
+    for name, (a, b), (da, db) in (("xy", (0, 1), (xd, yd)), ("xz", (0, 2), (xd, zd)), ("yz", (1, 2), (yd, zd))):
+        cell = c[:, a] * db + c[:, b]
+        num = np.bincount(cell, minlength=da * db).reshape(da, db)
+        ps, ts = np.zeros((da * db, inst)), np.zeros((da * db, inst))
+        np.add.at(ps, cell, p)
+        np.add.at(ts, cell, t)
+        out[name] = (ps.reshape(da, db, inst), ts.reshape(da, db, inst), num.astype(np.int32))
+    return out
+
+
+def project_voxels_to_planes_bwd(coords, grads, dims, n_inst):
+    """cuda_utils_kernel.cu:496-556: per voxel and instance the mean of the non-zero plane gradients at its three cells
+    (grads = dict xy / xz / yz of float [da, db, inst]); skipped voxels keep 0."""
+    import numpy as np
+
+    c = np.asarray(coords)[:, 1:].astype(np.int64)
+    xd, yd, zd = (int(d) for d in dims)
+    ok = (c >= 0).all(1) & (c[:, 0] < xd) & (c[:, 1] < yd) & (c[:, 2] < zd)
+    out = np.zeros((c.shape[0], n_inst), dtype=np.float32)
+    cc = c[ok]
+    g = [np.asarray(grads["xy"], dtype=np.float32)[cc[:, 0], cc[:, 1]], np.asarray(grads["xz"], dtype=np.float32)[cc[:, 0], cc[:, 2]],
+         np.asarray(grads["yz"], dtype=np.float32)[cc[:, 1], cc[:, 2]]]
+    cnt = sum((x != 0).astype(np.int32) for x in g)
+    s = (g[0] + g[1]) + g[2]
+    out[ok] = np.where(cnt > 0, s / np.maximum(cnt, 1).astype(np.float32), 0.0).astype(np.float32)
+    return out

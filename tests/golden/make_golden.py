@@ -173,9 +173,10 @@ def unpack_attention(gold):
 
 
 def run_mask3d_case(models_pkg, me, matcher, device="cpu", criterion_cls=None, attn_record=None, attn_override=None,
-                    attn_mismatches=None):
-    """Full self-training step (Mask3D forward, Hungarian matching, set criterion, backward)."""
-    coords, feats, raw, p2s, targets = mask3d_inputs()
+                    attn_mismatches=None, inputs=None):
+    """Full self-training step (Mask3D forward, Hungarian matching, set criterion, backward).  `inputs` replaces the small
+    fixture scene (coords [N, 4] int32 numpy, feats, raw coordinates, point2segment list, targets list)."""
+    coords, feats, raw, p2s, targets = inputs if inputs is not None else mask3d_inputs()
     backbone = models_pkg.res16unet.Res16UNet34C(3, 20, Cfg(), D=3, out_fpn=True)
     net = models_pkg.mask3d.Mask3D(type("C", (), {"backbone": backbone})(), **MASK3D_KW)
     net.load_state_dict(deterministic_state(net, 7))

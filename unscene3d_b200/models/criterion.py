@@ -3,9 +3,9 @@
 semantics: matcher -> weighted cross-entropy over (num_classes + no-object) -> per-scene sigmoid-CE + dice on the
 matched masks (optional DropLoss IoU gating) -> the same again for every auxiliary decoder output.
 
-The tri-plane noise-robust term (models/noise_robust_loss.py) is only evaluated when its weight is non-zero
-(models/criterion.py:170); the self-training configuration keeps it at 0 (conf/matcher/hungarian_matcher.yaml:6),
-and this implementation refuses a non-zero weight instead of silently ignoring it.
+The tri-plane noise-robust term (models/noise_robust_loss.py over libus3d's projection kernels) is only evaluated when its
+weight is non-zero (models/criterion.py:170); the self-training configuration keeps it at 0
+(conf/matcher/hungarian_matcher.yaml:6).
 """
 import torch
 import torch.distributed as dist
@@ -44,6 +44,9 @@ class SetCriterion(nn.Module):
         self.register_buffer("empty_weight", empty_weight)
         self.num_points, self.oversample_ratio, self.importance_sample_ratio = num_points, oversample_ratio, importance_sample_ratio
         self.directions = directions
+        from .noise_robust_loss import ProjectionMaskLoss  # binds `custom_cuda_utils` like the reference (models/criterion.py:19, 136)
+
+        self.noise_robust_projection_loss = ProjectionMaskLoss(directions=directions)
 
     def loss_labels(self, outputs, targets, indices, num_masks, mask_type, coords=None):
         logits = outputs["pred_logits"].float()
@@ -54,14 +57,21 @@ class SetCriterion(nn.Module):
         return {"loss_ce": F.cross_entropy(logits.transpose(1, 2), target_classes, self.empty_weight, ignore_index=253)}
 
     def loss_masks(self, outputs, targets, indices, num_masks, mask_type="masks", coords=None):
-        if self.weight_dict.get("loss_noise_robust", 0) != 0:
-            raise NotImplementedError("the tri-plane noise-robust loss (cost_noise_robust != 0) is not built")
+        use_robust = self.weight_dict.get("loss_noise_robust", 0) != 0
         ce, dice, robust = [], [], []
         core = type(self).mask_loss_core or _cuda_mask_losses
         for b, (map_id, target_id) in enumerate(indices):
             logits = outputs["pred_masks"][b]                 # [S, Q]
             tgt_all = targets[b][mask_type]                   # [T_all, S]
-            robust.append(torch.as_tensor(0.0, dtype=torch.float32, device=logits.device))
+            if use_robust:  # models/criterion.py:170-179: the matched masks at point resolution, projected onto the three planes
+                pred = logits[:, map_id].T
+                if coords.shape[0] != pred.shape[1]:
+                    pred = pred[:, targets[b]["point2segment"]]
+                scene = coords[:, 0] == b
+                batch_loss, all_shape = self.noise_robust_projection_loss(pred, targets[b]["masks"][target_id].float(), coords[scene])
+                robust.append(batch_loss / all_shape)
+            else:
+                robust.append(torch.as_tensor(0.0, dtype=torch.float32, device=logits.device))
             if self.num_points != -1:  # sub-sample the points shared by all masks (models/criterion.py:184-191)
                 pidx = torch.randperm(tgt_all.shape[1], device=tgt_all.device)[:int(self.num_points * tgt_all.shape[1])]
                 logits, tgt_all = logits[pidx], tgt_all[:, pidx]
