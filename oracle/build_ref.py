@@ -27,7 +27,8 @@ STAGED = [
     "models", "third_party/pointnet2/pointnet2_utils.py", "third_party/pointnet2/pytorch_utils.py",
     "pseudo_masks/unscene3d_pseudo_main.py", "pseudo_masks/freemask_main.py", "utils/freemask_utils.py", "utils/pc_utils.py",
     "utils/utils.py", "utils/kfold.py", "utils/votenet_utils", "datasets/utils.py", "trainer/trainer.py", "trainer/__init__.py",
-    "main_instance_segmentation.py", "conf", "utils/cuda_utils/cuda_utils.py", "utils/cuda_utils/raycast_image.py",
+    "main_instance_segmentation.py", "conf", "benchmark", "models/metrics", "utils/point_cloud_utils.py", "datasets/scannet200",
+    "datasets/__init__.py", "utils/__init__.py", "utils/cuda_utils/cuda_utils.py", "utils/cuda_utils/raycast_image.py",
     "models/noise_robust_loss.py",
 ]
 

@@ -209,3 +209,34 @@ def make_ncut_scene(n_points=300_000, n_segments=2048, seed=0):
     e = e[e[:, 0] != e[:, 1]]
     e = np.unique(np.concatenate([e, e[:, ::-1]]), axis=0)
     return seg.astype(np.int64), fa, fb, e.astype(np.int64)
+
+
+class SyntheticFreemaskDataset:
+    """Dataset stand-in with the sample layout of the reference's datasets/freemask_semseg.py (what FreeMaskVoxelizeCollate /
+    freemask_voxelize consume, datasets/utils.py:370-404): (coordinates float64 [P, 3] in metres, features float32 [P, 3 colour
+    + 3 raw xyz], freemasks int64 [P, 2 + T] = (label, T pseudo-mask columns, segment id), scene name, raw colours, raw normals,
+    raw coordinates, index, segment connectivity).  Selected from the unmodified conf/ tree with
+    `data.train_dataset._target_=unscene3d_b200.synthetic.SyntheticFreemaskDataset`; every other key of the dataset node is
+    accepted and ignored."""
+
+    def __init__(self, n_scenes: int = 4, n_voxels: int = 20000, num_masks: int = 8, voxel_size: float = 0.02, seed0: int = 0, mode="train",
+                 **unused):
+        self.n_scenes, self.n_voxels, self.num_masks, self.voxel_size, self.seed0 = int(n_scenes), int(n_voxels), int(num_masks), voxel_size, int(seed0)
+        self.mode = mode
+        self.label_info = {0: {"name": "background", "validation": True, "color": [0, 0, 0]},
+                           1: {"name": "foreground", "validation": True, "color": [255, 0, 0]}}
+        self._cache = {}
+
+    def __len__(self):
+        return self.n_scenes
+
+    def __getitem__(self, idx):
+        idx = int(idx) % self.n_scenes
+        if idx not in self._cache:
+            s = make_scene(self.n_voxels, seed=self.seed0 + idx, with_masks=True, num_masks=self.num_masks)
+            xyz = (s.coords.astype(np.float64) + 0.5) * self.voxel_size          # one point per voxel, at the voxel centre
+            feats = np.concatenate([s.colors, xyz.astype(np.float32)], 1).astype(np.float32)
+            fm = np.concatenate([np.zeros((s.n, 1), np.int64), s.masks.T.astype(np.int64), s.point2segment[:, None].astype(np.int64)], 1)
+            conn = np.concatenate([s.adjacency, s.adjacency[:, ::-1]]).astype(np.int64)
+            self._cache[idx] = (xyz, feats, fm, f"synthetic{self.seed0 + idx:04d}", s.colors.copy(), np.zeros_like(s.colors), xyz.copy(), idx, conn)
+        return self._cache[idx]
