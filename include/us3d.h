@@ -314,6 +314,14 @@ long long us3d_ncut_lanczos_workspace_bytes(int m);
 int us3d_ncut_lanczos(const uint32_t *bits, int s, double eps, const double *dinv, double *Q, double *alpha, double *beta, int j0,
                       int j1, int m, double breakdown, void *workspace, long long workspace_bytes, int *steps_done, void *stream);
 
+/* ---------------------------------------------------------------- Felzenszwalb mesh over-segmentation
+ * HOST function.  felzenszwalb_cpp.segment_mesh (utils/cpp_utils/segmentator.cpp:17-262; callers datasets/freemask_semseg.py:212,
+ * pseudo_masks/datasets/scannet.py:182): vertices / colors float[n_verts][3], faces int32[n_faces][3] -> comps int32[n_verts]
+ * (segment ids 0..S-1 in the order of their representative vertices) and the sorted distinct directed pairs of adjacent segments
+ * int32[<= cap][2].  Returns the number of pairs (the first `cap` are written) or a negative error code.                 */
+int us3d_felzenszwalb_segment_h(const float *vertices, const int32_t *faces, const float *colors, int n_verts, int n_faces, float kthr,
+                                int seg_min_verts, int32_t *comps, int32_t *pairs, int cap);
+
 /* ---------------------------------------------------------------- tri-plane projection (noise-robust loss)
  * custom_cuda_utils.project_sparse_voxels_to_planes[_backward] (utils/cuda_utils/cuda_utils.cpp:26-53, kernels
  * cuda_utils_kernel.cu:371-433, 496-556; callers models/noise_robust_loss.py:28-31, 67-69).  coords int32 [n, 4] (batch, x, y, z)

@@ -7,6 +7,7 @@ only; the outputs are git-ignored and travel to the GPU box with the snapshot). 
   `at::cuda::getCurrentCUDAStream()`, so it links against the torch libraries of this image.
 * `libplanes_ref.so`: the reference's tri-plane projection functions, utils/cuda_utils/cuda_utils_kernel.cu (:371-600), compiled
   the same way with oracle/planes_ref_shim.cu (needs --expt-relaxed-constexpr: the file calls std::sqrt in a kernel; ~2 min).
+* `felzenszwalb_ref/felzenszwalb_cpp*.so`: the reference's pybind module utils/cpp_utils/segmentator.cpp, compiled as it is.
 * `reference/`: the UNMODIFIED reference Python files of the hot path (models/, pointnet2_utils.py, the pseudo-mask
   functions, the trainer and its entry point) staged so that the `-m gpu` tests can execute them on the CUDA shim on the GPU
   box, where /root/reference does not exist.  Nothing here is committed: the reference's sources stay out of the history.
@@ -77,6 +78,28 @@ def build_planes(verbose=False):
     return lib
 
 
+def build_felzenszwalb(verbose=False):
+    """The reference's pybind module felzenszwalb_cpp, utils/cpp_utils/segmentator.cpp, compiled as it is (g++ -O2, the flags of
+    a default setuptools build) into oracle/_ref/felzenszwalb_ref/felzenszwalb_cpp<ext suffix>: imported by the tests under that
+    directory as the checker for us3d_felzenszwalb_segment_h."""
+    import sysconfig
+
+    import pybind11
+
+    src = os.path.join(REFERENCE, "utils/cpp_utils/segmentator.cpp")
+    out_dir = os.path.join(OUT, "felzenszwalb_ref")
+    os.makedirs(out_dir, exist_ok=True)
+    lib = os.path.join(out_dir, "felzenszwalb_cpp" + sysconfig.get_config_var("EXT_SUFFIX"))
+    if os.path.exists(lib):
+        return lib
+    cmd = ["g++", "-O2", "-shared", "-fPIC", "-std=c++17", "-fvisibility=hidden", "-w", "-I", pybind11.get_include(), "-I",
+           sysconfig.get_paths()["include"], "-I", os.path.join(REFERENCE, "utils/cpp_utils"), src, "-o", lib]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    subprocess.run(cmd, check=True)
+    return lib
+
+
 def stage_reference():
     dst_root = os.path.join(OUT, "reference")
     for rel in STAGED:
@@ -97,7 +120,7 @@ def build(verbose=False):
     if not os.path.isdir(REFERENCE):
         return None
     os.makedirs(OUT, exist_ok=True)
-    out = [build_fps(verbose), stage_reference()]
+    out = [build_fps(verbose), stage_reference(), build_felzenszwalb(verbose)]
     try:  # ~5 minutes of nvcc (torch/extension.h); the GPU tests skip the reference-kernel comparison when it is absent
         out.append(build_planes(verbose))
     except Exception as e:  # noqa: BLE001
