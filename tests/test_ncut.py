@@ -128,6 +128,30 @@ def test_cuda_other_modes_match_the_oracle(aggregation_mode, separation_mode, si
     assert want.shape[0] >= 1 and np.array_equal(got, want)
 
 
+def test_host_blob_growing_equals_the_oracle_on_random_graphs():
+    """unscene3d_b200.pseudo_masks.separate_segments (libus3d host function, no GPU involved) against the literal restatement,
+    all four modes, directed adjacency with ids that are not segments of the scene."""
+    import unscene3d_b200  # noqa: F401
+    from oracle import ncut_cpu
+    from unscene3d_b200 import pseudo_masks as pm
+
+    rng = np.random.default_rng(0)
+    for trial in range(120):
+        S = int(rng.integers(5, 60))
+        ids = np.sort(rng.choice(500, S, replace=False))
+        E = int(rng.integers(S, 4 * S))
+        conn = np.stack([rng.choice(ids, E), rng.choice(np.concatenate([ids, [777]]), E)], 1)
+        bip = rng.random(S) < 0.6
+        if not bip.any():
+            continue
+        vec = rng.normal(size=S)
+        vec[~bip] -= 10
+        for mode in ("max", "avg", "largest", "all"):
+            got = pm.separate_segments(bip, vec, torch.from_numpy(ids), torch.from_numpy(conn), mode)
+            want = ncut_cpu.separate_segments(bip, vec, torch.from_numpy(ids), torch.from_numpy(conn), mode)
+            assert got == set(int(x) for x in want), (trial, mode)
+
+
 def test_blob_growing_keeps_reference_quirks():
     """Directed neighbour lists and the skipped blob after a merge (reference :207-224) change the result; the literal
     restatement must keep both."""

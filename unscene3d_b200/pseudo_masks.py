@@ -277,42 +277,65 @@ def second_smallest_eigenvector(graph: NCutGraph, max_steps: int = 4096, tol: fl
     return dinv * _lanczos_top_deflated(matvec, u1, max_steps, tol, seed, info=info, pick=pick)
 
 
-def separate_segments(bipartition: np.ndarray, vec: np.ndarray, unique_segments: torch.Tensor, seg_connectivity: torch.Tensor, mode: str = "max"):
-    """The reference's incremental blob growing (:181-233) including its scan-index behaviour after a merge, on the host like
-    the reference; 'max' (configured, pseudo_masks/config/default.yaml:64-74): the blob containing argmax(vec); 'avg': the blob
-    with the highest mean of vec; 'largest': the blob with most segments; 'all': every foreground segment (:234-250)."""
+class SegmentGraph:
+    """Directed segment adjacency as CSR over POSITIONS in `unique_segments` (rows [a, b] of seg_connectivity: b is listed for a;
+    ids that are not segments of the scene are dropped — they can never be part of a blob).  Built once per scene."""
+
+    def __init__(self, unique_segments: torch.Tensor, seg_connectivity: torch.Tensor):
+        ids = unique_segments.cpu().numpy()
+        conn = seg_connectivity.cpu().numpy().reshape(-1, 2)
+        order = np.argsort(ids, kind="stable")
+        sorted_ids = ids[order]
+        pa = np.searchsorted(sorted_ids, conn[:, 0])
+        pb = np.searchsorted(sorted_ids, conn[:, 1])
+        ok = (pa < len(ids)) & (pb < len(ids))
+        ok[ok] &= (sorted_ids[pa[ok]] == conn[ok, 0]) & (sorted_ids[pb[ok]] == conn[ok, 1])
+        a, b = order[pa[ok]], order[pb[ok]]
+        by_a = np.argsort(a, kind="stable")
+        self.ids = ids
+        self.adj = np.ascontiguousarray(b[by_a], dtype=np.int32)
+        self.adj_ptr = np.zeros(len(ids) + 1, dtype=np.int32)
+        np.cumsum(np.bincount(a, minlength=len(ids)), out=self.adj_ptr[1:])
+
+    def blobs(self, bipartition: np.ndarray):
+        """The reference's incremental blob growing over the foreground segments (:190-226) — libus3d host function, literal
+        list semantics (visit in position order, join every blob that holds a listed neighbour, merge bridged blobs, the scan
+        index still advances after a merge).  Returns the blobs as arrays of positions, in the reference's list order."""
+        s = len(self.ids)
+        mask = np.ascontiguousarray(bipartition, dtype=np.uint8).reshape(1, s)
+        k = int(mask.sum())
+        if k == 0:
+            return []
+        query = np.empty(k, dtype=np.int32)
+        ptr = np.empty(k + 1, dtype=np.int32)
+        members = np.empty(k, dtype=np.int32)
+        nb = lib.us3d_freemask_separate_h(mask.ctypes.data, 1, s, self.adj_ptr.ctypes.data, self.adj.ctypes.data, query.ctypes.data,
+                                          ptr.ctypes.data, members.ctypes.data, k, k)
+        if nb < 0:
+            check(nb)
+        return [members[ptr[i]:ptr[i + 1]] for i in range(nb)]
+
+
+def separate_segments(bipartition: np.ndarray, vec: np.ndarray, unique_segments: torch.Tensor, seg_connectivity: torch.Tensor, mode: str = "max",
+                      graph: Optional[SegmentGraph] = None):
+    """separate_segments (:181-250): blobs of connected foreground segments, then 'max' (configured,
+    pseudo_masks/config/default.yaml:64-74): the blob containing argmax(vec); 'avg': the blob with the highest mean of vec;
+    'largest': the blob with most segments; 'all': every foreground segment.  Returns a set of segment ids."""
     if mode not in ("max", "avg", "largest", "all"):
         raise NotImplementedError(mode)
-    ids = unique_segments.cpu().numpy()
+    graph = graph or SegmentGraph(unique_segments, seg_connectivity)
+    ids = graph.ids
     if mode == "all":
         return set(int(c) for c in ids[bipartition])
-    conn = seg_connectivity.cpu().numpy()
-    order = np.argsort(conn[:, 0], kind="stable")
-    starts = np.searchsorted(conn[order, 0], ids, side="left")
-    ends = np.searchsorted(conn[order, 0], ids, side="right")
-    listed = {int(s): set(conn[order[a:b], 1].tolist()) for s, a, b in zip(ids, starts, ends)}
-    blobs = []
-    for c in ids[bipartition].tolist():
-        first, merged, pos = -1, False, 0
-        while pos < len(blobs):
-            blob = blobs[pos]
-            if listed[c] & blob:
-                merged = True
-                blob.add(c)
-                if first != -1:
-                    blobs[first] = blobs[first] | blob
-                    blobs.pop(pos)
-                else:
-                    first = pos
-            pos += 1
-        if not merged:
-            blobs.append({c})
+    blobs = graph.blobs(bipartition)
     if mode == "avg":
-        return blobs[int(np.argmax([np.mean(vec[np.isin(ids, list(b))]) for b in blobs]))]
-    if mode == "largest":
-        return blobs[int(np.argmax(np.array([len(b) for b in blobs])))]
-    seed_id = int(ids[int(np.argmax(vec))])
-    return next(b for b in blobs if seed_id in b)
+        pick = blobs[int(np.argmax([np.mean(vec[b]) for b in blobs]))]
+    elif mode == "largest":
+        pick = blobs[int(np.argmax(np.array([len(b) for b in blobs])))]
+    else:
+        seed = int(np.argmax(vec))
+        pick = next(b for b in blobs if seed in b)
+    return set(ids[pick].tolist())
 
 
 def unscene3d(aggregated_features, unique_segments, seg_connectivity, affinity_tau=0.65, max_number_of_instances=20,
@@ -328,6 +351,7 @@ def unscene3d(aggregated_features, unique_segments, seg_connectivity, affinity_t
     dev = fa.device
     ids = unique_segments.cpu().numpy()
     masks, foreground = [], set()
+    seg_graph = SegmentGraph(unique_segments, seg_connectivity)
     painting = torch.zeros(S, dtype=torch.bool, device=dev)
     current = None
     fa, fb = fa.clone(), fb.clone()
@@ -349,7 +373,7 @@ def unscene3d(aggregated_features, unique_segments, seg_connectivity, affinity_t
         bip = vec > vec.sum() / len(vec)
         if bip.sum() / len(bip) > max_extent_ratio:
             bip, vec = np.logical_not(bip), -vec
-        part = separate_segments(bip, vec, unique_segments, seg_connectivity, mode=separation_mode)
+        part = separate_segments(bip, vec, unique_segments, seg_connectivity, mode=separation_mode, graph=seg_graph)
         current = torch.from_numpy(np.isin(ids, list(part))).to(dev)
         iou = len(part & foreground) / len(part)
         if iou > 0.5 or len(part) < min_segment_size:
