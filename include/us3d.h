@@ -314,6 +314,17 @@ long long us3d_ncut_lanczos_workspace_bytes(int m);
 int us3d_ncut_lanczos(const uint32_t *bits, int s, double eps, const double *dinv, double *Q, double *alpha, double *beta, int j0,
                       int j1, int m, double breakdown, void *workspace, long long workspace_bytes, int *steps_done, void *stream);
 
+/* ---------------------------------------------------------------- 2D -> 3D feature lifting
+ * project_features_cuda.project_features_cuda (utils/cuda_utils/project_image_cuda_kernel.cu:24-146, 183-256; caller
+ * utils/cuda_utils/raycast_image.py:18-77): every pixel's camera ray is marched through the dense occupancy grid in steps of
+ * ray_inc from depth_min to depth_max (voxel units); the pixel's feature row is added to the first occupied voxel (int32 labels:
+ * maximum, when pred_mode) and the voxel's hit count incremented.  feats [B, V, H, W, C]; occ int64 [B, Z, Y, X], 0 = empty else
+ * voxel index; view_inv float [B, V, 4, 4]; intr float [B, 4] = (fx, fy, mx, my); hit int32 scratch [B * V * H * W]; counts
+ * int32 [n_vox] and out [n_vox, C] are accumulated into.                                                                */
+int us3d_project_features_2d3d(const void *feats, const long long *occ, const float *view_inv, const float *intr, int B, int V, int H, int W,
+                               int C, int Z, int Y, int X, float depth_min, float depth_max, float ray_inc, int pred_mode, int *hit,
+                               int *counts, void *out, void *stream);
+
 /* ---------------------------------------------------------------- Felzenszwalb mesh over-segmentation
  * HOST function.  felzenszwalb_cpp.segment_mesh (utils/cpp_utils/segmentator.cpp:17-262; callers datasets/freemask_semseg.py:212,
  * pseudo_masks/datasets/scannet.py:182): vertices / colors float[n_verts][3], faces int32[n_faces][3] -> comps int32[n_verts]

@@ -7,6 +7,8 @@ only; the outputs are git-ignored and travel to the GPU box with the snapshot). 
   `at::cuda::getCurrentCUDAStream()`, so it links against the torch libraries of this image.
 * `libplanes_ref.so`: the reference's tri-plane projection functions, utils/cuda_utils/cuda_utils_kernel.cu (:371-600), compiled
   the same way with oracle/planes_ref_shim.cu (needs --expt-relaxed-constexpr: the file calls std::sqrt in a kernel; ~2 min).
+* `libproject_ref.so`: the reference's 2D -> 3D feature projection, utils/cuda_utils/project_image_cuda_kernel.cu, likewise with
+  oracle/project_ref_shim.cu.
 * `felzenszwalb_ref/felzenszwalb_cpp*.so`: the reference's pybind module utils/cpp_utils/segmentator.cpp, compiled as it is.
 * `reference/`: the UNMODIFIED reference Python files of the hot path (models/, pointnet2_utils.py, the pseudo-mask
   functions, the trainer and its entry point) staged so that the `-m gpu` tests can execute them on the CUDA shim on the GPU
@@ -55,15 +57,15 @@ def build_fps(verbose=False):
     return lib
 
 
-def build_planes(verbose=False):
+def build_planes(verbose=False, src_rel="utils/cuda_utils/cuda_utils_kernel.cu", shim_name="planes_ref_shim.cu", lib_name="libplanes_ref.so"):
     import sysconfig
 
     import torch  # noqa: F401
     from torch.utils import cpp_extension as ce
 
-    src = os.path.join(REFERENCE, "utils/cuda_utils/cuda_utils_kernel.cu")
-    shim = os.path.join(HERE, "planes_ref_shim.cu")
-    lib = os.path.join(OUT, "libplanes_ref.so")
+    src = os.path.join(REFERENCE, src_rel)
+    shim = os.path.join(HERE, shim_name)
+    lib = os.path.join(OUT, lib_name)
     if os.path.exists(lib) and os.path.getmtime(lib) > os.path.getmtime(shim):
         return lib
     tlib = ce.library_paths(device_type="cuda")[0]
@@ -121,10 +123,12 @@ def build(verbose=False):
         return None
     os.makedirs(OUT, exist_ok=True)
     out = [build_fps(verbose), stage_reference(), build_felzenszwalb(verbose)]
-    try:  # ~5 minutes of nvcc (torch/extension.h); the GPU tests skip the reference-kernel comparison when it is absent
+    try:  # ~5 minutes of nvcc each (torch/extension.h); the GPU tests skip the reference-kernel comparison when they are absent
         out.append(build_planes(verbose))
+        # the reference's 2D -> 3D feature projection, utils/cuda_utils/project_image_cuda_kernel.cu
+        out.append(build_planes(verbose, "utils/cuda_utils/project_image_cuda_kernel.cu", "project_ref_shim.cu", "libproject_ref.so"))
     except Exception as e:  # noqa: BLE001
-        print(f"oracle/_ref: libplanes_ref.so not built ({e})", file=sys.stderr)
+        print(f"oracle/_ref: reference kernel library not built ({e})", file=sys.stderr)
     return tuple(out)
 
 

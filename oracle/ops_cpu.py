@@ -236,3 +236,53 @@ def project_voxels_to_planes_bwd(coords, grads, dims, n_inst):
     s = (g[0] + g[1]) + g[2]
     out[ok] = np.where(cnt > 0, s / np.maximum(cnt, 1).astype(np.float32), 0.0).astype(np.float32)
     return out
+
+
+def project_features_2d3d(feats, occ, view_inv, intr, depth_min, depth_max, ray_inc):
+    """utils/cuda_utils/project_image_cuda_kernel.cu:24-64, 113-146 restated with numpy float32 (vectorised over the pixels): every
+    pixel's ray is marched through occ [B, Z, Y, X] (0 = empty, else voxel index) from depth_min to depth_max in steps of ray_inc;
+    returns (hit [B, V, H, W] voxel index of the first occupied cell or 0, counts [n_vox], sums [n_vox, C]).  The CUDA kernels fuse
+    a * b + c into FMAs, numpy does not: rays grazing a cell boundary within float round-off may land in the neighbouring cell."""
+    import numpy as np
+
+    f32 = np.float32
+    feats, occ = np.asarray(feats, dtype=f32), np.asarray(occ)
+    view_inv, intr = np.asarray(view_inv, dtype=f32), np.asarray(intr, dtype=f32)
+    B, V, H, W, C = feats.shape
+    _, Z, Y, X = occ.shape
+    n_vox = int(occ.max()) + 1
+    hit = np.zeros((B, V, H, W), dtype=np.int64)
+    ys, xs = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    for b in range(B):
+        fx, fy, mx, my = intr[b]
+        depth = f32(1.0) * (f32(depth_max) - f32(depth_min)) + f32(depth_min)
+        cx = (xs.astype(f32) - mx) / fx
+        cy = (ys.astype(f32) - my) / fy
+        cam = np.stack([depth * cx, depth * cy, np.full_like(cx, depth)], -1).astype(f32)
+        cam = cam * (f32(1.0) / np.sqrt((cam * cam).sum(-1, dtype=f32)))[..., None]
+        for v in range(V):
+            m = view_inv[b, v]
+            origin = m[:3, 3]
+            d = (cam @ m[:3, :3].T).astype(f32)
+            d = d * (f32(1.0) / np.sqrt((d * d).sum(-1, dtype=f32)))[..., None]
+            scale = f32(1.0) / cam[..., 2]
+            ray = scale * f32(depth_min)
+            end = scale * f32(depth_max)
+            found = np.zeros((H, W), dtype=np.int64)
+            alive = ray < end
+            while alive.any():
+                w = origin[None, None, :] + ray[..., None] * d
+                p = (w + np.sign(w).astype(f32) * f32(0.5)).astype(np.int64)  # truncation toward zero, as int(float)
+                inside = alive & (p >= 0).all(-1) & (p[..., 0] < X) & (p[..., 1] < Y) & (p[..., 2] < Z)
+                val = np.zeros((H, W), dtype=np.int64)
+                val[inside] = occ[b, p[..., 2][inside], p[..., 1][inside], p[..., 0][inside]]
+                newly = inside & (val != 0) & (found == 0)
+                found[newly] = val[newly]
+                alive = alive & ~newly
+                ray = (ray + f32(ray_inc)).astype(f32)
+                alive = alive & (ray < end)
+            hit[b, v] = found
+    counts = np.bincount(hit[hit != 0].ravel(), minlength=n_vox)
+    sums = np.zeros((n_vox, C), dtype=np.float64)
+    np.add.at(sums, hit[hit != 0].ravel(), feats[hit != 0].astype(np.float64))
+    return hit, counts, sums

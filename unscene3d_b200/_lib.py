@@ -63,6 +63,7 @@ PROTOTYPES = {
     "us3d_ncut_gram": [_p, _i, _i, _p, _p, _p, _p],
     "us3d_ncut_threshold": [_p, _p, _i, _p, _p, _f, ctypes.c_double, _p, _p, _p, _p],
     "us3d_ncut_matvec": [_p, _i, ctypes.c_double, _p, _p, _p, _p],
+    "us3d_project_features_2d3d": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _f, _i, _p, _p, _p, _p],
     "us3d_felzenszwalb_segment_h": [_p, _p, _p, _i, _i, _f, _i, _p, _p, _i],
     "us3d_project_voxels_to_planes": [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "us3d_project_voxels_to_planes_bwd": [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p],

@@ -803,6 +803,12 @@ def mask_losses(logits_sq, targets_ts, qidx, tidx, weights, n):
 
 
 # ------------------------------------------------------------------------------------------- decoder attention masks
+def _count(index, n):
+    """Occurrences of 0..n-1 in `index` — torch.bincount(index, minlength=n) without its host synchronisation (bincount reads the
+    maximum back to size its result even when minlength is given)."""
+    return torch.zeros(n, dtype=torch.int64, device=index.device).scatter_add_(0, index, torch.ones_like(index))
+
+
 def _segment_pool_matrix(cm, key0, point2segment, sizes, steps):
     """CSR matrix A_L [N_L, S_total] with  avgpool^L(seglogit[point2segment])[v, :] = sum_s A_L[v, s] seglogit[s, :]  for the
     coordinate manager's pyramid below `key0`: A_0[p, seg(p)] = 1, A_{l+1}[v, :] = mean over the present children u of A_l[u, :]
@@ -827,7 +833,7 @@ def _segment_pool_matrix(cm, key0, point2segment, sizes, steps):
         nxt = cm.stride(key, (2, 2, 2))
         parent = cm._parents[(key, nxt)].long()
         n_next = cm.size(nxt)
-        count = torch.bincount(parent, minlength=n_next).float()
+        count = _count(parent, n_next).float()
         prow = parent[rows]
         merged, inv = torch.unique(prow * entry["S"] + cols, return_inverse=True)
         v2 = torch.zeros(merged.shape[0], dtype=torch.float32, device=vals.device).index_add_(0, inv, vals / count[prow])
@@ -837,7 +843,7 @@ def _segment_pool_matrix(cm, key0, point2segment, sizes, steps):
     if steps not in csr:
         n = cm.size(key)
         rowptr = torch.zeros(n + 1, dtype=torch.int64, device=rows.device)
-        rowptr[1:] = torch.cumsum(torch.bincount(rows, minlength=n), 0)   # rows are sorted (level 0: arange; above: unique keys)
+        rowptr[1:] = torch.cumsum(_count(rows, n), 0)   # rows are sorted (level 0: arange; above: unique keys)
         csr[steps] = (rowptr, cols.contiguous(), vals.contiguous())
     return (key, *csr[steps], entry["S"])
 
