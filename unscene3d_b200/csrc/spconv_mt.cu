@@ -43,7 +43,8 @@ constexpr int A_PLANE = M * 128;  // bytes of one plane of one A slot
 constexpr int PROD_WARPS = 4;
 constexpr int B_WARP = PROD_WARPS, MMA_WARP = PROD_WARPS + 1, EPI_WARP0 = PROD_WARPS + 2;
 constexpr int IDX_WARP = PROD_WARPS + 6;
-constexpr int THREADS = (PROD_WARPS + 2 + 4 + 1) * 32;
+constexpr int MMA_WARP_EXTRA0 = PROD_WARPS + 7;  // MMA warps 1 .. MAX_T-1 (one MMA-issuing warp per tile of the group)
+constexpr int THREADS = (PROD_WARPS + 2 + 4 + 1 + 3) * 32;
 constexpr int MAX_A = 8, MAX_B = 3, MAX_T = 4;
 constexpr int NIDX = 4;  // stages of the neighbour-index ring (one stage = the indices of one offset for the T tiles)
 
@@ -66,7 +67,7 @@ struct Params {
     long long *prof;  // optional per-CTA wait-cycle counters of the MMA thread (debug)
 };
 
-template <int PASSES, int LAG, bool FUSE>
+template <int PASSES, int LAG, bool FUSE, bool PROF>
 __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
     static_assert(!FUSE || PASSES == 3, "the fused [W_hi | W_lo] operand exists in three-term mode only");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -93,13 +94,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
         }
         for (int s = 0; s < p.b_slots; ++s) {
             mbar_init(smem_u32(&b_full[s]), 1);
-            mbar_init(smem_u32(&b_empty[s]), 1);
+            mbar_init(smem_u32(&b_empty[s]), T);  // every MMA warp releases the slab
         }
         for (int s = 0; s < NIDX; ++s) {
             mbar_init(smem_u32(&idx_full[s]), 32);
             mbar_init(smem_u32(&idx_empty[s]), PROD_WARPS);
         }
-        mbar_init(smem_u32(&acc_full), 1);
+        mbar_init(smem_u32(&acc_full), T);
         mbar_init(smem_u32(&acc_empty), 4);
         mbar_fence_init();
     }
@@ -152,8 +153,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
         const int grp = tid & 7;     // 16-byte chunk within the 128-byte row
         const int rbase = tid >> 3;
         int item = 0, signalled = 0;
-        int ps = 0, ss = 0;  // ring positions of `item` and `signalled`
-        uint32_t ppar = 0;
+        // Ring slots are dealt to the tiles of a group: tile t owns slots t, t + T, t + 2T, ... (a_slots is a multiple of T), so a
+        // slot is always consumed by the same MMA warp, which therefore observes every phase of its barrier in turn (a parity wait
+        // must not lag or lead its barrier by more than one phase).
+        const int spt = p.a_slots / T;  // slots per tile
+        int pos[MAX_T] = {0, 0, 0, 0};
+        uint32_t par[MAX_T] = {0, 0, 0, 0};
+        int hist[4] = {0, 0, 0, 0};  // slots of the last items (wait_group variants signal LAG items late)
         int is = 0;          // index-ring stage of the current (super-tile, offset)
         uint32_t ipar = 0;
         int tile0, nt;
@@ -181,6 +187,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
                             const int r = rbase + 16 * i;
                             idx[i] = row0 + r < p.n_rows ? idx_ring[is][t][r] : -1;
                         }
+                        const int ps = t + T * pos[t];
+                        const uint32_t ppar = par[t];
+                        if (++pos[t] == spt) {
+                            pos[t] = 0;
+                            par[t] ^= 1u;
+                        }
                         mbar_wait(smem_u32(&a_empty[ps]), ppar ^ 1, 0);
                         const uint32_t slot = a_base + (uint32_t)ps * A_SLOT;
 #pragma unroll
@@ -195,21 +207,17 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
                         if (LAG == 0) {
                             cp_async_arrive_noinc(smem_u32(&a_full[ps]));
                         } else {
+                            hist[item & 3] = ps;
                             cp_async_commit();
                             if (item - signalled >= LAG) {
                                 cp_async_wait<(LAG > 0 ? LAG : 1)>();
                                 fence_proxy_async();
                                 __syncwarp();
-                                if (lane == 0) mbar_arrive(smem_u32(&a_full[ss]));
+                                if (lane == 0) mbar_arrive(smem_u32(&a_full[hist[signalled & 3]]));
                                 ++signalled;
-                                if (++ss == p.a_slots) ss = 0;
                             }
                         }
                         ++item;
-                        if (++ps == p.a_slots) {
-                            ps = 0;
-                            ppar ^= 1u;
-                        }
                     }
                 }
                 __syncwarp();
@@ -224,10 +232,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
         if (LAG != 0) {
             fence_proxy_async();
             __syncwarp();
-            for (; signalled < item; ++signalled) {
-                if (lane == 0) mbar_arrive(smem_u32(&a_full[ss]));
-                if (++ss == p.a_slots) ss = 0;
-            }
+            for (; signalled < item; ++signalled)
+                if (lane == 0) mbar_arrive(smem_u32(&a_full[hist[signalled & 3]]));
         }
     } else if (warp == IDX_WARP) {
         // ------------------------------------------------------------------ neighbour indices, NIDX offsets ahead
@@ -293,18 +299,25 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
             }
         }
         __syncwarp();
-    } else if (warp == MMA_WARP) {
-        // ------------------------------------------------------------------ MMA issuer
+    } else if (warp == MMA_WARP || (warp >= MMA_WARP_EXTRA0 && warp - MMA_WARP_EXTRA0 + 1 < T)) {
+        // ------------------------------------------------------------------ MMA issuers, one warp per tile of the group
+        // The per-item work of an issuing thread (barrier test, proxy fence, descriptors, 8-12 MMAs, commit, bookkeeping) is a
+        // serial instruction stream of ~1000 cycles against ~450 tensor-pipe cycles of MMAs (profiles/r2_conv_pipeline.md): with
+        // one issuer per CTA the tensor pipe idles 60 % of the time.  Tile t of a group therefore has its own issuing warp mw = t:
+        // every warp walks the same item sequence (ring positions are pure counters), waits / issues / frees only the slots of
+        // its own tile, and all of them release the weight slab and the accumulators (barrier counts = T).
+        const int mw = warp == MMA_WARP ? 0 : warp - MMA_WARP_EXTRA0 + 1;
         // The whole warp runs the (warp-uniform) control flow so that descriptors and ring positions live in
         // uniform registers; one elected lane issues tcgen05.mma / tcgen05.commit.  (A single-lane branch makes
         // ptxas wrap every UTCHMMA in an elect + R2UR.BROADCAST loop: ~80 issue cycles per MMA, measured.)
         const uint32_t idesc = idesc_bf16(p.cout);
         const uint32_t idesc2 = idesc_bf16(2 * p.cout);  // FUSE: B = [W_hi rows | W_lo rows]
         const uint64_t a_desc0 = desc_k_sw128(a_base), b_desc0 = desc_k_sw128(b_base);
-        int as = 0, bs = 0, siter = 0, item = 0, bitem = 0;
+        const int spt = p.a_slots / T;  // ring slots of this warp's tile: mw, mw + T, ... (see the producers)
+        int apos = 0, bs = 0, siter = 0, item = 0, bitem = 0;
         uint32_t apar = 0, bpar = 0;
         long long w_acc = 0, w_b = 0, w_a = 0, t_first = 0;
-        const long long t_begin = clock64();
+        const long long t_begin = PROF ? clock64() : 0;  // the cycle counters exist only in the profiling instantiation
         int tile0, nt;
         uint32_t pm;
         for (int ui = 0; unit(ui, tile0, nt, pm); ++ui, ++siter) {
@@ -314,27 +327,31 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
                 m[t] = t < nt ? tile_kmask(tile0 + t, pm) : 0u;
                 U |= m[t];
             }
-            long long tw0 = clock64();
+            long long tw0 = PROF ? clock64() : 0;
             mbar_wait(smem_u32(&acc_empty), (siter & 1) ^ 1, 2);
-            w_acc += clock64() - tw0;
+            if (PROF) w_acc += clock64() - tw0;
             tc_fence_after();
             uint32_t started = 0;
             for (int k = 0; k < p.kvol; ++k) {
                 if (!((U >> k) & 1u)) continue;
                 for (int c = 0; c < p.nchunks; ++c) {
-                    long long tw1 = clock64();
+                    long long tw1 = PROF ? clock64() : 0;
                     mbar_wait(smem_u32(&b_full[bs]), bpar, 3);
-                    w_b += clock64() - tw1;
+                    if (PROF) w_b += clock64() - tw1;
                     const int ksteps = min(KC, p.cin - c * KC) / 16;
                     const uint64_t db_hi = b_desc0 + (uint64_t)((uint32_t)(bs * b_slot_bytes) >> 4);
                     const uint64_t db_lo = db_hi + (uint64_t)((uint32_t)p.b_plane >> 4);
 #pragma unroll
                     for (int t = 0; t < MAX_T; ++t) {
                         if (!((m[t] >> k) & 1u)) continue;
-                        long long tw2 = clock64();
+                        if (t != mw) continue;  // another warp's item
+                        const int as = mw + T * apos;
+                        long long tw2 = PROF ? clock64() : 0;
                         mbar_wait(smem_u32(&a_full[as]), apar, 4);
-                        w_a += clock64() - tw2;
-                        if (item == 0) t_first = clock64() - t_begin;
+                        if (PROF) {
+                            w_a += clock64() - tw2;
+                            if (item == 0) t_first = clock64() - t_begin;
+                        }
                         if (LAG == 0) fence_proxy_async();  // cp.async writes (generic proxy) -> tcgen05 reads (async proxy)
                         tc_fence_after();
                         const uint64_t da_hi = a_desc0 + (uint64_t)((uint32_t)(as * A_SLOT) >> 4);
@@ -360,8 +377,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
                         __syncwarp();
                         started |= 1u << t;
                         ++item;
-                        if (++as == p.a_slots) {
-                            as = 0;
+                        if (++apos == spt) {
+                            apos = 0;
                             apar ^= 1u;
                         }
                     }
@@ -382,7 +399,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
             }
             __syncwarp();
         }
-        if (p.prof != nullptr && lane == 0) {
+        if (PROF && p.prof != nullptr && lane == 0 && mw == 0) {
             long long *o = p.prof + (size_t)blockIdx.x * 8;
             o[0] = clock64() - t_begin;
             o[1] = w_acc;
@@ -547,7 +564,7 @@ __global__ void __launch_bounds__(256) k_reduce_parts(const float *__restrict__ 
 template <int PASSES, bool FUSE>
 static cudaError_t launch(int lag, int grid, size_t smem, cudaStream_t st, const Params &p) {
     // every instantiation needs the opt-in for > 48 KB of dynamic shared memory once per device
-    static bool attr_done[4][64] = {};
+    static bool attr_done[8][64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     auto go = [&](auto kernel, int slot) -> cudaError_t {
@@ -559,10 +576,16 @@ static cudaError_t launch(int lag, int grid, size_t smem, cudaStream_t st, const
         kernel<<<grid, THREADS, smem, st>>>(p);
         return cudaSuccess;
     };
-    if (lag <= 0) return go(k_spconv_mt<PASSES, 0, FUSE>, 0);
-    if (lag == 1) return go(k_spconv_mt<PASSES, 1, FUSE>, 1);
-    if (lag == 2) return go(k_spconv_mt<PASSES, 2, FUSE>, 2);
-    return go(k_spconv_mt<PASSES, 3, FUSE>, 3);
+    if (p.prof != nullptr) {  // the instantiation with the MMA thread's cycle counters (us3d_debug_set_prof)
+        if (lag <= 0) return go(k_spconv_mt<PASSES, 0, FUSE, true>, 4);
+        if (lag == 1) return go(k_spconv_mt<PASSES, 1, FUSE, true>, 5);
+        if (lag == 2) return go(k_spconv_mt<PASSES, 2, FUSE, true>, 6);
+        return go(k_spconv_mt<PASSES, 3, FUSE, true>, 7);
+    }
+    if (lag <= 0) return go(k_spconv_mt<PASSES, 0, FUSE, false>, 0);
+    if (lag == 1) return go(k_spconv_mt<PASSES, 1, FUSE, false>, 1);
+    if (lag == 2) return go(k_spconv_mt<PASSES, 2, FUSE, false>, 2);
+    return go(k_spconv_mt<PASSES, 3, FUSE, false>, 3);
 }
 
 }  // namespace mt
@@ -675,6 +698,13 @@ int us3d_spconv_gather_mt(const void *x_hi, const void *x_lo, int n_in, const in
     US3D_CHECK_ARG(p.a_slots >= 2, "spconv_gather_mt: operand slots do not fit in shared memory (cout %d)", cout);
     if (p.a_slots == mt::MAX_A && budget - p.a_slots * a_slot - 3 * b_slot >= 0) p.b_slots = 3;
     if (g_tune_a_slots >= 2 && g_tune_a_slots <= p.a_slots) p.a_slots = g_tune_a_slots;
+    // the ring slots are dealt to the tiles of a group in equal shares
+    if (p.a_slots < T) {
+        T = p.a_slots;
+        p.T = T;
+        p.n_super = ceil_div(p.n_tiles, T);
+    }
+    p.a_slots = (p.a_slots / T) * T;
     const size_t smem = (size_t)p.a_slots * a_slot + (size_t)p.b_slots * b_slot + 1024;
     const int grid = p.n_units < sms ? p.n_units : sms;
     // Groups a producer warp keeps in flight before it waits for the oldest.  Measured on B200 (200k voxels, 128 -> 96):
