@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define US3D_ABI_VERSION 15
+#define US3D_ABI_VERSION 16
 #define US3D_MAX_KVOL 27
 
 int us3d_abi_version(void);

@@ -122,13 +122,24 @@ def build(verbose=False):
     if not os.path.isdir(REFERENCE):
         return None
     os.makedirs(OUT, exist_ok=True)
-    out = [build_fps(verbose), stage_reference(), build_felzenszwalb(verbose)]
-    try:  # ~5 minutes of nvcc each (torch/extension.h); the GPU tests skip the reference-kernel comparison when they are absent
-        out.append(build_planes(verbose))
-        # the reference's 2D -> 3D feature projection, utils/cuda_utils/project_image_cuda_kernel.cu
-        out.append(build_planes(verbose, "utils/cuda_utils/project_image_cuda_kernel.cu", "project_ref_shim.cu", "libproject_ref.so"))
-    except Exception as e:  # noqa: BLE001
-        print(f"oracle/_ref: reference kernel library not built ({e})", file=sys.stderr)
+    # the two torch-extension libraries take ~5 minutes of nvcc each: all native builds run side by side; the GPU tests skip a
+    # reference-kernel comparison whose library is absent
+    from concurrent.futures import ThreadPoolExecutor
+
+    jobs = {
+        "fps": lambda: build_fps(verbose),
+        "felzenszwalb": lambda: build_felzenszwalb(verbose),
+        "planes": lambda: build_planes(verbose),
+        "project": lambda: build_planes(verbose, "utils/cuda_utils/project_image_cuda_kernel.cu", "project_ref_shim.cu", "libproject_ref.so"),
+    }
+    out = [stage_reference()]
+    with ThreadPoolExecutor(max_workers=len(jobs)) as pool:
+        futures = {name: pool.submit(fn) for name, fn in jobs.items()}
+        for name, fut in futures.items():
+            try:
+                out.append(fut.result())
+            except Exception as e:  # noqa: BLE001
+                print(f"oracle/_ref: {name} not built ({e})", file=sys.stderr)
     return tuple(out)
 
 
