@@ -295,6 +295,41 @@ def test_backbone_at_200k_matches_the_cpu_oracle(scene):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("training", [True, False])
+def test_c1_res16unet14_forward_at_50k_matches_the_oracle(training):
+    """BASELINE configs[0]: single synthetic 50k-voxel scene, Res16UNet14 forward only (the configuration the reference can run on
+    its CPU MinkowskiEngine build): coordinates of all returned maps bit-exact, features to 1e-3, in training mode (batch
+    statistics, running buffers updated) and in evaluation mode (running statistics)."""
+    import unscene3d_b200  # noqa: F401
+    from helpers import Cfg, our_models_on_oracle
+    from oracle import me_cpu
+    from unscene3d_b200 import engine, models
+    from unscene3d_b200.synthetic import make_scene
+    from unscene3d_b200.utils import seeded_state
+
+    s = make_scene(50_000, seed=0, with_masks=False)
+    c4 = torch.from_numpy(np.concatenate([np.zeros((s.n, 1), np.int32), s.coords], 1))
+    feats = torch.from_numpy(s.colors)
+    cpu_net = our_models_on_oracle().res16unet.Res16UNet14(3, 20, Cfg(), D=3, out_fpn=True).train(training)
+    state = seeded_state(cpu_net, 0)
+    cpu_net.load_state_dict(state)
+    gpu_net = models.Res16UNet14(3, 20, Cfg(), D=3, out_fpn=True)
+    gpu_net.load_state_dict(state)
+    gpu_net = gpu_net.cuda().train(training)
+    with torch.no_grad():
+        c_out, c_aux = cpu_net(me_cpu.SparseTensor(feats, c4))
+        g_out, g_aux = gpu_net(engine.SparseTensor(feats.cuda(), c4.cuda()))
+    assert _rel_cpu(g_out.F, c_out.F) < 1e-3 and len(g_aux) == len(c_aux) == 5
+    for g, c in zip(g_aux, c_aux):
+        assert torch.equal(g.C.cpu(), c.C) and _rel_cpu(g.F, c.F) < 1e-3
+    if training:
+        gb, cb = dict(gpu_net.named_buffers()), dict(cpu_net.named_buffers())
+        for k, v in cb.items():
+            if k.endswith(("running_mean", "running_var")):
+                assert _rel_cpu(gb[k], v) < 1e-3, k
+
+
+@pytest.mark.gpu
 def test_c4_shaped_ncut_scene_matches_the_oracle():
     """BASELINE configs[3] at its stated size: 300k points, S = 2048 segments, 384-d + 96-d features, tau = 0.6 — per-segment
     features (3e-6), thresholded affinity bits and degrees of the first graph (bit-exact away from the threshold), and the
