@@ -20,6 +20,11 @@ int us3d_debug_profile_stop(int *meta, float *ms, int cap);
  * buf = NULL switches the counters off. */
 void us3d_debug_set_prof(void *buf);
 
+/* us3d_spconv_wgrad_planes: per-CTA cycle counters, 16 x int64 per CTA: [0] producer loop, [1] / [2] of it waiting for a free dY /
+ * X ring slot, [3] epilogue; [4] MMA warp's loop, [5] / [6] of it waiting for dY / gathered X, [7] fence + issue + commit,
+ * [8] ring slots consumed.  buf = NULL switches the profiling instantiation off. */
+void us3d_debug_set_prof_wgrad(void *buf);
+
 /* Overrides of the launcher's choices for us3d_spconv_gather_mt (0 = launcher's choice): ring slots, producer completion
  * (1..3 = cp.async.wait_group look-ahead, 9 = cp.async.mbarrier.arrive.noinc), tiles per weight slab, fused [W_hi | W_lo]
  * operand (1 = off, 2 = on where eligible). */

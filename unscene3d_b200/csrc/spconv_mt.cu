@@ -157,6 +157,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
         // slot is always consumed by the same MMA warp, which therefore observes every phase of its barrier in turn (a parity wait
         // must not lag or lead its barrier by more than one phase).
         const int spt = p.a_slots / T;  // slots per tile
+        const uint32_t row_bytes = (uint32_t)p.cin * 2u;
         int pos[MAX_T] = {0, 0, 0, 0};
         uint32_t par[MAX_T] = {0, 0, 0, 0};
         int hist[4] = {0, 0, 0, 0};  // slots of the last items (wait_group variants signal LAG items late)
@@ -177,16 +178,17 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
                 for (int c = 0; c < p.nchunks; ++c) {
                     const int c0 = c * KC + grp * 8;
                     const bool col_ok = c0 < p.cin;
+                    // byte address of this thread's 16-byte column chunk in row 0 of each plane; a row is one 32 x 32 -> 64 bit
+                    // multiply-add away (IMAD.WIDE.U32), absent neighbours go through the copy's ignore-src predicate
+                    const uint8_t *col_hi = reinterpret_cast<const uint8_t *>(p.x_hi) + (col_ok ? c0 * 2 : 0);
+                    const uint8_t *col_lo = reinterpret_cast<const uint8_t *>(p.x_lo) + (col_ok ? c0 * 2 : 0);
 #pragma unroll
                     for (int t = 0; t < MAX_T; ++t) {
                         if (!((m[t] >> k) & 1u)) continue;
-                        const int row0 = (tile0 + t) * M;
+                        const int lim = col_ok ? p.n_rows - (tile0 + t) * M : 0;  // rows of the tile inside the map (0: nothing to fetch)
                         int idx[RPT];
 #pragma unroll
-                        for (int i = 0; i < RPT; ++i) {
-                            const int r = rbase + 16 * i;
-                            idx[i] = row0 + r < p.n_rows ? idx_ring[is][t][r] : -1;
-                        }
+                        for (int i = 0; i < RPT; ++i) idx[i] = idx_ring[is][t][rbase + 16 * i];
                         const int ps = t + T * pos[t];
                         const uint32_t ppar = par[t];
                         if (++pos[t] == spt) {
@@ -194,15 +196,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
                             par[t] ^= 1u;
                         }
                         mbar_wait(smem_u32(&a_empty[ps]), ppar ^ 1, 0);
-                        const uint32_t slot = a_base + (uint32_t)ps * A_SLOT;
+                        const uint32_t slot = a_base + (uint32_t)ps * A_SLOT + (uint32_t)rbase * 128u + (uint32_t)((grp ^ (rbase & 7)) << 4);
 #pragma unroll
                         for (int i = 0; i < RPT; ++i) {
-                            const int r = rbase + 16 * i;
-                            const uint32_t dst = slot + (uint32_t)r * 128u + (uint32_t)((grp ^ (r & 7)) << 4);
-                            const bool ok = idx[i] >= 0 && col_ok;
-                            const size_t off = ok ? (size_t)idx[i] * p.cin + c0 : 0;
-                            cp_async16(dst, p.x_hi + off, ok ? 16u : 0u);
-                            if (PASSES == 3) cp_async16(dst + A_PLANE, p.x_lo + off, ok ? 16u : 0u);
+                            const bool ign = idx[i] < 0 || rbase + 16 * i >= lim;
+                            const uint64_t off = (uint64_t)(uint32_t)max(idx[i], 0) * row_bytes;
+                            cp_async16_pred(slot + (uint32_t)i * 2048u, col_hi + off, ign);
+                            if (PASSES == 3) cp_async16_pred(slot + (uint32_t)i * 2048u + A_PLANE, col_lo + off, ign);
                         }
                         if (LAG == 0) {
                             cp_async_arrive_noinc(smem_u32(&a_full[ps]));
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
                     for (int q = 0; q < M / 32; ++q) {
                         const int r = lane + 32 * q;
                         const bool ok = row0 + r < p.n_rows;
-                        cp_async4(smem_u32(&idx_ring[is][t][r]), src_k + (ok ? row0 + r : 0), ok ? 4u : 0u);
+                        cp_async4_pred(smem_u32(&idx_ring[is][t][r]), src_k + (ok ? row0 + r : 0), !ok);
                     }
                 }
                 cp_async_arrive_noinc(smem_u32(&idx_full[is]));

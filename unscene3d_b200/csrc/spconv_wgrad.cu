@@ -29,10 +29,11 @@ using namespace tcx;
 
 constexpr int R = 64;             // rows (GEMM-K) per stage
 constexpr int SLAB = R * 128;     // one 64-channel block of one plane
-constexpr int PROD_WARPS = 4;
+constexpr int PROD_WARPS = 8;  // a warp sustains one scattered LDGSTS.128 per ~50 cycles: the gather rate scales with the warps
 constexpr int MMA_WARP = PROD_WARPS;
-constexpr int THREADS = (PROD_WARPS + 1) * 32;
-constexpr int MAX_A = 12, MAX_B = 3, MAX_KG = 4;
+constexpr int NMW = 2;  // MMA-issuing warps: offset kq of the group belongs to warp kq % NMW (its own accumulators, its own A ring)
+constexpr int THREADS = (PROD_WARPS + NMW) * 32;
+constexpr int MAX_A = 6, MAX_B = 3, MAX_KG = 4;  // MAX_A: slots per A ring
 
 struct Params {
     const __nv_bfloat16 *x_hi, *x_lo;    // [n_in, cin]
@@ -40,16 +41,17 @@ struct Params {
     const int32_t *nbr;
     int n_rows, kvol;
     float *dw;
-    int cin, cout, npad, mblks, splits, rows_per_split, kg, ngroups;
+    int cin, cout, npad, nmma, mblks, splits, rows_per_split, kg, ngroups;
     const uint32_t *tile_mask;
     const int32_t *dy_rows;  // optional: table column j pairs with dY row dy_rows[j] (pattern-ordered tables)
     int a_slots, b_slots, acc_cols;
+    long long *prof;  // optional per-CTA cycle counters (profiling instantiation only)
 };
 
-template <int PASSES>
+template <int PASSES, bool PROF>
 __global__ void __launch_bounds__(THREADS, 1) k_wgrad(Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t a_full[MAX_A], a_empty[MAX_A], b_full[MAX_B], b_empty[MAX_B], acc_full;
+    __shared__ __align__(8) uint64_t a_full[NMW][MAX_A], a_empty[NMW][MAX_A], b_full[MAX_B], b_empty[MAX_B], acc_full;
     __shared__ uint32_t tmem_base_s;
     constexpr int NPL = PASSES == 3 ? 2 : 1;
     constexpr int A_PLANE = 2 * SLAB;  // 128 input channels
@@ -59,7 +61,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad(Params p) {
     const int b_plane = (p.npad / 64) * SLAB;
     const int b_slot_bytes = NPL * b_plane;
     const uint32_t a_base = smem_u32(smem);
-    const uint32_t b_base = a_base + (uint32_t)p.a_slots * A_SLOT;
+    const uint32_t b_base = a_base + (uint32_t)(NMW * p.a_slots) * A_SLOT;  // ring m = slots [m a_slots, (m + 1) a_slots)
 
     int b = blockIdx.x;
     const int split = b % p.splits;
@@ -79,15 +81,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad(Params p) {
     };
 
     if (tid == 0) {
-        for (int s = 0; s < p.a_slots; ++s) {
-            mbar_init(smem_u32(&a_full[s]), PROD_WARPS * 32);
-            mbar_init(smem_u32(&a_empty[s]), 1);
-        }
+        for (int m = 0; m < NMW; ++m)
+            for (int s = 0; s < p.a_slots; ++s) {
+                mbar_init(smem_u32(&a_full[m][s]), PROD_WARPS * 32);
+                mbar_init(smem_u32(&a_empty[m][s]), 1);
+            }
         for (int s = 0; s < p.b_slots; ++s) {
             mbar_init(smem_u32(&b_full[s]), PROD_WARPS * 32);
-            mbar_init(smem_u32(&b_empty[s]), 1);
+            mbar_init(smem_u32(&b_empty[s]), NMW);  // every MMA warp releases the dY tile
         }
-        mbar_init(smem_u32(&acc_full), 1);
+        mbar_init(smem_u32(&acc_full), NMW);
         mbar_fence_init();
     }
     if (warp == MMA_WARP) tmem_alloc(&tmem_base_s, (uint32_t)p.acc_cols);
@@ -100,45 +103,83 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad(Params p) {
     if (warp < PROD_WARPS) {
         // ------------------------------------------------------------------ producers
         const int GB = p.cout / 8;  // 16-byte chunks per dY row
-        int as = 0, bs = 0;
-        uint32_t apar = 0, bpar = 0;
-        // this thread's 8 (row, 16-byte chunk) cells of an A slot: row = 8 i + tid / 16, chunk g = tid % 16
+        int as[NMW] = {0, 0}, bs = 0;
+        uint32_t apar[NMW] = {0, 0}, bpar = 0;
+        // this thread's APT (row, 16-byte chunk) cells of an A slot: row = RSTEP i + tid / 16, chunk g = tid % 16.  RSTEP (a multiple
+        // of 8) rows further is RSTEP / 8 swizzle atoms (1024 B each) further with the same XOR pattern: cells adst0 + 128 RSTEP i.
+        constexpr int RSTEP = PROD_WARPS * 2, APT = R / RSTEP;
         const int arow0 = tid >> 4, ag = tid & 15;
         const bool acol_ok = ci0 + ag * 8 < p.cin;
-        uint32_t adst[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int row = arow0 + 8 * i;
-            adst[i] = (uint32_t)(ag >> 3) * SLAB + (uint32_t)row * 128u + (uint32_t)(((ag & 7) ^ (row & 7)) << 4);
-        }
-        for (int r0 = r_begin; r0 < r_end; r0 += R) {
-            const uint32_t act = active(r0);
-            if (!act) continue;
-            touched |= act;
-            // neighbour rows of every offset of the group: requested first, consumed after the dY copies are issued
-            int src[MAX_KG][8];
+        const uint32_t adst0 = (uint32_t)(ag >> 3) * SLAB + (uint32_t)arow0 * 128u + (uint32_t)(((ag & 7) ^ (arow0 & 7)) << 4);
+        const uint32_t x_row_bytes = (uint32_t)p.cin * 2u, dy_row_bytes = (uint32_t)p.cout * 2u;
+        const uint8_t *acol_hi = reinterpret_cast<const uint8_t *>(p.x_hi) + (acol_ok ? (ci0 + ag * 8) * 2 : 0);
+        const uint8_t *acol_lo = reinterpret_cast<const uint8_t *>(p.x_lo) + (acol_ok ? (ci0 + ag * 8) * 2 : 0);
+        const int brow0 = tid / GB, bg0 = tid - brow0 * GB;                                      // cell tid of a dY row block
+        const int brow_step = (PROD_WARPS * 32) / GB, bg_step = PROD_WARPS * 32 - brow_step * GB;  // ... and the step to the next cell
+        // Neighbour rows of every offset of the group, one row block AHEAD (register double buffer): the L2 round trip of the index
+        // loads is covered by the copies of the current block instead of stalling all producers once per block.
+        int nxt[MAX_KG][APT];
+        auto load_indices = [&](int r0) {
 #pragma unroll
             for (int kq = 0; kq < MAX_KG; ++kq) {
-                if (kq >= nk || !((act >> (k0 + kq)) & 1u)) continue;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int j = r0 + arow0 + 8 * i;
-                    src[kq][i] = j < r_end ? __ldg(p.nbr + (size_t)(k0 + kq) * p.n_rows + j) : -1;
+                for (int i = 0; i < APT; ++i) {
+                    const int j = r0 + arow0 + RSTEP * i;
+                    nxt[kq][i] = (kq < nk && j < r_end) ? __ldg(p.nbr + (size_t)(k0 + kq) * p.n_rows + j) : -1;
                 }
             }
-            // ---- B item: 64 rows of dY
-            mbar_wait(smem_u32(&b_empty[bs]), bpar ^ 1, 0);
+        };
+        load_indices(r_begin);
+        long long pw_b = 0, pw_a = 0;
+        const long long pt0 = PROF ? clock64() : 0;
+        for (int r0 = r_begin; r0 < r_end; r0 += R) {
+            const uint32_t act = active(r0);
+            int src[MAX_KG][APT];
+#pragma unroll
+            for (int kq = 0; kq < MAX_KG; ++kq)
+#pragma unroll
+                for (int i = 0; i < APT; ++i) src[kq][i] = nxt[kq][i];
+            if (r0 + R < r_end) load_indices(r0 + R);
+            if (!act) continue;
+            touched |= act;
+            // ---- B item: 64 rows of dY.  Cell e = tid + 128 n of the row block is 16-byte chunk g = e % GB of row e / GB; without a row
+            // permutation the block is one contiguous range of dY, so the source of a cell is base + 16 e and only the swizzled
+            // destination needs (row, g) — stepped without a division.
+            {
+                const long long tw = PROF ? clock64() : 0;
+                mbar_wait(smem_u32(&b_empty[bs]), bpar ^ 1, 0);
+                if (PROF) pw_b += clock64() - tw;
+            }
             {
                 const uint32_t slot = b_base + (uint32_t)bs * b_slot_bytes;
-                for (int it = tid; it < R * GB; it += PROD_WARPS * 32) {
-                    const int row = it / GB, g = it - row * GB;
-                    const int j = r0 + row;
-                    const bool ok = j < r_end;
-                    const uint32_t dst = slot + (uint32_t)(g >> 3) * SLAB + (uint32_t)row * 128u + (uint32_t)(((g & 7) ^ (row & 7)) << 4);
-                    const int jr = (ok && p.dy_rows) ? __ldg(p.dy_rows + j) : j;
-                    const size_t off = ok ? (size_t)jr * p.cout + g * 8 : 0;
-                    cp_async16(dst, p.dy_hi + off, ok ? 16u : 0u);
-                    if (PASSES == 3) cp_async16(dst + b_plane, p.dy_lo + off, ok ? 16u : 0u);
+                const int rows_here = min(R, r_end - r0);
+                if (p.dy_rows == nullptr) {
+                    const uint8_t *src_hi = reinterpret_cast<const uint8_t *>(p.dy_hi) + (size_t)r0 * dy_row_bytes;
+                    const uint8_t *src_lo = reinterpret_cast<const uint8_t *>(p.dy_lo) + (size_t)r0 * dy_row_bytes;
+                    int row = brow0, g = bg0;
+                    for (int e = tid; e < R * GB; e += PROD_WARPS * 32) {
+                        const bool ign = row >= rows_here;
+                        const uint32_t dst = slot + (uint32_t)(g >> 3) * SLAB + (uint32_t)row * 128u + (uint32_t)(((g & 7) ^ (row & 7)) << 4);
+                        const uint32_t off = ign ? 0u : (uint32_t)e * 16u;
+                        cp_async16_pred(dst, src_hi + off, ign);
+                        if (PASSES == 3) cp_async16_pred(dst + b_plane, src_lo + off, ign);
+                        row += brow_step;
+                        g += bg_step;
+                        if (g >= GB) {
+                            g -= GB;
+                            ++row;
+                        }
+                    }
+                } else {
+                    for (int it = tid; it < R * GB; it += PROD_WARPS * 32) {
+                        const int row = it / GB, g = it - row * GB;
+                        const bool ign = row >= rows_here;
+                        const uint32_t dst = slot + (uint32_t)(g >> 3) * SLAB + (uint32_t)row * 128u + (uint32_t)(((g & 7) ^ (row & 7)) << 4);
+                        const uint32_t jr = ign ? 0u : (uint32_t)__ldg(p.dy_rows + r0 + row);
+                        const uint64_t off = (uint64_t)jr * dy_row_bytes + (uint32_t)g * 16u;
+                        cp_async16_pred(dst, reinterpret_cast<const uint8_t *>(p.dy_hi) + off, ign);
+                        if (PASSES == 3) cp_async16_pred(dst + b_plane, reinterpret_cast<const uint8_t *>(p.dy_lo) + off, ign);
+                    }
                 }
                 cp_async_arrive_noinc(smem_u32(&b_full[bs]));
                 if (++bs == p.b_slots) {
@@ -152,36 +193,42 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad(Params p) {
                 if (kq >= nk || !((act >> (k0 + kq)) & 1u)) continue;
 #pragma unroll
                 for (int pl = 0; pl < NPL; ++pl) {
-                    const __nv_bfloat16 *plane = pl == 0 ? p.x_hi : p.x_lo;
-                    mbar_wait(smem_u32(&a_empty[as]), apar ^ 1, 1);
-                    const uint32_t slot = a_base + (uint32_t)as * A_SLOT;
+                    const uint8_t *plane = pl == 0 ? acol_hi : acol_lo;
+                    const int m = kq % NMW;  // compile-time after unrolling
+                    const long long tw = PROF ? clock64() : 0;
+                    mbar_wait(smem_u32(&a_empty[m][as[m]]), apar[m] ^ 1, 1);
+                    if (PROF) pw_a += clock64() - tw;
+                    const uint32_t slot = a_base + (uint32_t)(m * p.a_slots + as[m]) * A_SLOT + adst0;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const bool ok = src[kq][i] >= 0 && acol_ok;
-                        const size_t off = ok ? (size_t)src[kq][i] * p.cin + ci0 + ag * 8 : 0;
-                        cp_async16(slot + adst[i], plane + off, ok ? 16u : 0u);
+                    for (int i = 0; i < APT; ++i) {
+                        const bool ign = src[kq][i] < 0 || !acol_ok;
+                        const uint64_t off = (uint64_t)(uint32_t)max(src[kq][i], 0) * x_row_bytes;
+                        cp_async16_pred(slot + (uint32_t)i * (128u * RSTEP), plane + off, ign);
                     }
-                    cp_async_arrive_noinc(smem_u32(&a_full[as]));
-                    if (++as == p.a_slots) {
-                        as = 0;
-                        apar ^= 1u;
+                    cp_async_arrive_noinc(smem_u32(&a_full[m][as[m]]));
+                    if (++as[m] == p.a_slots) {
+                        as[m] = 0;
+                        apar[m] ^= 1u;
                     }
                 }
             }
         }
         cp_async_wait_all();
+        const long long pt1 = PROF ? clock64() : 0;
 
         // ------------------------------------------------------------------ epilogue: lanes = ci, columns = co
         if (touched) {
             mbar_wait(smem_u32(&acc_full), 0, 2);
             tc_fence_after();
-            const int ci = warp * 32 + lane;  // warp w owns TMEM lanes 32 w .. 32 w + 31
+            // warp w may touch TMEM lanes 32 (w % 4) .. + 31; the PROD_WARPS / 4 warps of a lane quarter take alternate 16-column chunks
+            const int ci = (warp & 3) * 32 + lane;
             const bool ci_ok = ci0 + ci < p.cin;
+            constexpr int CW = PROD_WARPS / 4;
             for (int kq = 0; kq < nk; ++kq) {
                 if (!((touched >> (k0 + kq)) & 1u)) continue;
                 float *drow = p.dw + ((size_t)(k0 + kq) * p.cin + ci0 + ci) * p.cout;
-                const uint32_t taddr = tmem_base + (uint32_t)(kq * p.npad) + ((uint32_t)(warp * 32) << 16);
-                for (int col = 0; col < p.cout; col += 16) {
+                const uint32_t taddr = tmem_base + (uint32_t)(kq * p.npad) + ((uint32_t)((warp & 3) * 32) << 16);
+                for (int col = (warp >> 2) * 16; col < p.cout; col += 16 * CW) {
                     float acc[16];
                     tmem_ld16(taddr + (uint32_t)col, acc);
                     if (ci_ok) {
@@ -191,26 +238,48 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad(Params p) {
                 }
             }
         }
+        if (PROF && p.prof != nullptr && tid == 0) {
+            long long *o = p.prof + (size_t)blockIdx.x * 16;
+            o[0] = pt1 - pt0;          // producer loop
+            o[1] = pw_b;               // ... waiting for a free dY slot
+            o[2] = pw_a;               // ... waiting for a free X slot
+            o[3] = clock64() - pt1;    // epilogue (incl. the wait for the last MMAs)
+        }
     } else {
-        // ------------------------------------------------------------------ MMA issuer (uniform warp, elected lane)
-        const uint32_t idesc = idesc_bf16(p.npad, true, true);
-        const uint64_t a_desc0 = desc_mn_sw128(a_base, SLAB), b_desc0 = desc_mn_sw128(b_base, SLAB);
+        // ------------------------------------------------------------------ MMA issuers (uniform warps, one elected lane issues)
+        // tcgen05.mma issue blocks for about the instruction's execution time, so a single issuing warp leaves the tensor pipe idle
+        // while it waits for a slot, fences and books (measured: 58 % issue, 42 % other).  Two warps, each with its own offsets,
+        // accumulators and A ring, keep the pipe fed; both consume every dY tile.
+        const int mw = warp - MMA_WARP;
+        const uint32_t idesc = idesc_bf16(p.nmma, true, true);  // N = cout rounded up to 16: columns past it are never read back
+        const uint64_t a_desc0 = desc_mn_sw128(a_base + (uint32_t)(mw * p.a_slots) * A_SLOT, SLAB), b_desc0 = desc_mn_sw128(b_base, SLAB);
         int as = 0, bs = 0;
-        uint32_t apar = 0, bpar = 0;
+        uint32_t apar = 0, bpar = 0, mine = 0;  // mine: offsets of this warp that received an MMA
+        long long mw_b = 0, mw_a = 0, m_issue = 0, n_slots = 0;
+        const long long mt0 = PROF ? clock64() : 0;
         for (int r0 = r_begin; r0 < r_end; r0 += R) {
             const uint32_t act = active(r0);
             if (!act) continue;
+            touched |= act;
+            const long long twb = PROF ? clock64() : 0;
             mbar_wait(smem_u32(&b_full[bs]), bpar, 3);
+            if (PROF) mw_b += clock64() - twb;
             const uint64_t db_hi = b_desc0 + (uint64_t)((uint32_t)(bs * b_slot_bytes) >> 4);
             const uint64_t db_lo = db_hi + (uint64_t)((uint32_t)b_plane >> 4);
-            for (int kq = 0; kq < nk; ++kq) {
+            for (int kq = mw; kq < nk; kq += NMW) {
                 const int k = k0 + kq;
                 if (!((act >> k) & 1u)) continue;
                 const uint32_t acc = tmem_base + (uint32_t)(kq * p.npad);
-                const uint32_t first = (touched >> k) & 1u;
+                const uint32_t first = (mine >> k) & 1u;
 #pragma unroll
                 for (int pl = 0; pl < NPL; ++pl) {
-                    mbar_wait(smem_u32(&a_full[as]), apar, 4);
+                    const long long twa = PROF ? clock64() : 0;
+                    mbar_wait(smem_u32(&a_full[mw][as]), apar, 4);
+                    const long long ti0 = PROF ? clock64() : 0;
+                    if (PROF) {
+                        mw_a += ti0 - twa;
+                        ++n_slots;
+                    }
                     fence_proxy_async();  // cp.async writes of the producers (generic proxy) -> tcgen05 reads (async proxy)
                     tc_fence_after();
                     const uint64_t da = a_desc0 + (uint64_t)((uint32_t)(as * A_SLOT) >> 4);
@@ -229,17 +298,18 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad(Params p) {
                                 umma(acc, da + adv, db_hi + adv, idesc, 1);
                             }
                         }
-                        umma_commit(smem_u32(&a_empty[as]));
+                        umma_commit(smem_u32(&a_empty[mw][as]));
                     }
                     __syncwarp();
+                    if (PROF) m_issue += clock64() - ti0;
                     if (++as == p.a_slots) {
                         as = 0;
                         apar ^= 1u;
                     }
                 }
-                touched |= 1u << k;
+                mine |= 1u << k;
             }
-            if (elect_one()) umma_commit(smem_u32(&b_empty[bs]));
+            if (elect_one()) umma_commit(smem_u32(&b_empty[bs]));  // arrives once this warp's MMAs on the tile are done (at once if none)
             __syncwarp();
             if (++bs == p.b_slots) {
                 bs = 0;
@@ -248,6 +318,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad(Params p) {
         }
         if (touched && elect_one()) umma_commit(smem_u32(&acc_full));
         __syncwarp();
+        if (PROF && p.prof != nullptr && lane == 0 && mw == 0) {
+            long long *o = p.prof + (size_t)blockIdx.x * 16;
+            o[4] = clock64() - mt0;  // MMA warp loop
+            o[5] = mw_b;             // ... waiting for dY
+            o[6] = mw_a;             // ... waiting for gathered X
+            o[7] = m_issue;          // ... fence + issue + commit
+            o[8] = n_slots;
+        }
     }
 
     tc_fence_before();
@@ -275,7 +353,12 @@ k_permute_planes(const uint4 *__restrict__ hi, const uint4 *__restrict__ lo, con
 
 using namespace us3d;
 
+static long long *g_wgrad_prof = nullptr;
+
 extern "C" {
+
+/* debug hook (include/us3d_debug.h): per-CTA cycle counters of the weight-gradient kernel's roles, 16 int64 per CTA */
+void us3d_debug_set_prof_wgrad(void *buf) { g_wgrad_prof = (long long *)buf; }
 
 int us3d_spconv_wgrad_planes(const void *x_hi, const void *x_lo, const void *dy_hi, const void *dy_lo, const int32_t *nbr,
                              int n_rows, int kvol, float *dw, int cin, int cout, int passes, const uint32_t *tile_mask,
@@ -291,6 +374,7 @@ int us3d_spconv_wgrad_planes(const void *x_hi, const void *x_lo, const void *dy_
     p.dy_hi = (const __nv_bfloat16 *)dy_hi; p.dy_lo = (const __nv_bfloat16 *)dy_lo;
     p.nbr = nbr; p.n_rows = n_rows; p.kvol = kvol; p.dw = dw; p.cin = cin; p.cout = cout; p.tile_mask = tile_mask; p.dy_rows = dy_rows;
     p.npad = ceil_div(cout, 64) * 64;
+    p.nmma = ceil_div(cout, 16) * 16;
     p.mblks = ceil_div(cin, 128);
     int kg = 512 / p.npad;
     if (kg > wg::MAX_KG) kg = wg::MAX_KG;
@@ -312,25 +396,29 @@ int us3d_spconv_wgrad_planes(const void *x_hi, const void *x_lo, const void *dy_
     const int a_slot = 2 * wg::SLAB, b_slot = npl * (p.npad / 64) * wg::SLAB;
     const int budget = 220 * 1024;
     p.b_slots = 2;
-    p.a_slots = (budget - p.b_slots * b_slot) / a_slot;
+    p.a_slots = (budget - p.b_slots * b_slot) / a_slot / wg::NMW;  // per A ring (one ring per MMA-issuing warp)
     if (p.a_slots > wg::MAX_A) p.a_slots = wg::MAX_A;
     US3D_CHECK_ARG(p.a_slots >= 2, "spconv_wgrad_planes: operand slots do not fit in shared memory (cout %d)", cout);
-    const size_t smem = (size_t)p.a_slots * a_slot + (size_t)p.b_slots * b_slot + 1024;
+    const size_t smem = (size_t)(wg::NMW * p.a_slots) * a_slot + (size_t)p.b_slots * b_slot + 1024;
     static bool attr_done[64] = {};  // the opt-in for > 48 KB of dynamic shared memory is per device
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !attr_done[dev]) {
-        US3D_CUDA(cudaFuncSetAttribute(wg::k_wgrad<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-        US3D_CUDA(cudaFuncSetAttribute(wg::k_wgrad<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        US3D_CUDA(cudaFuncSetAttribute(wg::k_wgrad<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        US3D_CUDA(cudaFuncSetAttribute(wg::k_wgrad<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        US3D_CUDA(cudaFuncSetAttribute(wg::k_wgrad<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
         attr_done[dev] = true;
     }
     const int grid = p.ngroups * p.mblks * p.splits;
     {
         ProfScope prof(st, 1, n_rows, n_rows, kvol, cin, cout);
-        if (passes == 3)
-            wg::k_wgrad<3><<<grid, wg::THREADS, smem, st>>>(p);
+        p.prof = g_wgrad_prof;
+        if (passes == 3 && p.prof != nullptr)
+            wg::k_wgrad<3, true><<<grid, wg::THREADS, smem, st>>>(p);
+        else if (passes == 3)
+            wg::k_wgrad<3, false><<<grid, wg::THREADS, smem, st>>>(p);
         else
-            wg::k_wgrad<1><<<grid, wg::THREADS, smem, st>>>(p);
+            wg::k_wgrad<1, false><<<grid, wg::THREADS, smem, st>>>(p);
     }
     US3D_LAUNCH_CHECK();
     return 0;

@@ -68,6 +68,22 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32
 __device__ __forceinline__ void cp_async4(uint32_t dst, const void *src, uint32_t src_bytes) {  // zero-fills 4 - src_bytes
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+// 16 / 4-byte cp.async with the PTX ignore-src operand: `ignore` -> zeros are written and the source is not read.  One LDGSTS with a
+// predicate; the src-size form above makes ptxas emit ~8 instructions of size / address arithmetic per copy (profiles/r2_conv_pipeline.md).
+__device__ __forceinline__ void cp_async16_pred(uint32_t dst, const void *src, bool ignore) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %2, 0;\n\t"
+        "cp.async.cg.shared.global [%0], [%1], 16, p;\n\t}" ::"r"(dst), "l"(src), "r"((uint32_t)ignore)
+        : "memory");
+}
+__device__ __forceinline__ void cp_async4_pred(uint32_t dst, const void *src, bool ignore) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %2, 0;\n\t"
+        "cp.async.ca.shared.global [%0], [%1], 4, p;\n\t}" ::"r"(dst), "l"(src), "r"((uint32_t)ignore)
+        : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
