@@ -40,11 +40,17 @@ using namespace tcx;
 constexpr int M = 128;
 constexpr int KC = 64;
 constexpr int A_PLANE = M * 128;  // bytes of one plane of one A slot
-constexpr int PROD_WARPS = 4;
+#ifndef US3D_MT_PROD_WARPS
+#define US3D_MT_PROD_WARPS 8
+#endif
+constexpr int PROD_WARPS = US3D_MT_PROD_WARPS;
 constexpr int B_WARP = PROD_WARPS, MMA_WARP = PROD_WARPS + 1, EPI_WARP0 = PROD_WARPS + 2;
 constexpr int IDX_WARP = PROD_WARPS + 6;
 constexpr int MMA_WARP_EXTRA0 = PROD_WARPS + 7;  // MMA warps 1 .. MAX_T-1 (one MMA-issuing warp per tile of the group)
-constexpr int THREADS = (PROD_WARPS + 2 + 4 + 1 + 3) * 32;
+constexpr int EPI2_WARP0 = PROD_WARPS + 10;      // second epilogue set (PROD_WARPS % 4 == 0: warp % 4 covers the four TMEM lane quarters)
+constexpr int EPI_SETS = 2;                      // epilogue set e reads out tiles t = e, e + 2 of a group
+constexpr int THREADS = (PROD_WARPS + 2 + 4 + 1 + 3 + 4) * 32;
+static_assert(PROD_WARPS % 4 == 0, "epilogue warps are placed by warp % 4");
 constexpr int MAX_A = 8, MAX_B = 3, MAX_T = 4;
 constexpr int NIDX = 4;  // stages of the neighbour-index ring (one stage = the indices of one offset for the T tiles)
 
@@ -71,7 +77,7 @@ template <int PASSES, int LAG, bool FUSE, bool PROF>
 __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
     static_assert(!FUSE || PASSES == 3, "the fused [W_hi | W_lo] operand exists in three-term mode only");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t a_full[MAX_A], a_empty[MAX_A], b_full[MAX_B], b_empty[MAX_B], acc_full, acc_empty;
+    __shared__ __align__(8) uint64_t a_full[MAX_A], a_empty[MAX_A], b_full[MAX_B], b_empty[MAX_B], acc_full[MAX_T], acc_empty[MAX_T];
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(8) uint64_t idx_full[NIDX], idx_empty[NIDX];
     __shared__ int32_t idx_ring[NIDX][MAX_T][M];
@@ -100,8 +106,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
             mbar_init(smem_u32(&idx_full[s]), 32);
             mbar_init(smem_u32(&idx_empty[s]), PROD_WARPS);
         }
-        mbar_init(smem_u32(&acc_full), T);
-        mbar_init(smem_u32(&acc_empty), 4);
+        for (int t = 0; t < MAX_T; ++t) {  // per tile: MMA warp t -> the epilogue set of tile t -> MMA warp t
+            mbar_init(smem_u32(&acc_full[t]), 1);
+            mbar_init(smem_u32(&acc_empty[t]), 4);
+        }
         mbar_fence_init();
     }
     if (warp == MMA_WARP) tmem_alloc(&tmem_base_s, tmem_cols);
@@ -149,7 +157,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
         // ------------------------------------------------------------------ A producers
         // Neighbour indices come from the index ring in shared memory (filled ahead of time by the index warp): no global
         // load sits between two gathers, and no index lives in a register across an item.
-        constexpr int RPT = 8;       // rows per thread: rbase + 16 i
+        constexpr int RSTEP = PROD_WARPS * 4, RPT = M / RSTEP;  // rows per thread: rbase + RSTEP i
         const int grp = tid & 7;     // 16-byte chunk within the 128-byte row
         const int rbase = tid >> 3;
         int item = 0, signalled = 0;
@@ -188,7 +196,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
                         const int lim = col_ok ? p.n_rows - (tile0 + t) * M : 0;  // rows of the tile inside the map (0: nothing to fetch)
                         int idx[RPT];
 #pragma unroll
-                        for (int i = 0; i < RPT; ++i) idx[i] = idx_ring[is][t][rbase + 16 * i];
+                        for (int i = 0; i < RPT; ++i) idx[i] = idx_ring[is][t][rbase + RSTEP * i];
                         const int ps = t + T * pos[t];
                         const uint32_t ppar = par[t];
                         if (++pos[t] == spt) {
@@ -199,10 +207,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
                         const uint32_t slot = a_base + (uint32_t)ps * A_SLOT + (uint32_t)rbase * 128u + (uint32_t)((grp ^ (rbase & 7)) << 4);
 #pragma unroll
                         for (int i = 0; i < RPT; ++i) {
-                            const bool ign = idx[i] < 0 || rbase + 16 * i >= lim;
+                            const bool ign = idx[i] < 0 || rbase + RSTEP * i >= lim;
                             const uint64_t off = (uint64_t)(uint32_t)max(idx[i], 0) * row_bytes;
-                            cp_async16_pred(slot + (uint32_t)i * 2048u, col_hi + off, ign);
-                            if (PASSES == 3) cp_async16_pred(slot + (uint32_t)i * 2048u + A_PLANE, col_lo + off, ign);
+                            cp_async16_pred(slot + (uint32_t)i * (128u * RSTEP), col_hi + off, ign);
+                            if (PASSES == 3) cp_async16_pred(slot + (uint32_t)i * (128u * RSTEP) + A_PLANE, col_lo + off, ign);
                         }
                         if (LAG == 0) {
                             cp_async_arrive_noinc(smem_u32(&a_full[ps]));
@@ -328,7 +336,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
                 U |= m[t];
             }
             long long tw0 = PROF ? clock64() : 0;
-            mbar_wait(smem_u32(&acc_empty), (siter & 1) ^ 1, 2);
+            mbar_wait(smem_u32(&acc_empty[mw]), (siter & 1) ^ 1, 2);
             if (PROF) w_acc += clock64() - tw0;
             tc_fence_after();
             uint32_t started = 0;
@@ -393,9 +401,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
             }
             if (elect_one()) {
                 if (started)
-                    umma_commit(smem_u32(&acc_full));
+                    umma_commit(smem_u32(&acc_full[mw]));
                 else
-                    mbar_arrive(smem_u32(&acc_full));
+                    mbar_arrive(smem_u32(&acc_full[mw]));
             }
             __syncwarp();
         }
@@ -409,8 +417,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
             o[5] = bitem;
             o[6] = t_first;  // cycles until the first gathered tile has landed (prologue + one index + one gather round trip)
         }
-    } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + 4) {
+    } else if ((warp >= EPI_WARP0 && warp < EPI_WARP0 + 4) || (warp >= EPI2_WARP0 && warp < EPI2_WARP0 + 4)) {
         // ------------------------------------------------------------------ epilogue
+        // Two sets of four warps; set e reads out tiles e, e + 2 of every group.  Each tile has its own accumulator barriers, so the
+        // MMA warp of a tile starts the next group as soon as ITS accumulator has been read, while the other tiles are still being
+        // written; everything that does not depend on the accumulator (tile mask, output row) is fetched before the wait.
+        const int eset = warp >= EPI2_WARP0 ? 1 : 0;
         const int quarter = warp & 3;
         const bool vec = (p.ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
         int siter = 0;
@@ -419,28 +431,31 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
         uint32_t pm;
         for (int ui = 0; unit(ui, tile0, nt, pm); ++ui, ++siter) {
             const int part = p.ksplit == 1 ? 0 : (blockIdx.x + ui * gridDim.x) % p.ksplit;
-            mbar_wait(smem_u32(&acc_full), siter & 1, 5);
-            tc_fence_after();
-            for (int t = 0; t < nt; ++t) {
+            for (int t = eset; t < T; t += EPI_SETS) {
                 const int tile = tile0 + t;
-                if (tile >= p.n_tiles) break;
-                const bool has_acc = tile_kmask(tile, pm) != 0;
+                const bool live = t < nt && tile < p.n_tiles;
+                const bool has_acc = live && tile_kmask(tile, pm) != 0;
                 const int j = tile * M + quarter * 32 + lane;
-                const bool row_ok = j < p.n_rows;
+                const bool row_ok = live && j < p.n_rows;
                 float *yrow = nullptr;
                 if (row_ok)
                     yrow = split ? p.ws + ((size_t)part * p.n_rows + j) * p.cout
                                  : p.y + (size_t)(p.out_rows ? p.out_rows[j] : j) * p.ldy;
+                mbar_wait(smem_u32(&acc_full[t]), siter & 1, 5);
+                tc_fence_after();
                 const uint32_t acc_addr = tmem_base + (uint32_t)(t * p.acc_cols) + ((uint32_t)(quarter * 32) << 16);
-                for (int col = 0; col < p.cout; col += 16) {
+                for (int col = 0; live && col < p.cout; col += 16) {
                     float acc[16];
                     if (has_acc) {
-                        tmem_ld16(acc_addr + (uint32_t)col, acc);
-                        if (FUSE) {
+                        if (FUSE) {  // both column groups requested before the one wait
                             float acc2[16];
-                            tmem_ld16(acc_addr + (uint32_t)(p.cout + col), acc2);
+                            tmem_ld16_nowait(acc_addr + (uint32_t)col, acc);
+                            tmem_ld16_nowait(acc_addr + (uint32_t)(p.cout + col), acc2);
+                            tmem_ld_wait(acc, acc2);
 #pragma unroll
                             for (int e = 0; e < 16; ++e) acc[e] += acc2[e];
+                        } else {
+                            tmem_ld16(acc_addr + (uint32_t)col, acc);
                         }
                     } else {
 #pragma unroll
@@ -472,10 +487,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
                         for (int e = 0; e < 16; ++e) yrow[col + e] = p.accumulate ? yrow[col + e] + acc[e] : acc[e];
                     }
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&acc_empty[t]));
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&acc_empty));
         }
     }
 
