@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define US3D_ABI_VERSION 16
+#define US3D_ABI_VERSION 17
 #define US3D_MAX_KVOL 27
 
 int us3d_abi_version(void);
@@ -110,6 +110,23 @@ int us3d_spconv_gather_mt(const void *x_hi, const void *x_lo, int n_in, const in
                           const void *wpack, int cin, int cout, int passes, const float *bias, const int32_t *out_rows,
                           float *y, int ldy, int accumulate, const uint32_t *tile_mask, const int32_t *partition,
                           void *workspace, long long workspace_bytes, void *stream);
+/* The same launch with the BatchNorm statistics of y folded in (MinkowskiConvolution -> MinkowskiBatchNorm,
+ * /root/reference/models/modules/common.py:20-22, resnet_block.py:48-58): the epilogue (or, on split maps, the pass that sums the
+ * partial tiles) adds the column sums and sums of squares of the rows it writes, the last CTA finalises mean / invstd and the
+ * running statistics exactly like us3d_bn_stats_fused — one launch and one read of y fewer per normalised convolution.
+ * bn == NULL: plain us3d_spconv_gather_mt.  bn->ws: the scratch of us3d_bn_workspace_bytes (zero on entry, zero on exit);
+ * running_mean / running_var / num_batches_tracked may be NULL; accumulate must be 0. */
+typedef struct us3d_bn_fuse {
+    double *ws;
+    float *mean, *invstd;                 /* out: [cout] */
+    float *running_mean, *running_var;    /* in/out, may be NULL */
+    long long *num_batches_tracked;       /* in/out, may be NULL */
+    float eps, momentum;
+} us3d_bn_fuse_t;
+int us3d_spconv_gather_mt_bn(const void *x_hi, const void *x_lo, int n_in, const int32_t *nbr, int n_rows, int kvol,
+                             const void *wpack, int cin, int cout, int passes, const float *bias, const int32_t *out_rows,
+                             float *y, int ldy, int accumulate, const uint32_t *tile_mask, const int32_t *partition,
+                             void *workspace, long long workspace_bytes, const us3d_bn_fuse_t *bn, void *stream);
 /* workspace (may be NULL; 16-byte aligned, contents irrelevant): room for the partial tiles of the split mode,
  * [parts][n_rows][cout] fp32, summed in part order by a second launch (no atomics: results are bit-reproducible).
  * us3d_spconv_gather_mt_workspace_bytes = the most the launcher can use for a map (0: it would not split).             */

@@ -30,6 +30,8 @@ void us3d_debug_set_prof_wgrad(void *buf);
  * operand (1 = off, 2 = on where eligible). */
 void us3d_debug_set_tuning4(int a_slots, int lag, int T, int fuse);
 void us3d_debug_set_tuning(int a_slots, int lag, int T);
+/* accumulator sets of us3d_spconv_gather_mt: 0 = launcher's choice, 1 = one, 2 = two (tile groups shrink to fit the 512 TMEM columns) */
+void us3d_debug_set_tuning_acc(int sets);
 
 #ifdef __cplusplus
 }

@@ -263,6 +263,46 @@ def test_convolution_on_pattern_ordered_tables(eng, ora, cin, cout, ks, stride):
     assert rel_err(outs[1][2], outs[0][2]) < 1e-5
 
 
+@pytest.mark.parametrize("n,cin,cout,order_rows", [(60000, 32, 96, 0), (60000, 32, 96, 1 << 30), (4000, 64, 64, 1 << 30), (131, 16, 256, 1 << 30),
+                                                  (40001, 96, 32, 0)])
+def test_batchnorm_statistics_from_the_convolution_epilogue(eng, n, cin, cout, order_rows):
+    """us3d_spconv_gather_mt_bn: mean / invstd / running statistics / counter produced by the convolution launch itself (epilogue
+    of the range mode on large and pattern-ordered maps, the partial-tile reduction on small maps) equal those the statistics
+    kernel computes from the written y (same sums, other order: 1e-5), including a ragged last tile; the scratch is left zero."""
+    from unscene3d_b200.engine import coords as C
+    from unscene3d_b200.engine import functional as Fn
+
+    C.set_row_ordering(order_rows)
+    try:
+        c = random_scene(n, 77, batch=2, extent=64)
+        x = eng.SparseTensor(torch.zeros(c.shape[0], 1, device="cuda"), torch.from_numpy(c).cuda())
+        cm, key = x.coordinate_manager, x.coordinate_map_key
+        table = cm.forward_table(key, key, (3, 3, 3))
+        g = torch.Generator(device="cuda").manual_seed(5)
+        f = torch.randn(table.n_rows, cin, device="cuda", generator=g) + 0.3
+        w = torch.randn(27, cin, cout, device="cuda", generator=g) * 0.05
+        rm0, rv0 = torch.randn(cout, device="cuda", generator=g), torch.rand(cout, device="cuda", generator=g) + 0.5
+        res = []
+        for fused in (True, False):
+            Fn.set_fused_bn_stats(fused)
+            rm, rv, nbt = rm0.clone(), rv0.clone(), torch.tensor(3, device="cuda")
+            req = Fn.BnRequest(rm, rv, 0.1, 1e-5, nbt)
+            y = Fn.spconv_gather(f, table, w, cin, cout, False, False, bn=req)
+            res.append((y, req.mean.clone(), req.invstd.clone(), rm, rv, int(nbt)))
+        # y: same products; on large maps the launch with statistics keeps two accumulator sets and the unfused weight operand,
+        # i.e. another fp32 summation order of the three split terms
+        assert rel_err(res[0][0], res[1][0]) < 1e-5
+        ref_mean, ref_var = res[1][0].double().mean(0), res[1][0].double().var(0, unbiased=False)
+        assert rel_err(res[1][1], ref_mean) < 1e-5 and rel_err(res[1][2], (ref_var + 1e-5).rsqrt()) < 1e-5
+        for a, b in zip(res[0][1:5], res[1][1:5]):
+            assert rel_err(a, b) < 1e-5
+        assert res[0][5] == res[1][5] == 4
+        assert float(Fn._bn_workspace(f.device, cout)[: 2 * cout + 1].abs().max()) == 0.0
+    finally:
+        Fn.set_fused_bn_stats(True)
+        C.set_row_ordering(32768)
+
+
 def test_transposed_convolution_on_pattern_ordered_tables(eng, ora):
     from unscene3d_b200.engine import coords as C
 

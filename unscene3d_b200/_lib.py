@@ -9,6 +9,13 @@ LIB_PATH = os.environ.get("US3D_LIB") or os.path.join(_HERE, "csrc", "libus3d.so
 _i, _ll, _f = ctypes.c_int, ctypes.c_longlong, ctypes.c_float
 _p = ctypes.c_void_p
 
+class BnFuse(ctypes.Structure):
+    """us3d_bn_fuse_t (include/us3d.h): BatchNorm statistics folded into us3d_spconv_gather_mt_bn."""
+
+    _fields_ = [("ws", _p), ("mean", _p), ("invstd", _p), ("running_mean", _p), ("running_var", _p), ("num_batches_tracked", _p),
+                ("eps", _f), ("momentum", _f)]
+
+
 # name -> argtypes (all functions return int unless listed in _RESTYPE)
 PROTOTYPES = {
     "us3d_abi_version": [],
@@ -25,6 +32,7 @@ PROTOTYPES = {
     "us3d_spconv_pack_weights": [_p, _i, _i, _i, _i, _i, _i, _p, _p],
     "us3d_split_bf16": [_p, _i, _i, _i, _p, _p, _p],
     "us3d_spconv_gather_mt": [_p, _p, _i, _p, _i, _i, _p, _i, _i, _i, _p, _p, _p, _i, _i, _p, _p, _p, _ll, _p],
+    "us3d_spconv_gather_mt_bn": [_p, _p, _i, _p, _i, _i, _p, _i, _i, _i, _p, _p, _p, _i, _i, _p, _p, _p, _ll, _p, _p],
     "us3d_spconv_gather_mt_workspace_bytes": [_i, _i, _i],
     "us3d_spconv_partition_size": [],
     "us3d_spconv_partition": [_p, _i, _i, _p, _p],

@@ -54,6 +54,68 @@ static_assert(PROD_WARPS % 4 == 0, "epilogue warps are placed by warp % 4");
 constexpr int MAX_A = 8, MAX_B = 3, MAX_T = 4;
 constexpr int NIDX = 4;  // stages of the neighbour-index ring (one stage = the indices of one offset for the T tiles)
 
+// BatchNorm statistics of the output, folded into the epilogue (ws == NULL: off).  ws = 2 cout doubles (column sums, sums of
+// squares) + a ticket, zero on entry and zero again on exit — the same scratch and the same finalisation as us3d_bn_stats_fused.
+struct BnFuse {
+    double *ws;
+    float *mean, *invstd, *running_mean, *running_var;
+    long long *num_batches_tracked;
+    float eps, momentum;
+};
+
+// Column sums over the 32 rows of a warp: lane l holds v[0..15] of its row; on return v[0] of lane l is the sum of column
+// ((l >> 1) & 15 read as bits 4..1 of l: 8 (l>>4 & 1) + 4 (l>>3 & 1) + 2 (l>>2 & 1) + (l>>1 & 1)) over all 32 lanes.
+// A halving butterfly: 8 + 4 + 2 + 1 + 1 shuffles.
+__device__ __forceinline__ void warp_colsum16(float (&v)[16], int lane) {
+#pragma unroll
+    for (int w = 8, bit = 16; w >= 1; w >>= 1, bit >>= 1) {
+#pragma unroll
+        for (int i = 0; i < w; ++i) {
+            const bool up = (lane & bit) != 0;
+            const float keep = up ? v[i + w] : v[i];
+            const float send = up ? v[i] : v[i + w];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+        }
+    }
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+__device__ __forceinline__ int warp_colsum16_col(int lane) {
+    return 8 * ((lane >> 4) & 1) + 4 * ((lane >> 3) & 1) + 2 * ((lane >> 2) & 1) + ((lane >> 1) & 1);
+}
+
+// The CTA's column sums (shared memory, [2][c] floats) go to the global fp64 scratch; the CTA that takes the last ticket
+// finalises mean / invstd / running statistics and zeroes the scratch (fused::k_bn_stats_fused does the same after its own sums).
+__device__ __forceinline__ void bn_publish_and_finalize(const BnFuse &bn, const float *s_sum, int c, int n, int tid, int nthreads,
+                                                        unsigned int n_ctas, bool *last_s) {
+    for (int k = tid; k < 2 * c; k += nthreads) atomicAdd(&bn.ws[k], (double)s_sum[k]);
+    __threadfence();
+    __syncthreads();
+    unsigned int *ticket = reinterpret_cast<unsigned int *>(bn.ws + 2 * c);
+    if (tid == 0) *last_s = atomicAdd(ticket, 1u) == n_ctas - 1;
+    __syncthreads();
+    if (!*last_s) return;
+    __threadfence();
+    for (int k = tid; k < c; k += nthreads) {
+        const double sum = __ldcg(&bn.ws[k]), sq = __ldcg(&bn.ws[c + k]);
+        const double m = sum / n;
+        double var = sq / n - m * m;
+        if (var < 0) var = 0;
+        bn.mean[k] = (float)m;
+        bn.invstd[k] = (float)(1.0 / sqrt(var + (double)bn.eps));
+        if (bn.running_mean) bn.running_mean[k] = (float)((1.0 - bn.momentum) * bn.running_mean[k] + bn.momentum * m);
+        if (bn.running_var) {
+            const double unbiased = n > 1 ? var * n / (n - 1.0) : var;
+            bn.running_var[k] = (float)((1.0 - bn.momentum) * bn.running_var[k] + bn.momentum * unbiased);
+        }
+        bn.ws[k] = 0.0;
+        bn.ws[c + k] = 0.0;
+    }
+    if (tid == 0) {
+        *ticket = 0u;
+        if (bn.num_batches_tracked) *bn.num_batches_tracked += 1;
+    }
+}
+
 struct Params {
     const __nv_bfloat16 *x_hi, *x_lo;  // [n_in, cin] planes
     const int32_t *nbr;
@@ -66,21 +128,26 @@ struct Params {
     int ldy, accumulate;
     const uint32_t *tile_mask;
     int a_slots, b_slots, b_plane, acc_cols;
+    int dbl;                              // 1: two accumulator sets, the epilogue of a tile group overlaps the next group's MMAs
     float *ws;                            // split mode: partial tiles [ksplit][n_rows][cout]
     const int32_t *part;                  // range mode: tiles [part[b], part[b + 1]) belong to CTA b (NULL: equal counts)
     int ksplit, n_units;                  // small maps: the offsets of a tile are dealt to `ksplit` CTAs (T == 1)
     uint32_t part_mask[US3D_MAX_KVOL];    // offsets handled by part q (k % ksplit == q)
     long long *prof;  // optional per-CTA wait-cycle counters of the MMA thread (debug)
+    BnFuse bn;        // range mode: statistics of y from the epilogue; split mode: from k_reduce_parts
 };
 
 template <int PASSES, int LAG, bool FUSE, bool PROF>
 __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
     static_assert(!FUSE || PASSES == 3, "the fused [W_hi | W_lo] operand exists in three-term mode only");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t a_full[MAX_A], a_empty[MAX_A], b_full[MAX_B], b_empty[MAX_B], acc_full[MAX_T], acc_empty[MAX_T];
+    __shared__ __align__(8) uint64_t a_full[MAX_A], a_empty[MAX_A], b_full[MAX_B], b_empty[MAX_B], acc_full[2 * MAX_T], acc_empty[2 * MAX_T];  // [set][tile]
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(8) uint64_t idx_full[NIDX], idx_empty[NIDX];
     __shared__ int32_t idx_ring[NIDX][MAX_T][M];
+    __shared__ float bn_sum[2 * 256];  // column sums / sums of squares of this CTA's output rows (cout <= 256)
+    __shared__ bool bn_last;
+    const bool bn_on = p.bn.ws != nullptr && p.ksplit == 1;
     constexpr int NPL = PASSES == 3 ? 2 : 1;
     constexpr int A_SLOT = NPL * A_PLANE;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -91,7 +158,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
     const uint32_t all_k = p.kvol >= 32 ? 0xFFFFFFFFu : ((1u << p.kvol) - 1u);
     const int T = p.T;
     uint32_t tmem_cols = 32;  // tcgen05.alloc takes a power of two >= 32 (T = 3 accumulators of 128 columns -> 512)
-    while (tmem_cols < (uint32_t)(T * p.acc_cols)) tmem_cols <<= 1;
+    while (tmem_cols < (uint32_t)(T * p.acc_cols * (1 + p.dbl))) tmem_cols <<= 1;
 
     if (tid == 0) {
         for (int s = 0; s < p.a_slots; ++s) {
@@ -106,13 +173,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
             mbar_init(smem_u32(&idx_full[s]), 32);
             mbar_init(smem_u32(&idx_empty[s]), PROD_WARPS);
         }
-        for (int t = 0; t < MAX_T; ++t) {  // per tile: MMA warp t -> the epilogue set of tile t -> MMA warp t
+        for (int t = 0; t < 2 * MAX_T; ++t) {  // per accumulator: MMA warp t -> the epilogue set of tile t -> MMA warp t
             mbar_init(smem_u32(&acc_full[t]), 1);
             mbar_init(smem_u32(&acc_empty[t]), 4);
         }
         mbar_fence_init();
     }
     if (warp == MMA_WARP) tmem_alloc(&tmem_base_s, tmem_cols);
+    if (bn_on && threadIdx.x < 2 * 256) bn_sum[threadIdx.x] = 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -336,7 +404,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
                 U |= m[t];
             }
             long long tw0 = PROF ? clock64() : 0;
-            mbar_wait(smem_u32(&acc_empty[mw]), (siter & 1) ^ 1, 2);
+            // accumulator set of this group and how often it has been used before (the barrier's phase)
+            const int aset = p.dbl ? (siter & 1) : 0, ause = p.dbl ? (siter >> 1) : siter;
+            mbar_wait(smem_u32(&acc_empty[aset * MAX_T + mw]), (ause & 1) ^ 1, 2);
             if (PROF) w_acc += clock64() - tw0;
             tc_fence_after();
             uint32_t started = 0;
@@ -364,7 +434,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
                         tc_fence_after();
                         const uint64_t da_hi = a_desc0 + (uint64_t)((uint32_t)(as * A_SLOT) >> 4);
                         const uint64_t da_lo = da_hi + (uint64_t)(A_PLANE >> 4);
-                        const uint32_t acc = tmem_base + (uint32_t)(t * p.acc_cols);
+                        const uint32_t acc = tmem_base + (uint32_t)((aset * T + t) * p.acc_cols);
                         const uint32_t first = (started >> t) & 1u;
                         if (elect_one()) {
                             for (int kk = 0; kk < ksteps; ++kk) {
@@ -401,9 +471,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
             }
             if (elect_one()) {
                 if (started)
-                    umma_commit(smem_u32(&acc_full[mw]));
+                    umma_commit(smem_u32(&acc_full[aset * MAX_T + mw]));
                 else
-                    mbar_arrive(smem_u32(&acc_full[mw]));
+                    mbar_arrive(smem_u32(&acc_full[aset * MAX_T + mw]));
             }
             __syncwarp();
         }
@@ -431,6 +501,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
         uint32_t pm;
         for (int ui = 0; unit(ui, tile0, nt, pm); ++ui, ++siter) {
             const int part = p.ksplit == 1 ? 0 : (blockIdx.x + ui * gridDim.x) % p.ksplit;
+            const int aset = p.dbl ? (siter & 1) : 0, ause = p.dbl ? (siter >> 1) : siter;
             for (int t = eset; t < T; t += EPI_SETS) {
                 const int tile = tile0 + t;
                 const bool live = t < nt && tile < p.n_tiles;
@@ -441,9 +512,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
                 if (row_ok)
                     yrow = split ? p.ws + ((size_t)part * p.n_rows + j) * p.cout
                                  : p.y + (size_t)(p.out_rows ? p.out_rows[j] : j) * p.ldy;
-                mbar_wait(smem_u32(&acc_full[t]), siter & 1, 5);
+                mbar_wait(smem_u32(&acc_full[aset * MAX_T + t]), ause & 1, 5);
                 tc_fence_after();
-                const uint32_t acc_addr = tmem_base + (uint32_t)(t * p.acc_cols) + ((uint32_t)(quarter * 32) << 16);
+                const uint32_t acc_addr = tmem_base + (uint32_t)((aset * T + t) * p.acc_cols) + ((uint32_t)(quarter * 32) << 16);
                 for (int col = 0; live && col < p.cout; col += 16) {
                     float acc[16];
                     if (has_acc) {
@@ -461,8 +532,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
 #pragma unroll
                         for (int e = 0; e < 16; ++e) acc[e] = 0.f;
                     }
-                    if (!row_ok) continue;
                     if (split) {  // plain stores of the partial tile (cout % 16 == 0, workspace 16-byte aligned)
+                        if (!row_ok) continue;
 #pragma unroll
                         for (int e = 0; e < 16; e += 4)
                             *reinterpret_cast<float4 *>(yrow + col + e) = make_float4(acc[e], acc[e + 1], acc[e + 2], acc[e + 3]);
@@ -471,25 +542,42 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
                     if (p.bias)
 #pragma unroll
                         for (int e = 0; e < 16; ++e) acc[e] += __ldg(p.bias + col + e);
-                    if (vec) {
+                    if (row_ok) {
+                        if (vec) {
 #pragma unroll
-                        for (int e = 0; e < 16; e += 4) {
-                            float4 o = make_float4(acc[e], acc[e + 1], acc[e + 2], acc[e + 3]);
-                            float4 *dst = reinterpret_cast<float4 *>(yrow + col + e);
-                            if (p.accumulate) {
-                                float4 old = *dst;
-                                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                            for (int e = 0; e < 16; e += 4) {
+                                float4 o = make_float4(acc[e], acc[e + 1], acc[e + 2], acc[e + 3]);
+                                float4 *dst = reinterpret_cast<float4 *>(yrow + col + e);
+                                if (p.accumulate) {
+                                    float4 old = *dst;
+                                    o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                                }
+                                *dst = o;
                             }
-                            *dst = o;
-                        }
-                    } else {
+                        } else {
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) yrow[col + e] = p.accumulate ? yrow[col + e] + acc[e] : acc[e];
+                            for (int e = 0; e < 16; ++e) yrow[col + e] = p.accumulate ? yrow[col + e] + acc[e] : acc[e];
+                        }
+                    }
+                    if (bn_on) {  // the whole warp: column sums of the 32 rows, one shared-memory add per column
+                        float sq[16];
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            acc[e] = row_ok ? acc[e] : 0.f;
+                            sq[e] = acc[e] * acc[e];
+                        }
+                        warp_colsum16(acc, lane);
+                        warp_colsum16(sq, lane);
+                        if (!(lane & 1)) {
+                            const int cc = col + warp_colsum16_col(lane);
+                            atomicAdd(&bn_sum[cc], acc[0]);
+                            atomicAdd(&bn_sum[p.cout + cc], sq[0]);
+                        }
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&acc_empty[t]));
+                if (lane == 0) mbar_arrive(smem_u32(&acc_empty[aset * MAX_T + t]));
             }
         }
     }
@@ -497,6 +585,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
     tc_fence_before();
     __syncthreads();
     if (warp == MMA_WARP) tmem_dealloc(tmem_base, tmem_cols);
+    if (bn_on) bn_publish_and_finalize(p.bn, bn_sum, p.cout, p.n_rows, tid, THREADS, gridDim.x, &bn_last);
 }
 
 // Cost-weighted partition of the output tiles over G CTAs: tile i costs (active offsets of its mask) + 2 (index / epilogue
@@ -554,10 +643,21 @@ __global__ void __launch_bounds__(1024) k_partition(const uint32_t *__restrict__
 // Split mode, second half: y[row] (=|+=) bias + sum_q ws[q][row], parts added in index order (bit-reproducible; the vector
 // reds this replaces cost ~25 us per 128-row tile on the B200: ~76 G fp32 atomics/s chip-wide).
 __global__ void __launch_bounds__(256) k_reduce_parts(const float *__restrict__ ws, int ksplit, int n_rows, int cout,
-                                                      const float *__restrict__ bias, float *__restrict__ y, int ldy, int accumulate) {
+                                                      const float *__restrict__ bias, float *__restrict__ y, int ldy, int accumulate,
+                                                      BnFuse bn) {
+    __shared__ float bn_sum[2 * 256];
+    __shared__ bool bn_last;
+    const bool bn_on = bn.ws != nullptr;
+    if (bn_on) {
+        for (int k = threadIdx.x; k < 2 * cout; k += blockDim.x) bn_sum[k] = 0.f;
+        __syncthreads();
+    }
     const int g = cout / 4;
     const long long total = (long long)n_rows * g;
     const size_t plane = (size_t)n_rows * cout;
+    // the launcher makes the grid stride a multiple of g, so a thread stays on ONE column group: its sums live in registers
+    float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
+    int my_c = -1;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         const int r = (int)(e / g), c = (int)(e - (long long)r * g) * 4;
         float4 acc = *reinterpret_cast<const float4 *>(ws + (size_t)r * cout + c);
@@ -573,6 +673,22 @@ __global__ void __launch_bounds__(256) k_reduce_parts(const float *__restrict__ 
             acc.x += dst[0]; acc.y += dst[1]; acc.z += dst[2]; acc.w += dst[3];
         }
         dst[0] = acc.x; dst[1] = acc.y; dst[2] = acc.z; dst[3] = acc.w;
+        if (bn_on) {
+            my_c = c;
+            s4[0] += acc.x; s4[1] += acc.y; s4[2] += acc.z; s4[3] += acc.w;
+            q4[0] += acc.x * acc.x; q4[1] += acc.y * acc.y; q4[2] += acc.z * acc.z; q4[3] += acc.w * acc.w;
+        }
+    }
+    if (bn_on && my_c >= 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            atomicAdd(&bn_sum[my_c + i], s4[i]);
+            atomicAdd(&bn_sum[cout + my_c + i], q4[i]);
+        }
+    }
+    if (bn_on) {
+        __syncthreads();
+        bn_publish_and_finalize(bn, bn_sum, cout, n_rows, threadIdx.x, blockDim.x, gridDim.x, &bn_last);
     }
 }
 
@@ -584,7 +700,7 @@ static cudaError_t launch(int lag, int grid, size_t smem, cudaStream_t st, const
     cudaGetDevice(&dev);
     auto go = [&](auto kernel, int slot) -> cudaError_t {
         if (dev >= 0 && dev < 64 && !attr_done[slot][dev]) {
-            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);  // + 9 KB static (index ring, barriers) <= 227 KB
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 214 * 1024);  // + 11 KB static (index ring, barriers, BatchNorm sums) <= 227 KB
             if (e != cudaSuccess) return e;
             attr_done[slot][dev] = true;
         }
@@ -611,9 +727,10 @@ using namespace us3d;
 static long long *g_prof = nullptr;
 // launcher defaults (set from the measurements in profiles/r2_conv_tuning.md)
 static bool g_default_fuse = true;
+static int g_default_dbl = 0;
 static int g_default_lag = 0;  // 0: completion by cp.async.mbarrier.arrive.noinc (measured best on every level, profiles/r2_conv_tuning.md); -1: wait_group look-ahead 1 (three-term) / 2 (single pass)
 
-static int g_tune_a_slots = 0, g_tune_lag = 0, g_tune_T = 0, g_tune_fuse = 0;
+static int g_tune_a_slots = 0, g_tune_lag = 0, g_tune_T = 0, g_tune_fuse = 0, g_tune_dbl = 0;
 
 extern "C" {
 
@@ -628,6 +745,8 @@ void us3d_debug_set_tuning4(int a_slots, int lag, int T, int fuse) {
     g_tune_fuse = fuse;
 }
 void us3d_debug_set_tuning(int a_slots, int lag, int T) { us3d_debug_set_tuning4(a_slots, lag, T, 0); }
+/* accumulator sets: 0 = launcher's choice, 1 = one, 2 = two (where TMEM has room) */
+void us3d_debug_set_tuning_acc(int sets) { g_tune_dbl = sets; }
 
 int us3d_spconv_partition(const uint32_t *tile_mask, int n_tiles, int kvol, int32_t *partition, void *stream_) {
     US3D_CHECK_ARG(tile_mask != nullptr && partition != nullptr && n_tiles >= 0 && kvol >= 1 && kvol <= US3D_MAX_KVOL, "spconv_partition: bad arguments");
@@ -642,6 +761,14 @@ int us3d_spconv_gather_mt(const void *x_hi, const void *x_lo, int n_in, const in
                           const void *wpack, int cin, int cout, int passes, const float *bias, const int32_t *out_rows,
                           float *y, int ldy, int accumulate, const uint32_t *tile_mask, const int32_t *partition, void *workspace,
                           long long workspace_bytes, void *stream_) {
+    return us3d_spconv_gather_mt_bn(x_hi, x_lo, n_in, nbr, n_rows, kvol, wpack, cin, cout, passes, bias, out_rows, y, ldy, accumulate,
+                                    tile_mask, partition, workspace, workspace_bytes, nullptr, stream_);
+}
+
+int us3d_spconv_gather_mt_bn(const void *x_hi, const void *x_lo, int n_in, const int32_t *nbr, int n_rows, int kvol,
+                             const void *wpack, int cin, int cout, int passes, const float *bias, const int32_t *out_rows,
+                             float *y, int ldy, int accumulate, const uint32_t *tile_mask, const int32_t *partition, void *workspace,
+                             long long workspace_bytes, const us3d_bn_fuse_t *bn, void *stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     US3D_CHECK_ARG(kvol >= 1 && kvol <= US3D_MAX_KVOL, "spconv_gather_mt: kvol %d out of range", kvol);
     US3D_CHECK_ARG(passes == 1 || passes == 3, "spconv_gather_mt: passes must be 1 or 3");
@@ -650,23 +777,19 @@ int us3d_spconv_gather_mt(const void *x_hi, const void *x_lo, int n_in, const in
     US3D_CHECK_ARG((reinterpret_cast<uintptr_t>(x_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(x_lo) & 15) == 0,
                    "spconv_gather_mt: planes must be 16-byte aligned");
     US3D_CHECK_ARG(ldy >= cout && n_in > 0, "spconv_gather_mt: bad sizes");
+    US3D_CHECK_ARG(bn == nullptr || (bn->ws != nullptr && bn->mean != nullptr && bn->invstd != nullptr && !accumulate && n_rows > 0),
+                   "spconv_gather_mt_bn: statistics need ws / mean / invstd, a non-empty map and accumulate == 0");
     if (n_rows == 0) return 0;
     mt::Params p;
+    p.bn = mt::BnFuse{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f, 0.f};
+    if (bn != nullptr)
+        p.bn = mt::BnFuse{bn->ws, bn->mean, bn->invstd, bn->running_mean, bn->running_var, bn->num_batches_tracked, bn->eps, bn->momentum};
     p.x_hi = (const __nv_bfloat16 *)x_hi; p.x_lo = (const __nv_bfloat16 *)x_lo;
     p.nbr = nbr; p.n_rows = n_rows; p.kvol = kvol; p.n_tiles = ceil_div(n_rows, mt::M);
     p.wpack = (const uint8_t *)wpack; p.cin = cin; p.cout = cout; p.nchunks = ceil_div(cin, mt::KC);
     p.bias = bias; p.out_rows = out_rows; p.y = y; p.ldy = ldy; p.accumulate = accumulate; p.tile_mask = tile_mask;
     const int npl = passes == 3 ? 2 : 1;
-    // fused [W_hi | W_lo] operand: one N = 2 Cout MMA for the two products that share X_hi (three-term mode, N <= 256)
-    bool fuse = passes == 3 && 2 * cout <= 256 && g_default_fuse;
-    if (g_tune_fuse == 1) fuse = false;
-    if (g_tune_fuse == 2) fuse = passes == 3 && 2 * cout <= 256;
-    int cols = 32;
-    while (cols < (fuse ? 2 * cout : cout)) cols <<= 1;
-    p.acc_cols = cols;
     const int sms = num_sms();
-    int T = 512 / cols;
-    if (T > mt::MAX_T) T = mt::MAX_T;
     p.prof = g_prof;
     // Work decomposition.  The kernel's cost is ~ the (tile, offset) products on the busiest CTA plus ~2 of them per tile for the
     // epilogue.  With the offsets of a tile dealt to `ks` CTAs (each writes a partial tile to the workspace, k_reduce_parts sums
@@ -685,6 +808,24 @@ int us3d_spconv_gather_mt(const void *x_hi, const void *x_lo, int n_in, const in
             }
         }
     }
+    // fused [W_hi | W_lo] operand: one N = 2 Cout MMA for the two products that share X_hi (three-term mode, N <= 256).
+    // Two accumulator sets (the epilogue of a tile group overlaps the MMAs of the next) where the epilogue also carries the
+    // BatchNorm statistics of a large map: measured on B200 (scripts/tune_acc.py, 200k voxels 96 -> 96 with statistics) fused /
+    // one set 291 us, unfused / two sets 270 us, fused / two sets with single-tile groups 365 us; without statistics 262 / 262 us.
+    bool fuse = passes == 3 && 2 * cout <= 256 && g_default_fuse;
+    int dbl = (bn != nullptr && ksplit == 1) ? 1 : g_default_dbl;
+    if (g_tune_dbl == 1) dbl = 0;
+    if (g_tune_dbl == 2) dbl = 1;
+    if (dbl && 2 * cout > 128 && g_tune_fuse != 2) fuse = false;  // 2 x 256 columns would leave one tile per group
+    if (g_tune_fuse == 1) fuse = false;
+    if (g_tune_fuse == 2) fuse = passes == 3 && 2 * cout <= 256;
+    int cols = 32;
+    while (cols < (fuse ? 2 * cout : cout)) cols <<= 1;
+    p.acc_cols = cols;
+    if (2 * cols > 512) dbl = 0;
+    p.dbl = dbl;
+    int T = 512 / (cols * (1 + dbl));
+    if (T > mt::MAX_T) T = mt::MAX_T;
     p.ws = (float *)workspace;
     if (ksplit > 1) T = 1;
     // range mode: every CTA owns a contiguous range of tiles; no more accumulators than its share of the tiles
@@ -740,8 +881,13 @@ int us3d_spconv_gather_mt(const void *x_hi, const void *x_lo, int n_in, const in
         US3D_LAUNCH_CHECK();
         if (ksplit > 1) {
             long long blocks = ((long long)n_rows * (cout / 4) + 255) / 256;
-            if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
-            mt::k_reduce_parts<<<(int)blocks, 256, 0, st>>>(p.ws, ksplit, n_rows, cout, bias, y, ldy, accumulate);
+            const long long cap = p.bn.ws != nullptr ? (long long)sms : (long long)sms * 8;  // with statistics: every block ends in 2 cout fp64 atomics + a ticket
+            if (blocks > cap) blocks = cap;
+            // grid stride (256 blocks) a multiple of cout / 4 = 4 (cout / 16): blocks a multiple of the odd part of cout / 16
+            int odd = cout / 16;
+            while (odd % 2 == 0) odd /= 2;
+            blocks = (blocks + odd - 1) / odd * odd;
+            mt::k_reduce_parts<<<(int)blocks, 256, 0, st>>>(p.ws, ksplit, n_rows, cout, bias, y, ldy, accumulate, p.bn);
             US3D_LAUNCH_CHECK();
         }
     }

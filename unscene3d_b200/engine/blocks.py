@@ -36,12 +36,23 @@ def _w3(kernel, table):
     return kernel.detach().contiguous().view(table.kvol, kernel.shape[-2], kernel.shape[-1])
 
 
-def _conv_forward(x, kernel, table, flip):
+def _conv_forward(x, kernel, table, flip, bn=None):
     w3 = _w3(kernel, table)
     cin, cout = w3.shape[1], w3.shape[2]
     mode = Fn.get_precision()
     wf = Fn.packed_weights(kernel, w3, flip, mode, True)[0] if (mode != 0 and cin > 4) else None
-    return Fn.spconv_gather(x, table, w3, cin, cout, False, False, None, wpack=wf)
+    return Fn.spconv_gather(x, table, w3, cin, cout, False, False, None, wpack=wf, bn=bn)
+
+
+def _conv_norm_stats(x, kernel, table, flip, norm):
+    """y = conv(x) and the statistics norm will normalise y with: (y, mean, invstd, batch statistics?).  In training mode the
+    convolution's epilogue produces them (no separate pass over y)."""
+    req = norm.stats_request()
+    y = _conv_forward(x, kernel, table, flip, req)
+    if req is not None:
+        return y, req.mean, req.invstd, True
+    m, s, t = norm.statistics(y)
+    return y, m, s, t
 
 
 def _planes(t):
@@ -59,16 +70,13 @@ class FusedBasicBlockFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, k1, g1, b1, k2, g2, b2, kd, gd, bd, plan: _Plan):
         x = Fn._rows(x)
-        y1 = _conv_forward(x, k1, plan.fwd1, plan.flip1)
-        m1, s1, t1 = plan.norm1.statistics(y1)
+        y1, m1, s1, t1 = _conv_norm_stats(x, k1, plan.fwd1, plan.flip1, plan.norm1)
         a1, g1c = Fn.bn_apply_raw(y1, g1, b1, None, m1, s1, True)
-        y2 = _conv_forward(a1, k2, plan.fwd2, plan.flip2)
-        m2, s2, t2 = plan.norm2.statistics(y2)
+        y2, m2, s2, t2 = _conv_norm_stats(a1, k2, plan.fwd2, plan.flip2, plan.norm2)
         yd = md = sd = gdc = None
         td = False
         if kd is not None:
-            yd = _conv_forward(x, kd, plan.fwdd, plan.flipd)
-            md, sd, td = plan.normd.statistics(yd)
+            yd, md, sd, td = _conv_norm_stats(x, kd, plan.fwdd, plan.flipd, plan.normd)
             res, gdc = Fn.bn_apply_raw(yd, gd, bd, None, md, sd, False)
         else:
             res = x
@@ -156,8 +164,7 @@ class FusedConvNormReLUFunction(torch.autograd.Function):
     def forward(ctx, x, k, g, b, plan):
         x = Fn._rows(x)
         fwd, bwd_getter, flip, norm = plan
-        y = _conv_forward(x, k, fwd, flip)
-        m, s, t = norm.statistics(y)
+        y, m, s, t = _conv_norm_stats(x, k, fwd, flip, norm)
         out, gc = Fn.bn_apply_raw(y, g, b, None, m, s, True)
         ctx.save_for_backward(x, y, out, m, s, gc, k)
         ctx.plan, ctx.training, ctx.planes = plan, bool(t), _planes(x)

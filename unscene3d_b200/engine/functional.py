@@ -6,11 +6,12 @@ with its row stride as leading dimension (so column slices of a concatenation ne
 """
 from __future__ import annotations
 
+import ctypes
 import os
 
 import torch
 
-from .._lib import check, lib
+from .._lib import BnFuse, check, lib
 from .coords import NeighbourTable, _stream
 
 
@@ -265,9 +266,38 @@ def _tc_ok(cin, cout):  # == us3d_spconv_tc_supported, without the FFI round tri
     return cin >= 16 and cin % 16 == 0 and cout >= 16 and cout % 16 == 0 and cout <= 256
 
 
-def spconv_gather(x, table: NeighbourTable, w3, cin, cout, transpose_w, flip_k, bias=None, out=None, accumulate=False, wpack=None):
+class BnRequest:
+    """BatchNorm statistics asked of the convolution that produces the normalised tensor: the tensor-core kernel folds the column
+    sums into its epilogue (us3d_spconv_gather_mt_bn); any other path computes them with the statistics kernel afterwards.
+    After spconv_gather: .mean / .invstd are fp32 [c]; the running statistics are updated like nn.BatchNorm1d's."""
+
+    __slots__ = ("running_mean", "running_var", "momentum", "eps", "num_batches_tracked", "mean", "invstd")
+
+    def __init__(self, running_mean, running_var, momentum, eps, num_batches_tracked):
+        self.running_mean, self.running_var, self.momentum, self.eps = running_mean, running_var, momentum, eps
+        self.num_batches_tracked = num_batches_tracked
+        self.mean = self.invstd = None
+
+
+_bn_fuse = {"on": os.environ.get("US3D_FUSED_BN_STATS", "1") == "1"}
+
+
+def set_fused_bn_stats(on: bool):
+    """BatchNorm statistics from the convolution's epilogue (default) or from the separate statistics kernel (same sums)."""
+    _bn_fuse["on"] = bool(on)
+
+
+def spconv_gather(x, table: NeighbourTable, w3, cin, cout, transpose_w, flip_k, bias=None, out=None, accumulate=False, wpack=None,
+                  bn: "BnRequest" = None):
     """y[j] = sum_k x[nbr[k, j]] . W'[k]  (W' = W[k], or W[K-1-k]^T / W[k]^T for the input gradient).  `wpack` is the
-    cached weight image of packed_weights(); without it the image is built here."""
+    cached weight image of packed_weights(); without it the image is built here.  `bn`: see BnRequest."""
+    y = _spconv_gather(x, table, w3, cin, cout, transpose_w, flip_k, bias, out, accumulate, wpack, bn)
+    if bn is not None and bn.mean is None:
+        bn.mean, bn.invstd = bn_batch_stats(y, bn.running_mean, bn.running_var, bn.momentum, bn.eps, bn.num_batches_tracked)
+    return y
+
+
+def _spconv_gather(x, table, w3, cin, cout, transpose_w, flip_k, bias, out, accumulate, wpack, bn):
     x = _rows(x)
     y = out if out is not None else torch.empty((table.n_rows, cout), dtype=torch.float32, device=x.device)
     st = _stream()
@@ -287,10 +317,18 @@ def spconv_gather(x, table: NeighbourTable, w3, cin, cout, transpose_w, flip_k, 
         nbr, mask, order = table.ordered() or (table.nbr, table.mask, None)
         part = table.partition() if order is not None else None
         ws, ws_bytes = _conv_workspace(x.device, table.n_rows, table.kvol, cout) if order is None else (None, 0)
+        desc = None
+        if bn is not None and _bn_fuse["on"] and not accumulate and table.n_rows > 0:
+            stats = torch.empty((2, cout), dtype=torch.float32, device=x.device)
+            desc = BnFuse(_bn_workspace(x.device, cout).data_ptr(), stats.data_ptr(), stats.data_ptr() + 4 * cout, _ptr(bn.running_mean),
+                          _ptr(bn.running_var), _ptr(bn.num_batches_tracked), float(bn.eps),
+                          float(bn.momentum if bn.momentum is not None else 0.0))
+            bn.mean, bn.invstd = stats[0], stats[1]
         _timed(kind, x.shape[0], table.n_rows, table.kvol, cin, cout, lambda: check(
-            lib.us3d_spconv_gather_mt(hi.data_ptr(), _ptr(lo), x.shape[0], nbr.data_ptr(), table.n_rows, table.kvol, wpack.data_ptr(),
-                                      cin, cout, mode, _ptr(bias), _ptr(order), y.data_ptr(), _ld(y), int(accumulate), _ptr(mask),
-                                      _ptr(part), _ptr(ws), ws_bytes, st)), table, "mt")
+            lib.us3d_spconv_gather_mt_bn(hi.data_ptr(), _ptr(lo), x.shape[0], nbr.data_ptr(), table.n_rows, table.kvol, wpack.data_ptr(),
+                                         cin, cout, mode, _ptr(bias), _ptr(order), y.data_ptr(), _ld(y), int(accumulate), _ptr(mask),
+                                         _ptr(part), _ptr(ws), ws_bytes, ctypes.byref(desc) if desc is not None else None, st)),
+               table, "mt")
         return y
     _timed(kind, x.shape[0], table.n_rows, table.kvol, cin, cout, lambda: check(
         lib.us3d_spconv_gather(x.data_ptr(), _ld(x), table.nbr.data_ptr(), table.n_rows, table.kvol, w3.data_ptr(), cin, cout,

@@ -424,6 +424,19 @@ class MinkowskiBatchNorm(nn.Module):
             invstd = torch.rsqrt(bn.running_var.detach().float() + bn.eps)
         return mean, invstd, use_batch
 
+    def stats_request(self):
+        """The batch-statistics request a producing convolution can fold into its epilogue (Fn.BnRequest), or None when the
+        statistics are not this batch's (evaluation mode) or the momentum is the cumulative average (host-side counter)."""
+        bn = self.bn
+        if not (bn.training or not bn.track_running_stats):
+            return None
+        tracking = bn.training and bn.track_running_stats
+        if tracking and bn.momentum is None:
+            return None
+        nbt = bn.num_batches_tracked if (tracking and bn.num_batches_tracked is not None) else None
+        rm = bn.running_mean if tracking else None
+        return Fn.BnRequest(rm, bn.running_var if rm is not None else None, bn.momentum, bn.eps, nbt)
+
     def forward(self, x: SparseTensor, residual: SparseTensor = None, relu: bool = False) -> SparseTensor:
         bn = self.bn
         f = x.F
