@@ -62,7 +62,7 @@ torch.cuda.synchronize()
 print(f"host time/step with timed lib {(t1 - t) / 3 * 1e3:.2f} ms; C-ABI calls:")
 for name, (n, tot) in sorted(tl.acc.items(), key=lambda kv: -kv[1][1]):
     print(f"  {name:34s} {n / 3:7.1f} calls/step  {tot / 3 * 1e3:8.3f} ms/step  {tot / max(n, 1) * 1e6:8.1f} us/call")
-sm = tl.samples.get("us3d_spconv_gather_mt", [])
+sm = tl.samples.get("us3d_spconv_gather_mt_bn", [])
 main = threading.get_ident()
 for label, sel in (("main thread", [x for x in sm if x[1] == main]), ("other threads", [x for x in sm if x[1] != main])):
     d = sorted(x[0] * 1e6 for x in sel)
