@@ -42,10 +42,12 @@ UNIT = "voxels/s"
 N_VOXELS = 200_000
 # dram__bytes_read.sum + dram__bytes_write.sum of the largest launch of each kernel, from the ncu --set full capture summarised
 # in profiles/ (see there for the command), next to the algorithmic bytes of that launch
-NCU_TRAFFIC = {"mt": {"launch": "200k voxels, k3, 128 -> 96 (pattern order)", "dram_bytes": 502625792, "alg_bytes": 180500000,
-                      "source": "profiles/r2_ncu_full_summary.md"},
-               "wgrad": {"launch": "200k voxels, k3, 128 -> 96", "dram_bytes": 242054656, "alg_bytes": 180500000,
-                         "source": "profiles/r2_ncu_full_summary.md"}}
+NCU_TRAFFIC = {"mt": {"launch": "200k voxels, k3, 128 -> 96 (pattern order)", "dram_bytes": 497897984, "alg_bytes": 180500000,
+                      "l2_to_sm_bytes": 2117809000, "duration_us": 280.3,  # the launch is bound by the L2 -> SM path: 7.6 TB/s
+                      "source": "profiles/r2_final_ncu_full_summary.md"},
+               "wgrad": {"launch": "200k voxels, k3, 128 -> 96", "dram_bytes": 225198336, "alg_bytes": 180500000,
+                         "l2_to_sm_bytes": 1905437000, "duration_us": 362.0,
+                         "source": "profiles/r2_final_ncu_full_summary.md"}}
 DTYPE = "bf16x3"  # tcgen05 bf16 products, three-term split hi*hi + lo*hi + hi*lo (fp32-faithful), fp32 accumulation in TMEM
 PRIME_STEPS = 30  # untimed steps BEFORE the --warmup steps: allocator pools of the two streams, NVML, clock / power ramp
 
@@ -486,7 +488,7 @@ def run_ours(args):
 
         dom = [r for r in recs if r[0] in ("fwd", "dgrad") and r[7] == "mt"]
         wg = [r for r in recs if r[0] == "wgrad" and r[7] == "wgrad-tc"]
-        # `traffic`: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (ncu --set full, profiles/r2_ncu_full_summary.md)
+        # `traffic`: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (ncu --set full, profiles/r2_final_ncu_full_summary.md)
         # next to that launch's algorithmic bytes
         roofline = view(dom, "us3d::mt::k_spconv_mt (tcgen05 sparse-conv forward + input-gradient launches)", NCU_TRAFFIC["mt"])
         roofline_wgrad = view(wg, "us3d::wg::k_wgrad (tcgen05 weight-gradient launches)", NCU_TRAFFIC["wgrad"])

@@ -8,6 +8,10 @@
 extern "C" {
 #endif
 
+/* Programmatic dependent launch of the convolution / BatchNorm kernels (a kernel's prologue overlaps its predecessor's tail):
+ * on by default, US3D_PDL=0 in the environment or on = 0 here launches the same kernels without the attribute. */
+void us3d_debug_set_pdl(int on);
+
 /* Per-launch timing of the convolution kernels: between start and stop every convolution entry point brackets its launch
  * with CUDA events recorded on the launch stream.  stop() synchronises the events and fills, per launch in launch order,
  * meta[7] = (kind 0 fwd/dgrad | 1 wgrad as tagged, n_in, n_rows, kvol, cin, cout, tag) and ms; returns the launch count. */

@@ -71,6 +71,30 @@ struct ProfScope {
     }
 };
 
+// ---- programmatic dependent launch ---------------------------------------------------------------
+// The step is ~560 short launches of this library on one stream.  A kernel launched through launch_pdl may be scheduled while
+// its predecessor is still draining: it runs its prologue (barrier init, TMEM allocation, shared-memory clears) and then blocks in
+// pdl_wait() until the predecessor has completed and its writes are visible; pdl_trigger() in the predecessor is what lets the
+// scheduler start it early.  Every kernel launched this way executes pdl_wait() before its first global access.  US3D_PDL=0
+// (or us3d_debug_set_pdl(0)) launches the same kernels without the attribute; the two instructions are then no-ops.
+extern bool g_pdl;
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // ---- voxel keys -------------------------------------------------------------------------------

@@ -16,6 +16,7 @@
 #include <mutex>
 #include <vector>
 
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace us3d {
@@ -32,6 +33,10 @@ void set_error(const char *fmt, ...) {
 
 // ---- per-launch profiling -----------------------------------------------------------------------
 bool g_profile = false;
+bool g_pdl = [] {
+    const char *e = getenv("US3D_PDL");
+    return !(e && e[0] == '0');
+}();
 namespace {
 struct ProfRec {
     cudaEvent_t s, e;
@@ -311,6 +316,9 @@ long long us3d_launch_count(void) { return g_launches.load(); }
 /* Profiling hooks (debug surface, used by bench.py): start collecting, tag the next gather launches (0 forward,
  * 2 input gradient), stop = synchronise and return up to `cap` records as meta[7 * i .. ] = (kind, n_in, n_rows, kvol,
  * cin, cout, 0) and ms[i]; kind 1 = weight gradient. */
+/* programmatic dependent launch of the conv / BatchNorm kernels on (default, or US3D_PDL != 0) / off */
+void us3d_debug_set_pdl(int on) { g_pdl = on != 0; }
+
 void us3d_debug_profile_start(void) {
     std::lock_guard<std::mutex> lk(g_prof_mu);
     for (auto &r : g_prof_recs) {

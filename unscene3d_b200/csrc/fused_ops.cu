@@ -65,6 +65,8 @@ struct StatsArgs {
 __global__ void __launch_bounds__(256) k_bn_stats_fused(StatsArgs a) {
     __shared__ double s0[8][33], s1[8][33];
     __shared__ bool last;
+    pdl_wait();
+    pdl_trigger();
     const int ch = blockIdx.y * 32 + threadIdx.x;
     const int r_begin = blockIdx.x * a.rows, r_end = min(a.n, r_begin + a.rows);
     float a0 = 0.f, a1 = 0.f;
@@ -124,6 +126,8 @@ k_bn_apply_planes(const float *__restrict__ x, int ldx, int n, int c, const floa
                   float *__restrict__ y, int ldy, uint4 *__restrict__ hi, uint4 *__restrict__ lo) {
     const int g = c / 8;
     const long long total = (long long)n * g;
+    pdl_wait();
+    pdl_trigger();
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         const int r = (int)(e / g), ch = (int)(e % g) * 8;
         const float4 *src = reinterpret_cast<const float4 *>(x + (size_t)r * ldx + ch);
@@ -157,6 +161,8 @@ k_bn_bwd_reduce(const float *__restrict__ dy, int lddy, const float *__restrict_
     const int ch = blockIdx.y * 32 + threadIdx.x;
     const int r_begin = blockIdx.x * rows, r_end = min(n, r_begin + rows);
     float a0 = 0.f, a1 = 0.f;
+    pdl_wait();
+    pdl_trigger();
     if (ch < c) {
         const float m = mean[ch], is = invstd[ch];
         for (int r = r_begin + threadIdx.y; r < r_end; r += 8) {
@@ -194,6 +200,8 @@ k_bn_bwd_apply(const float *__restrict__ dy, int lddy, const float *__restrict__
     extern __shared__ float coef[];  // [3][c]
     __shared__ bool last;
     float *ca = coef, *cb = coef + c, *cd = coef + 2 * c;
+    pdl_wait();
+    pdl_trigger();
     {
         const double inv_n = 1.0 / (double)n;
         for (int k = threadIdx.x; k < c; k += blockDim.x) {
@@ -482,7 +490,7 @@ int us3d_bn_stats_fused(const float *x, int ldx, int n, int c, float eps, float 
     const int rows = fused::reduce_rows(n);
     fused::StatsArgs a{x, ldx, n, c, eps, momentum, mean, invstd, running_mean, running_var, num_batches_tracked, ws, rows};
     dim3 grid(ceil_div(n, rows), ceil_div(c, 32)), block(32, 8);
-    fused::k_bn_stats_fused<<<grid, block, 0, st>>>(a);
+    US3D_CUDA(launch_pdl(fused::k_bn_stats_fused, grid, block, 0, st, a));
     US3D_LAUNCH_CHECK();
     return 0;
 }
@@ -497,8 +505,8 @@ int us3d_bn_apply_planes(const float *x, int ldx, int n, int c, const float *mea
                      (!residual || (ldr % 4 == 0 && fused::al16(residual)));
     US3D_CHECK_ARG(vec || hi == nullptr, "bn_apply_planes: planes need c %% 8 == 0 and 16-byte aligned rows");
     if (!vec) return us3d_bn_apply(x, ldx, n, c, mean, invstd, gamma, beta, residual, ldr, relu, y, ldy, stream_);
-    fused::k_bn_apply_planes<<<fused::flat_grid((long long)n * c / 8), 256, 0, st>>>(x, ldx, n, c, mean, invstd, gamma, beta, residual, ldr,
-                                                                                  relu, y, ldy, (uint4 *)hi, (uint4 *)lo);
+    US3D_CUDA(launch_pdl(fused::k_bn_apply_planes, dim3(fused::flat_grid((long long)n * c / 8)), dim3(256), 0, st, x, ldx, n, c, mean, invstd, gamma,
+                         beta, residual, ldr, relu, y, ldy, (uint4 *)hi, (uint4 *)lo));
     US3D_LAUNCH_CHECK();
     return 0;
 }
@@ -511,15 +519,15 @@ int us3d_bn_backward_planes(const float *dy, int lddy, const float *x, int ldx, 
     US3D_CHECK_ARG(n > 0 && c > 0 && c <= 4096, "bn_backward_planes: bad shape");
     const int rows = fused::reduce_rows(n);
     dim3 grid(ceil_div(n, rows), ceil_div(c, 32)), block(32, 8);
-    fused::k_bn_bwd_reduce<<<grid, block, 0, st>>>(dy, lddy, x, ldx, y, ldy, n, c, mean, invstd, relu, ws, rows);
+    US3D_CUDA(launch_pdl(fused::k_bn_bwd_reduce, grid, block, 0, st, dy, lddy, x, ldx, y, ldy, n, c, mean, invstd, relu, ws, rows));
     US3D_LAUNCH_CHECK();
     const bool vec = c % 8 == 0 && lddy % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && lddx % 4 == 0 && fused::al16(dy) && fused::al16(x) &&
                      fused::al16(y) && fused::al16(dx) && (!dres || (lddres % 4 == 0 && fused::al16(dres)));
     US3D_CHECK_ARG(vec || dx_hi == nullptr, "bn_backward_planes: planes need c %% 8 == 0 and 16-byte aligned rows");
     if (vec)
-        fused::k_bn_bwd_apply<8><<<fused::flat_grid((long long)n * c / 8), 256, 3 * (size_t)c * sizeof(float), st>>>(
-            dy, lddy, x, ldx, y, ldy, n, c, mean, invstd, gamma, relu, ws, dx, lddx, dres, lddres, dgamma, dbeta, batch_terms,
-            (uint4 *)dx_hi, (uint4 *)dx_lo);
+        US3D_CUDA(launch_pdl(fused::k_bn_bwd_apply<8>, dim3(fused::flat_grid((long long)n * c / 8)), dim3(256), 3 * (size_t)c * sizeof(float), st,
+                             dy, lddy, x, ldx, y, ldy, n, c, mean, invstd, gamma, relu, ws, dx, lddx, dres, lddres, dgamma, dbeta, batch_terms,
+                             (uint4 *)dx_hi, (uint4 *)dx_lo));
     else
         fused::k_bn_bwd_apply<1><<<fused::flat_grid((long long)n * c), 256, 3 * (size_t)c * sizeof(float), st>>>(
             dy, lddy, x, ldx, y, ldy, n, c, mean, invstd, gamma, relu, ws, dx, lddx, dres, lddres, dgamma, dbeta, batch_terms, nullptr,

@@ -185,6 +185,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_mt(Params p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
+    pdl_wait();     // everything above overlaps the previous kernel's tail; nothing below runs before its writes are visible
+    pdl_trigger();  // the next kernel of the stream may set itself up while this one works
 
     auto tile_kmask = [&](int tile, uint32_t pm) -> uint32_t {
         if (tile >= p.n_tiles) return 0u;
@@ -652,6 +654,8 @@ __global__ void __launch_bounds__(256) k_reduce_parts(const float *__restrict__ 
         for (int k = threadIdx.x; k < 2 * cout; k += blockDim.x) bn_sum[k] = 0.f;
         __syncthreads();
     }
+    pdl_wait();
+    pdl_trigger();
     const int g = cout / 4;
     const long long total = (long long)n_rows * g;
     const size_t plane = (size_t)n_rows * cout;
@@ -704,8 +708,7 @@ static cudaError_t launch(int lag, int grid, size_t smem, cudaStream_t st, const
             if (e != cudaSuccess) return e;
             attr_done[slot][dev] = true;
         }
-        kernel<<<grid, THREADS, smem, st>>>(p);
-        return cudaSuccess;
+        return launch_pdl(kernel, dim3(grid), dim3(THREADS), smem, st, p);
     };
     if (p.prof != nullptr) {  // the instantiation with the MMA thread's cycle counters (us3d_debug_set_prof)
         if (lag <= 0) return go(k_spconv_mt<PASSES, 0, FUSE, true>, 4);
@@ -887,7 +890,7 @@ int us3d_spconv_gather_mt_bn(const void *x_hi, const void *x_lo, int n_in, const
             int odd = cout / 16;
             while (odd % 2 == 0) odd /= 2;
             blocks = (blocks + odd - 1) / odd * odd;
-            mt::k_reduce_parts<<<(int)blocks, 256, 0, st>>>(p.ws, ksplit, n_rows, cout, bias, y, ldy, accumulate, p.bn);
+            US3D_CUDA(launch_pdl(mt::k_reduce_parts, dim3((int)blocks), dim3(256), 0, st, (const float *)p.ws, ksplit, n_rows, cout, bias, y, ldy, accumulate, p.bn));
             US3D_LAUNCH_CHECK();
         }
     }

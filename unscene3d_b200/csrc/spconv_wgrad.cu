@@ -98,6 +98,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad(Params p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
+    pdl_wait();     // (common.cuh) the prologue above overlaps the previous kernel's tail
+    pdl_trigger();
     uint32_t touched = 0;  // offsets (relative to k0) that received at least one MMA — same in every role
 
     if (warp < PROD_WARPS) {
@@ -414,11 +416,11 @@ int us3d_spconv_wgrad_planes(const void *x_hi, const void *x_lo, const void *dy_
         ProfScope prof(st, 1, n_rows, n_rows, kvol, cin, cout);
         p.prof = g_wgrad_prof;
         if (passes == 3 && p.prof != nullptr)
-            wg::k_wgrad<3, true><<<grid, wg::THREADS, smem, st>>>(p);
+            US3D_CUDA(launch_pdl(wg::k_wgrad<3, true>, dim3(grid), dim3(wg::THREADS), smem, st, p));
         else if (passes == 3)
-            wg::k_wgrad<3, false><<<grid, wg::THREADS, smem, st>>>(p);
+            US3D_CUDA(launch_pdl(wg::k_wgrad<3, false>, dim3(grid), dim3(wg::THREADS), smem, st, p));
         else
-            wg::k_wgrad<1, false><<<grid, wg::THREADS, smem, st>>>(p);
+            US3D_CUDA(launch_pdl(wg::k_wgrad<1, false>, dim3(grid), dim3(wg::THREADS), smem, st, p));
     }
     US3D_LAUNCH_CHECK();
     return 0;
