@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define US3D_ABI_VERSION 17
+#define US3D_ABI_VERSION 18
 #define US3D_MAX_KVOL 27
 
 int us3d_abi_version(void);
@@ -127,6 +127,26 @@ int us3d_spconv_gather_mt_bn(const void *x_hi, const void *x_lo, int n_in, const
                              const void *wpack, int cin, int cout, int passes, const float *bias, const int32_t *out_rows,
                              float *y, int ldy, int accumulate, const uint32_t *tile_mask, const int32_t *partition,
                              void *workspace, long long workspace_bytes, const us3d_bn_fuse_t *bn, void *stream);
+/* Launch lists (csrc/executor.cu): the launches of a residual block's forward or backward pass
+ * (/root/reference/models/modules/resnet_block.py:24-64: conv - norm - relu - conv - norm - (+ shortcut) - relu) issued by ONE call.
+ * Every op names an entry point of this header and carries its resolved arguments — p[]: pointers, v[]: integers, f[]: floats, in
+ * the order documented next to each kind in csrc/executor.cu (the entry point's own argument order).  us3d_run_ops calls them in
+ * list order on `stream` and returns the first non-zero return code; results are those of the call-by-call route. */
+enum { US3D_OP_CONV = 1,        /* us3d_spconv_gather_mt_bn   */
+       US3D_OP_BN_APPLY = 2,    /* us3d_bn_apply_planes       */
+       US3D_OP_BN_BACKWARD = 3, /* us3d_bn_backward_planes    */
+       US3D_OP_WGRAD = 4,       /* us3d_spconv_wgrad_planes   */
+       US3D_OP_ADD = 5 };       /* us3d_add                   */
+typedef struct us3d_op {
+    int kind;
+    const void *p[16];
+    long long v[10];
+    float f[2];
+} us3d_op_t;
+int us3d_run_ops(const us3d_op_t *ops, int n_ops, void *stream);
+/* the same list as flat arrays (one conversion for a ctypes caller): a = n_ops x [kind, p[16], v[10]] (int64), f = n_ops x [f0, f1] (double) */
+int us3d_run_ops_flat(const long long *a, const double *f, int n_ops, void *stream);
+
 /* workspace (may be NULL; 16-byte aligned, contents irrelevant): room for the partial tiles of the split mode,
  * [parts][n_rows][cout] fp32, summed in part order by a second launch (no atomics: results are bit-reproducible).
  * us3d_spconv_gather_mt_workspace_bytes = the most the launcher can use for a map (0: it would not split).             */

@@ -303,6 +303,49 @@ def test_batchnorm_statistics_from_the_convolution_epilogue(eng, n, cin, cout, o
         C.set_row_ordering(32768)
 
 
+def test_launch_lists_equal_the_call_by_call_route(eng):
+    """engine/blocks.py: a residual block's launches issued by one us3d_run_ops call are the launches of the call-by-call route
+    (same kernels, arguments, order): features, BatchNorm buffers and gradients agree to the run-to-run noise of the atomics in the
+    statistics / weight-gradient sums (1e-6 / 1e-5), in training and in evaluation mode, with and without a shortcut convolution."""
+    from unscene3d_b200 import _lib, models
+    from unscene3d_b200.engine import blocks as B
+    from unscene3d_b200.utils import BackboneConfig, seeded_state
+
+    c = random_scene(9000, 3, batch=2, extent=48)
+    coords = torch.from_numpy(c).cuda()
+    feats = torch.randn(c.shape[0], 3, generator=torch.Generator().manual_seed(1)).cuda()
+    res = {}
+    for on in (True, False, None):  # None: the call-by-call route a second time = the run-to-run noise floor of the atomics
+        B.set_launch_lists(bool(on))
+        try:
+            net = models.Res16UNet14(3, 20, BackboneConfig(), D=3, out_fpn=True)
+            net.load_state_dict(seeded_state(net, 0))
+            net = net.cuda().train()
+            _lib.reset_launch_count()
+            out, _ = net(eng.SparseTensor(feats, coords))
+            (out.F * torch.linspace(-1, 1, out.F.shape[1], device="cuda")).mean().backward()
+            grads = {k: p.grad.detach().clone() for k, p in net.named_parameters() if p.grad is not None}
+            bufs = {k: b.detach().clone() for k, b in net.named_buffers()}
+            net.eval()
+            with torch.no_grad():
+                ev, _ = net(eng.SparseTensor(feats, coords))
+            res[on] = (out.F.detach().clone(), grads, bufs, ev.F.clone(), _lib.launch_count())
+        finally:
+            B.set_launch_lists(True)
+    assert res[True][4] == res[False][4], "the two routes must launch the same number of kernels"
+    # the statistics' shared-memory / fp64 atomics and the weight gradient's reds make two runs of ONE route differ in the last
+    # bits (amplified to ~1e-5 by 30 layers); the two routes must differ by no more than two such runs do
+    floor_f = max(rel_err(res[None][0], res[False][0]), rel_err(res[None][3], res[False][3]), 1e-7)
+    assert floor_f < 2e-4
+    assert rel_err(res[True][0], res[False][0]) < 4 * floor_f and rel_err(res[True][3], res[False][3]) < 4 * floor_f
+    assert set(res[True][1]) == set(res[False][1])
+    for k, g in res[False][1].items():
+        floor_g = max(rel_err(res[None][1][k], g), 1e-6)
+        assert rel_err(res[True][1][k], g) < 8 * floor_g + 1e-5, k
+    for k, b in res[False][2].items():
+        assert rel_err(res[True][2][k].float(), b.float()) < 1e-5, k
+
+
 def test_transposed_convolution_on_pattern_ordered_tables(eng, ora):
     from unscene3d_b200.engine import coords as C
 

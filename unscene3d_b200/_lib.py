@@ -16,6 +16,14 @@ class BnFuse(ctypes.Structure):
                 ("eps", _f), ("momentum", _f)]
 
 
+class Op(ctypes.Structure):
+    """us3d_op_t (include/us3d.h): one launch of a launch list (us3d_run_ops)."""
+
+    _fields_ = [("kind", _i), ("p", _p * 16), ("v", _ll * 10), ("f", _f * 2)]
+
+
+OP_CONV, OP_BN_APPLY, OP_BN_BACKWARD, OP_WGRAD, OP_ADD = 1, 2, 3, 4, 5
+
 # name -> argtypes (all functions return int unless listed in _RESTYPE)
 PROTOTYPES = {
     "us3d_abi_version": [],
@@ -33,6 +41,8 @@ PROTOTYPES = {
     "us3d_split_bf16": [_p, _i, _i, _i, _p, _p, _p],
     "us3d_spconv_gather_mt": [_p, _p, _i, _p, _i, _i, _p, _i, _i, _i, _p, _p, _p, _i, _i, _p, _p, _p, _ll, _p],
     "us3d_spconv_gather_mt_bn": [_p, _p, _i, _p, _i, _i, _p, _i, _i, _i, _p, _p, _p, _i, _i, _p, _p, _p, _ll, _p, _p],
+    "us3d_run_ops": [_p, _i, _p],
+    "us3d_run_ops_flat": [_p, _p, _i, _p],
     "us3d_spconv_gather_mt_workspace_bytes": [_i, _i, _i],
     "us3d_spconv_partition_size": [],
     "us3d_spconv_partition": [_p, _i, _i, _p, _p],

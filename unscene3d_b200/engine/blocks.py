@@ -11,7 +11,9 @@ from __future__ import annotations
 
 import torch
 
-from .._lib import check, lib
+import numpy as np
+
+from .._lib import OP_ADD, OP_BN_APPLY, OP_BN_BACKWARD, OP_CONV, OP_WGRAD, check, lib
 from . import functional as Fn
 from .coords import _stream
 
@@ -33,7 +35,19 @@ class _Plan:
 
 
 def _w3(kernel, table):
-    return kernel.detach().contiguous().view(table.kvol, kernel.shape[-2], kernel.shape[-1])
+    """The kernel as a contiguous [kvol, cin, cout] view, kept on the parameter while its storage is unchanged (detach +
+    contiguous + view are three tensor ops, 372 times per step)."""
+    c = getattr(kernel, "_us3d_w3", None)
+    ptr = kernel.data_ptr()
+    if c is not None and c[0] == ptr and c[1] == table.kvol:
+        return c[2]
+    w3 = kernel.detach().contiguous().view(table.kvol, kernel.shape[-2], kernel.shape[-1])
+    if w3.data_ptr() == ptr:  # a real view of the parameter (not a contiguous copy): safe to keep
+        try:
+            kernel._us3d_w3 = (ptr, table.kvol, w3)
+        except Exception:  # pragma: no cover
+            pass
+    return w3
 
 
 def _conv_forward(x, kernel, table, flip, bn=None):
@@ -64,12 +78,214 @@ def _restore(t, planes):
         t._us3d_planes = planes
 
 
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# Launch lists: the launches of a block's forward / backward pass resolved into us3d_op_t records and issued by ONE C call
+# (us3d_run_ops, csrc/executor.cu).  Same kernels, same arguments, same order as the call-by-call route below — which stays
+# the fallback for everything a list does not cover (exact-fp32 mode, shapes off the tensor-core path, gradients wider than 256
+# channels) and the reference for the bit-identity test (tests/test_gpu_ops.py::test_launch_lists_equal_the_call_by_call_route).
+_lists = {"on": os.environ.get("US3D_LAUNCH_LISTS", "1") == "1"}
+_Z = (0,) * 16
+
+
+class _Ops:
+    """A launch list under assembly: flat int64 records [kind, p[16], v[10]] + two floats per op (us3d_run_ops_flat) — Python ints
+    appended to a list and converted ONCE (a ctypes structure per op costs as much host time as the call it replaces)."""
+
+    __slots__ = ("a", "f", "n")
+
+    def __init__(self):
+        self.a, self.f, self.n = [], [], 0
+
+    def emit(self, kind, p, v, f0=0.0, f1=0.0):
+        a = self.a
+        a.append(kind)
+        a.extend(p)
+        a.extend(_Z[:16 - len(p)])
+        a.extend(v)
+        a.extend(_Z[:10 - len(v)])
+        self.f.append(f0)
+        self.f.append(f1)
+        self.n += 1
+
+
+def set_launch_lists(on: bool):
+    _lists["on"] = bool(on)
+
+
+class _Fallback(Exception):
+    """Raised while a list is being assembled (nothing launched yet except plane splits of existing tensors): take the other route."""
+
+
+_pending_meta = []  # timer records of the list being assembled (bench.py's roofline leg pairs them with the library's events)
+
+
+def _run(ops):
+    t = Fn._timer
+    if t is not None:
+        t.meta.extend(_pending_meta)
+    _pending_meta.clear()
+    a, f = np.array(ops.a, dtype=np.int64), np.array(ops.f, dtype=np.float64)
+    check(lib.us3d_run_ops_flat(a.ctypes.data, f.ctypes.data, ops.n, _stream()))
+
+
+def _meta(kind, n_in, table, cin, cout, path):
+    if Fn._timer is not None:
+        _pending_meta.append((kind, n_in, table.n_rows, table.kvol, cin, cout, table.pairs(), path))
+
+
+def _planes_of(t, mode):
+    """(hi, lo) of an EXISTING tensor (cached, or split now — the tensor is complete in stream order)."""
+    if t.data_ptr() % 16 != 0 or Fn._ld(t) % 4 != 0 or t.shape[1] % 8 != 0:
+        raise _Fallback
+    return Fn.bf16_planes(t, mode == 3)
+
+
+def _new_rows(n, c, dev, mode):
+    """fp32 rows + the bf16 planes the pass that fills them will also write (attached like bn_apply_raw does)."""
+    y = torch.empty((n, c), dtype=torch.float32, device=dev)
+    if not (Fn._want_planes(c) and n > 0):
+        raise _Fallback
+    hi = torch.empty((n, c), dtype=torch.bfloat16, device=dev)
+    lo = torch.empty((n, c), dtype=torch.bfloat16, device=dev) if mode == 3 else None
+    y._us3d_planes = (hi, lo, y._version)
+    return y, hi, lo
+
+
+def _op_conv(ops, kind, planes, n_in, table, wimg, cin, cout, mode, dev, req):
+    """y = gather-conv over `table` of the tensor whose planes are given; returns y (appends the op, the timer record)."""
+    if wimg is None or not Fn._tc_ok(cin, cout) or cin <= 4:
+        raise _Fallback
+    hi, lo = planes
+    y = torch.empty((table.n_rows, cout), dtype=torch.float32, device=dev)
+    nbr, mask, order = table.ordered() or (table.nbr, table.mask, None)
+    part = table.partition() if order is not None else None
+    ws, ws_bytes = Fn._conv_workspace(dev, table.n_rows, table.kvol, cout) if order is None else (None, 0)
+    bn = [0, 0, 0, 0, 0, 0]
+    eps = mom = 0.0
+    if req is not None and table.n_rows > 0:
+        stats = torch.empty((2, cout), dtype=torch.float32, device=dev)
+        sp = stats.data_ptr()
+        bn = [Fn._bn_workspace(dev, cout).data_ptr(), sp, sp + 4 * cout, Fn._ptr(req.running_mean), Fn._ptr(req.running_var),
+              Fn._ptr(req.num_batches_tracked)]
+        eps, mom = float(req.eps), float(req.momentum if req.momentum is not None else 0.0)
+        req.mean, req.invstd = stats[0], stats[1]
+    _meta(kind, n_in, table, cin, cout, "mt")
+    ops.emit(OP_CONV, (hi.data_ptr(), Fn._ptr(lo), nbr.data_ptr(), wimg.data_ptr(), 0, Fn._ptr(order), y.data_ptr(), Fn._ptr(mask),
+                       Fn._ptr(part), Fn._ptr(ws), *bn),
+             (n_in, table.n_rows, table.kvol, cin, cout, mode, cout, 0, ws_bytes), eps, mom)
+    return y
+
+
+def _stats(ops, kind, planes, n_in, table, kernel, flip, norm, mode, dev):
+    """conv + the statistics its norm will use: (y, mean, invstd, batch statistics?, w3)."""
+    w3 = _w3(kernel, table)
+    cin, cout = w3.shape[1], w3.shape[2]
+    wimg = Fn.packed_weights(kernel, w3, flip, mode, True)[0] if cin > 4 else None
+    req = norm.stats_request()
+    y = _op_conv(ops, kind, planes, n_in, table, wimg, cin, cout, mode, dev, req)
+    if req is not None:
+        if req.mean is None:
+            raise _Fallback
+        return y, req.mean, req.invstd, True
+    m, s, t = norm.statistics(y)  # evaluation mode: running statistics, independent of y
+    if t:
+        raise _Fallback
+    return y, m, s, False
+
+
+def _op_bn_apply(ops, x, mean, invstd, gamma, beta, residual, relu, mode):
+    n, c = x.shape
+    g, b = Fn._detached(gamma), Fn._detached(beta)
+    y, hi, lo = _new_rows(n, c, x.device, mode)
+    ops.emit(OP_BN_APPLY, (x.data_ptr(), mean.data_ptr(), invstd.data_ptr(), g.data_ptr(), b.data_ptr(), Fn._ptr(residual), y.data_ptr(),
+                           hi.data_ptr(), Fn._ptr(lo)),
+             (c, n, c, 0 if residual is None else Fn._ld(residual), int(relu), c))
+    return y, g
+
+
+def _op_bn_backward(ops, dy, x, y, mean, invstd, g, relu, training, has_res, mode):
+    n, c = x.shape
+    dev = x.device
+    yy = y if y is not None else x
+    if dy.data_ptr() % 16 != 0 or Fn._ld(dy) % 4 != 0 or x.data_ptr() % 16 != 0 or Fn._ld(x) % 4 != 0:
+        raise _Fallback
+    dx, hi, lo = _new_rows(n, c, dev, mode)
+    dres = torch.empty((n, c), dtype=torch.float32, device=dev) if has_res else None
+    dgb = torch.empty((2, c), dtype=torch.float32, device=dev)
+    gp = dgb.data_ptr()
+    ops.emit(OP_BN_BACKWARD, (dy.data_ptr(), x.data_ptr(), yy.data_ptr(), mean.data_ptr(), invstd.data_ptr(), g.data_ptr(),
+                              Fn._bn_workspace(dev, c).data_ptr(), dx.data_ptr(), Fn._ptr(dres), gp, gp + 4 * c, hi.data_ptr(), Fn._ptr(lo)),
+             (Fn._ld(dy), Fn._ld(x), Fn._ld(yy), n, c, int(relu), int(training), c, c))
+    return dx, dres, dgb[0], dgb[1]
+
+
+def _op_dgrad(ops, dy, kernel, w3, bwd_getter, flip_dgrad, mode):
+    cin, cout = w3.shape[1], w3.shape[2]
+    bwd, flip = bwd_getter()
+    if flip != flip_dgrad or cin <= 4:
+        raise _Fallback
+    chunks = Fn.packed_weights(kernel, w3, flip, mode, True)[1]
+    if chunks is None or len(chunks) != 1:
+        raise _Fallback
+    return _op_conv(ops, "dgrad", dy._us3d_planes[:2], dy.shape[0], bwd, chunks[0][2], cout, cin, mode, dy.device, None)
+
+
+def _op_wgrad(ops, x_planes, n_in, table, dy, cin, cout, mode, kshape):
+    if not Fn._wgrad_tc_ok(cin, cout) or cin == 3 or Fn._wgrad_order["mode"] == "permute":
+        raise _Fallback
+    dw = Fn._zero_arena.take(table.kvol * cin * cout, dy.device)
+    nbr, mask, order = (table.ordered() if table.kvol <= 8 else None) or (table.nbr, table.mask, None)
+    dh, dl = dy._us3d_planes[:2]
+    _meta("wgrad", n_in, table, cin, cout, "wgrad-tc")
+    ops.emit(OP_WGRAD, (x_planes[0].data_ptr(), Fn._ptr(x_planes[1]), dh.data_ptr(), Fn._ptr(dl), nbr.data_ptr(), dw.data_ptr(), Fn._ptr(mask),
+                        Fn._ptr(order)),
+             (table.n_rows, table.kvol, cin, cout, mode))
+    return dw.view(kshape)
+
+
 class FusedBasicBlockFunction(torch.autograd.Function):
     """out = relu(bn2(conv2(relu(bn1(conv1(x))))) + shortcut(x)),  shortcut = identity or bn_d(conv_d(x))."""
 
     @staticmethod
     def forward(ctx, x, k1, g1, b1, k2, g2, b2, kd, gd, bd, plan: _Plan):
         x = Fn._rows(x)
+        res = None
+        mode = Fn.get_precision()
+        if _lists["on"] and mode != 0 and Fn._bn_fuse["on"]:
+            try:
+                res = FusedBasicBlockFunction._forward_list(x, k1, g1, b1, k2, g2, b2, kd, gd, bd, plan, mode)
+            except _Fallback:
+                _pending_meta.clear()
+                res = None
+        if res is None:
+            res = FusedBasicBlockFunction._forward_calls(x, k1, g1, b1, k2, g2, b2, kd, gd, bd, plan)
+        y1, a1, y2, out, yd, m1, s1, m2, s2, md, sd, g1c, g2c, gdc, t1, t2, td = res
+        ctx.save_for_backward(x, y1, a1, y2, out, yd, m1, s1, m2, s2, md, sd, g1c, g2c, gdc, k1, k2, kd)
+        ctx.plan, ctx.training = plan, (bool(t1), bool(t2), bool(td))
+        ctx.planes = (_planes(x), _planes(a1))  # the weight gradients re-use the forward's bf16 planes
+        return out
+
+    @staticmethod
+    def _forward_list(x, k1, g1, b1, k2, g2, b2, kd, gd, bd, plan, mode):
+        dev, n_in, ops = x.device, x.shape[0], _Ops()
+        xp = _planes_of(x, mode)
+        y1, m1, s1, t1 = _stats(ops, "fwd", xp, n_in, plan.fwd1, k1, plan.flip1, plan.norm1, mode, dev)
+        a1, g1c = _op_bn_apply(ops, y1, m1, s1, g1, b1, None, True, mode)
+        y2, m2, s2, t2 = _stats(ops, "fwd", a1._us3d_planes[:2], a1.shape[0], plan.fwd2, k2, plan.flip2, plan.norm2, mode, dev)
+        yd = md = sd = gdc = None
+        td = False
+        if kd is not None:
+            yd, md, sd, td = _stats(ops, "fwd", xp, n_in, plan.fwdd, kd, plan.flipd, plan.normd, mode, dev)
+            res, gdc = _op_bn_apply(ops, yd, md, sd, gd, bd, None, False, mode)
+        else:
+            res = x
+        out, g2c = _op_bn_apply(ops, y2, m2, s2, g2, b2, res, True, mode)
+        _run(ops)
+        return y1, a1, y2, out, yd, m1, s1, m2, s2, md, sd, g1c, g2c, gdc, t1, t2, td
+
+    @staticmethod
+    def _forward_calls(x, k1, g1, b1, k2, g2, b2, kd, gd, bd, plan):
         y1, m1, s1, t1 = _conv_norm_stats(x, k1, plan.fwd1, plan.flip1, plan.norm1)
         a1, g1c = Fn.bn_apply_raw(y1, g1, b1, None, m1, s1, True)
         y2, m2, s2, t2 = _conv_norm_stats(a1, k2, plan.fwd2, plan.flip2, plan.norm2)
@@ -81,19 +297,57 @@ class FusedBasicBlockFunction(torch.autograd.Function):
         else:
             res = x
         out, g2c = Fn.bn_apply_raw(y2, g2, b2, res, m2, s2, True)
-        ctx.save_for_backward(x, y1, a1, y2, out, yd, m1, s1, m2, s2, md, sd, g1c, g2c, gdc, k1, k2, kd)
-        ctx.plan, ctx.training = plan, (bool(t1), bool(t2), bool(td))
-        ctx.planes = (_planes(x), _planes(a1))  # the weight gradients re-use the forward's bf16 planes
-        return out
+        return y1, a1, y2, out, yd, m1, s1, m2, s2, md, sd, g1c, g2c, gdc, t1, t2, td
 
     @staticmethod
     def backward(ctx, dout):
         x, y1, a1, y2, out, yd, m1, s1, m2, s2, md, sd, g1c, g2c, gdc, k1, k2, kd = ctx.saved_tensors
         plan = ctx.plan
-        t1, t2, td = ctx.training
         _restore(x, ctx.planes[0])
         _restore(a1, ctx.planes[1])
         dout = Fn._rows(dout)
+        mode = Fn.get_precision()
+        if _lists["on"] and mode != 0:
+            try:
+                return FusedBasicBlockFunction._backward_list(ctx, dout, mode)
+            except _Fallback:
+                _pending_meta.clear()
+        return FusedBasicBlockFunction._backward_calls(ctx, dout)
+
+    @staticmethod
+    def _backward_list(ctx, dout, mode):
+        x, y1, a1, y2, out, yd, m1, s1, m2, s2, md, sd, g1c, g2c, gdc, k1, k2, kd = ctx.saved_tensors
+        plan = ctx.plan
+        t1, t2, td = ctx.training
+        need_dx = ctx.needs_input_grad[0]
+        ops = _Ops()
+        xp, a1p = _planes_of(x, mode), _planes_of(a1, mode)
+        # norm2 (+ residual, ReLU) -> conv2
+        dy2, dres, dg2, db2 = _op_bn_backward(ops, dout, y2, out, m2, s2, g2c, True, t2, True, mode)
+        w32 = _w3(k2, plan.fwd2)
+        da1 = _op_dgrad(ops, dy2, k2, w32, plan.bwd2, plan.flip2, mode)
+        dk2 = _op_wgrad(ops, a1p, a1.shape[0], plan.fwd2, dy2, w32.shape[1], w32.shape[2], mode, k2.shape)
+        # norm1 (ReLU) -> conv1
+        dy1, _, dg1, db1 = _op_bn_backward(ops, da1, y1, a1, m1, s1, g1c, True, t1, False, mode)
+        w31 = _w3(k1, plan.fwd1)
+        dx = _op_dgrad(ops, dy1, k1, w31, plan.bwd1, plan.flip1, mode) if need_dx else None
+        dk1 = _op_wgrad(ops, xp, x.shape[0], plan.fwd1, dy1, w31.shape[1], w31.shape[2], mode, k1.shape)
+        dkd = dgd = dbd = None
+        if kd is not None:
+            dyd, _, dgd, dbd = _op_bn_backward(ops, dres, yd, None, md, sd, gdc, False, td, False, mode)
+            w3d = _w3(kd, plan.fwdd)
+            dkd = _op_wgrad(ops, xp, x.shape[0], plan.fwdd, dyd, w3d.shape[1], w3d.shape[2], mode, kd.shape)
+            dres = _op_dgrad(ops, dyd, kd, w3d, plan.bwdd, plan.flipd, mode) if need_dx else None
+        if dx is not None:
+            ops.emit(OP_ADD, (dx.data_ptr(), dres.data_ptr(), dx.data_ptr()), (dx.numel(),))
+        _run(ops)
+        return dx, dk1, dg1, db1, dk2, dg2, db2, dkd, dgd, dbd, None
+
+    @staticmethod
+    def _backward_calls(ctx, dout):
+        x, y1, a1, y2, out, yd, m1, s1, m2, s2, md, sd, g1c, g2c, gdc, k1, k2, kd = ctx.saved_tensors
+        plan = ctx.plan
+        t1, t2, td = ctx.training
         # norm2 (+ residual, ReLU)
         dy2, dres, dg2, db2 = Fn.bn_backward_raw(dout, y2, out, m2, s2, g2c, True, t2, True)
         w32 = _w3(k2, plan.fwd2)

@@ -337,9 +337,30 @@ def _spconv_gather(x, table, w3, cin, cout, transpose_w, flip_k, bias, out, accu
     return y
 
 
+class _ZeroArena:
+    """Zero-filled fp32 storage for the weight gradients of a backward pass: one allocation + one fill per ~64 MB instead of one
+    torch.zeros (allocation + fill launch) per convolution.  Slices are handed out once and never reused — the gradients
+    outlive the pass (.grad, optimizer) and keep their arena alive through the view."""
+
+    def __init__(self):
+        self.buf, self.off = {}, {}
+
+    def take(self, n: int, dev: torch.device) -> torch.Tensor:
+        buf, off = self.buf.get(dev.index), self.off.get(dev.index, 0)
+        need = (n + 63) & ~63  # 256-byte granules
+        if buf is None or off + need > buf.numel():
+            buf = torch.zeros(max(need, 16 << 20), dtype=torch.float32, device=dev)
+            off = 0
+        self.buf[dev.index], self.off[dev.index] = buf, off + need
+        return buf[off:off + n]
+
+
+_zero_arena = _ZeroArena()
+
+
 def spconv_wgrad(x, table: NeighbourTable, dy, cin, cout):
     x, dy = _rows(x), _rows(dy)
-    dw = torch.zeros((table.kvol, cin, cout), dtype=torch.float32, device=x.device)
+    dw = _zero_arena.take(table.kvol * cin * cout, x.device).view(table.kvol, cin, cout)
     st = _stream()
     mode = _precision["mode"]
     if cin == 3 and table.kvol in (1, 8, 27):
@@ -472,6 +493,21 @@ def _want_planes(c):
     return _precision["mode"] != 0 and c % 16 == 0
 
 
+def _detached(p: torch.Tensor) -> torch.Tensor:
+    """p.detach().contiguous(), kept on the parameter while its storage is unchanged (shares the storage: values stay current)."""
+    c = getattr(p, "_us3d_det", None)
+    ptr = p.data_ptr()
+    if c is not None and c[0] == ptr:
+        return c[1]
+    d = p.detach().contiguous()
+    if d.data_ptr() == ptr:
+        try:
+            p._us3d_det = (ptr, d)
+        except Exception:  # pragma: no cover
+            pass
+    return d
+
+
 def bn_apply_raw(x, gamma, beta, residual, mean, invstd, relu):
     """One pass: y = [relu](bn(x) [+ residual]) as fp32 rows + the bf16 planes of y (cached on y for the next convolution).
     Returns (y, gamma as passed to the kernel)."""
@@ -479,8 +515,8 @@ def bn_apply_raw(x, gamma, beta, residual, mean, invstd, relu):
     dev = x.device
     if residual is not None:
         residual = _rows(residual)
-    g = gamma.detach().contiguous() if gamma is not None else torch.ones(c, device=dev)
-    b = beta.detach().contiguous() if beta is not None else torch.zeros(c, device=dev)
+    g = _detached(gamma) if gamma is not None else torch.ones(c, device=dev)
+    b = _detached(beta) if beta is not None else torch.zeros(c, device=dev)
     y = torch.empty((n, c), dtype=torch.float32, device=dev)
     hi = lo = None
     if _want_planes(c) and n > 0:
