@@ -79,6 +79,7 @@ def load_package(pkg_dir: str, alias: str, me_modules: dict):
 
 def our_models_on_oracle():
     from oracle import ops_cpu
+    import unscene3d_b200  # noqa: F401  (shims on sys.path: SetCriterion binds `custom_cuda_utils` when it is instantiated)
 
     mod = load_package(os.path.join(REPO, "unscene3d_b200", "models"), "oracle_backed_models", oracle_me_modules())
     mod.mask3d.CrossAttentionLayer.attention_core = staticmethod(ops_cpu.multihead_cross_attention)

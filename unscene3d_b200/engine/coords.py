@@ -12,6 +12,7 @@ Layout in HBM
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 import os
 from typing import Dict, List, Optional, Sequence, Tuple
@@ -90,6 +91,7 @@ class CoordinateMap:
         self.n = coords.shape[0]
         self.cap = keys.shape[0]
         self._batch_slices: Optional[List] = None
+        self._side = None  # the coordinate stream the map was built on (the host has synchronised with it), if any
 
 
 # Tables with at least this many rows are also kept in neighbour-pattern order for the tcgen05 kernels (0 disables)
@@ -160,6 +162,7 @@ class NeighbourTable:
 
 
 _coordinate_streams: Dict[int, "torch.cuda.Stream"] = {}
+_SLICES_ON_SIDE = os.environ.get("US3D_SLICES_ON_SIDE", "1") == "1"  # batch_slices' host reads on the coordinate stream
 
 
 def set_coordinate_stream(stream: Optional["torch.cuda.Stream"], device=None):
@@ -194,6 +197,7 @@ def unique_coords(coords: torch.Tensor, tensor_stride=(1, 1, 1), side_ok: bool =
     main = torch.cuda.current_stream(coords.device)
     with torch.cuda.stream(side):
         cmap, first, inverse = _unique_coords_on_current(coords, tensor_stride)
+    cmap._side = side
     # the maps are consumed by kernels of the compute stream: their memory must not be recycled by the coordinate
     # stream's allocator pool while those kernels are pending
     for t in (cmap.coords, cmap.keys, cmap.vals, first, inverse):
@@ -278,14 +282,25 @@ class CoordinateManager:
             if cmap.n == 0:
                 cmap._batch_slices = []
             else:
-                counts = torch.bincount(b.long())
-                sorted_ok = bool((b[1:] >= b[:-1]).all()) if cmap.n > 1 else True
-                if sorted_ok:
-                    ends = torch.cumsum(counts, 0).tolist()
-                    starts = [0] + ends[:-1]
-                    cmap._batch_slices = [slice(s, e) for s, e in zip(starts, ends)]
-                else:
-                    cmap._batch_slices = [torch.nonzero(b == i).flatten() for i in range(counts.shape[0])]
+                # Three host reads.  On the compute stream each of them waits for everything queued there — in Mask3D that is the
+                # whole backbone forward, after which the device idles while the host queues the decoder.  A map built on the
+                # coordinate stream is complete there (the host has synchronised with it), so the reads go to that stream.
+                side = cmap._side if _SLICES_ON_SIDE else None
+                main = torch.cuda.current_stream(b.device)
+                with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+                    counts = torch.bincount(b.long())
+                    sorted_ok = bool((b[1:] >= b[:-1]).all()) if cmap.n > 1 else True
+                    if sorted_ok:
+                        ends = torch.cumsum(counts, 0).tolist()
+                        starts = [0] + ends[:-1]
+                        cmap._batch_slices = [slice(s, e) for s, e in zip(starts, ends)]
+                    else:
+                        sel = [torch.nonzero(b == i).flatten() for i in range(counts.shape[0])]
+                        if side is not None:
+                            side.synchronize()  # index tensors consumed on the compute stream
+                            for t in sel:
+                                t.record_stream(main)
+                        cmap._batch_slices = sel
         return cmap._batch_slices
 
     # ---- neighbour tables ------------------------------------------------------------------

@@ -104,19 +104,49 @@ class SetCriterion(nn.Module):
         assert loss in table, f"do you really want to compute {loss} loss?"
         return table[loss](outputs, targets, indices, num_masks, mask_type, coords)
 
+    def _all_assignments(self, outs, targets, mask_type):
+        """Hungarian assignments of every decoder output at once, or None when the matcher is not the device-side one.
+
+        The reference matches output by output (models/criterion.py:255-276) and every match reads its B cost matrices back to the
+        host — 13 x B stream synchronisations per step, each draining the device queue in the middle of the step.  The cost
+        matrices do not depend on earlier assignments, so all of them are computed first and cross the bus in ONE copy; the
+        assignments are the same.  Only without point sub-sampling: with it the order of the random permutations is part of the
+        result (matcher and losses alternate in the reference)."""
+        m = self.matcher
+        if not hasattr(m, "cost_matrices") or getattr(m, "num_points", 0) != -1 or self.num_points != -1:
+            return None
+        from scipy.optimize import linear_sum_assignment
+
+        costs = [m.cost_matrices(o, targets, mask_type) for o in outs]
+        flat = torch.cat([c.reshape(-1).float() for cs in costs for c in cs]).cpu()
+        res, off = [], 0
+        for cs in costs:
+            per_scene = []
+            for c in cs:
+                n = c.numel()
+                i, j = linear_sum_assignment(flat[off:off + n].view(c.shape))
+                off += n
+                per_scene.append((torch.as_tensor(i, dtype=torch.int64), torch.as_tensor(j, dtype=torch.int64)))
+            res.append(per_scene)
+        return res
+
     def forward(self, outputs, targets, mask_type, coords=None):
         main = {k: v for k, v in outputs.items() if k != "aux_outputs"}
-        indices = self.matcher(main, targets, mask_type)
-        num_masks = torch.as_tensor([sum(len(t["labels"]) for t in targets)], dtype=torch.float,
-                                    device=next(iter(outputs.values())).device)
+        aux_outputs = outputs.get("aux_outputs", [])
+        assigned = self._all_assignments([main] + list(aux_outputs), targets, mask_type)
+        indices = assigned[0] if assigned is not None else self.matcher(main, targets, mask_type)
+        n_targets = sum(len(t["labels"]) for t in targets)
         if dist.is_available() and dist.is_initialized():
+            num_masks = torch.as_tensor([n_targets], dtype=torch.float, device=next(iter(outputs.values())).device)
             dist.all_reduce(num_masks)
-        num_masks = torch.clamp(num_masks / _world_size(), min=1).item()
+            num_masks = torch.clamp(num_masks / _world_size(), min=1).item()
+        else:  # single process: the count is known on the host (no device round trip)
+            num_masks = float(max(n_targets, 1))
         losses = {}
         for loss in self.losses:
             losses.update(self.get_loss(loss, outputs, targets, indices, num_masks, mask_type, coords))
-        for i, aux in enumerate(outputs.get("aux_outputs", [])):
-            indices = self.matcher(aux, targets, mask_type)
+        for i, aux in enumerate(aux_outputs):
+            indices = assigned[i + 1] if assigned is not None else self.matcher(aux, targets, mask_type)
             for loss in self.losses:
                 losses.update({f"{k}_{i}": v for k, v in
                                self.get_loss(loss, aux, targets, indices, num_masks, mask_type, coords).items()})
