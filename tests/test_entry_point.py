@@ -93,3 +93,73 @@ def test_unmodified_entry_point_runs_training_steps_on_the_shim(tmp_path):
     assert "train_loss_mask" in model.logged and "train_mean_loss_dice" in model.logged
     assert os.path.isfile(f"{tmp_path}/saved/last-epoch.ckpt"), "RegularCheckpointing did not fire"
     print(f"entry point: 4 training steps, losses {[round(l, 3) for l in trainer.losses]}, {_lib.launch_count()} libus3d launches")
+
+
+def _run_entry_point(root, tmp_path, overrides, on_fit):
+    """Runs the unmodified main_instance_segmentation.py with `overrides`; `on_fit(trainer, model)` sees the model right before fit."""
+    from unscene3d_b200 import standins
+
+    standins.install()
+    import pytorch_lightning as pl
+
+    for k in [k for k in sys.modules if k == "models" or k.startswith(("models.", "trainer", "datasets", "utils.", "benchmark")) or k == "utils"]:
+        del sys.modules[k]
+    orig_fit = pl.Trainer.fit
+
+    def fit(self, model):
+        on_fit(self, model)
+        return orig_fit(self, model)
+
+    pl.Trainer.fit = fit
+    argv, cwd = sys.argv, os.getcwd()
+    sys.path.insert(0, root)
+    os.chdir(tmp_path)
+    try:
+        sys.argv = ["main_instance_segmentation.py"] + overrides
+        runpy.run_path(os.path.join(root, "main_instance_segmentation.py"), run_name="__main__")
+    finally:
+        sys.argv = argv
+        os.chdir(cwd)
+        sys.path.remove(root)
+        pl.Trainer.fit = orig_fit
+
+
+@pytest.mark.gpu
+def test_unmodified_entry_point_loads_checkpoints_on_the_shim(tmp_path):
+    """SURVEY §8(f1), checkpoint half: a checkpoint written by one run of the unmodified entry point (RegularCheckpointing,
+    trainer/trainer.py:30-36) is loaded by the next through the reference's own loaders — `general.checkpoint` ->
+    load_checkpoint_with_missing_or_exsessive_keys (utils/utils.py:98-128) and `general.backbone_checkpoint` ->
+    load_backbone_checkpoint_with_missing_or_exsessive_keys (utils/utils.py:58-96): every parameter and buffer name of the shim's
+    modules is the reference's, so nothing is reported missing and the loaded model equals the saved one."""
+    import unscene3d_b200  # noqa: F401
+    from unscene3d_b200 import standins
+
+    standins.install()
+    import pytorch_lightning as pl
+
+    if "us3d-standin" not in getattr(pl, "__version__", ""):
+        pytest.skip("a real pytorch_lightning is installed: the stand-in loop is not in use")
+    root = staged_reference_root()
+    base = [o for o in OVERRIDES if not o.startswith(("trainer.max_epochs", "+trainer.limit_train_batches"))]
+    base += ["trainer.max_epochs=1", "+trainer.limit_train_batches=1", "general.gpus=1"]
+    # run 1: one step, writes <save_dir>/last-epoch.ckpt
+    _run_entry_point(root, tmp_path, base + [f"general.save_dir={tmp_path}/run1"], lambda tr, m: None)
+    ckpt = f"{tmp_path}/run1/last-epoch.ckpt"
+    saved = torch.load(ckpt)["state_dict"]
+    assert any(k.startswith("model.backbone.") for k in saved) and any(k.startswith("model.mask_embed_head") for k in saved)
+    # run 2: general.checkpoint -> the whole model comes from the file
+    seen = {}
+    _run_entry_point(root, tmp_path, base + [f"general.save_dir={tmp_path}/run2", f"general.checkpoint={ckpt}"],
+                     lambda tr, m: seen.update({k: v.detach().cpu().clone() for k, v in m.state_dict().items()}))
+    assert set(seen) == set(saved)
+    assert all(torch.equal(seen[k], saved[k].cpu()) for k in saved), "the loaded model differs from the checkpoint"
+    # run 3: general.backbone_checkpoint -> a backbone-only file (keys without the `model.backbone.` prefix)
+    bb = {k[len("model.backbone."):]: v for k, v in saved.items() if k.startswith("model.backbone.")}
+    bb_path = f"{tmp_path}/backbone.ckpt"
+    torch.save({"state_dict": bb}, bb_path)
+    seen3 = {}
+    _run_entry_point(root, tmp_path, base + [f"general.save_dir={tmp_path}/run3", f"general.backbone_checkpoint={bb_path}"],
+                     lambda tr, m: seen3.update({k: v.detach().cpu().clone() for k, v in m.state_dict().items()}))
+    assert all(torch.equal(seen3["model.backbone." + k], v.cpu()) for k, v in bb.items()), "the backbone differs from the checkpoint"
+    head = [k for k in saved if k.startswith("model.mask_embed_head") and saved[k].dtype.is_floating_point]
+    assert any(not torch.equal(seen3[k], saved[k].cpu()) for k in head), "the decoder should have kept its fresh initialisation"
