@@ -332,7 +332,10 @@ def test_launch_lists_equal_the_call_by_call_route(eng):
             res[on] = (out.F.detach().clone(), grads, bufs, ev.F.clone(), _lib.launch_count())
         finally:
             B.set_launch_lists(True)
-    assert res[True][4] == res[False][4], "the two routes must launch the same number of kernels"
+    # same kernels except the shortcut gradient: the list route lets the input-gradient launch accumulate it (y += ...), the
+    # call-by-call route adds it in a separate pass — one launch per residual block with an input gradient
+    n_blocks = sum(1 for m in net.modules() if type(m).__name__ == "BasicBlock")
+    assert 0 <= res[False][4] - res[True][4] <= n_blocks, (res[False][4], res[True][4], n_blocks)
     # the statistics' shared-memory / fp64 atomics and the weight gradient's reds make two runs of ONE route differ in the last
     # bits (amplified to ~1e-5 by 30 layers); the two routes must differ by no more than two such runs do
     floor_f = max(rel_err(res[None][0], res[False][0]), rel_err(res[None][3], res[False][3]), 1e-7)

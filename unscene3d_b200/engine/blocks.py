@@ -13,7 +13,7 @@ import torch
 
 import numpy as np
 
-from .._lib import OP_ADD, OP_BN_APPLY, OP_BN_BACKWARD, OP_CONV, OP_WGRAD, check, lib
+from .._lib import OP_BN_APPLY, OP_BN_BACKWARD, OP_CONV, OP_WGRAD, check, lib
 from . import functional as Fn
 from .coords import _stream
 
@@ -152,12 +152,13 @@ def _new_rows(n, c, dev, mode):
     return y, hi, lo
 
 
-def _op_conv(ops, kind, planes, n_in, table, wimg, cin, cout, mode, dev, req):
-    """y = gather-conv over `table` of the tensor whose planes are given; returns y (appends the op, the timer record)."""
+def _op_conv(ops, kind, planes, n_in, table, wimg, cin, cout, mode, dev, req, into=None):
+    """y = gather-conv over `table` of the tensor whose planes are given (`into`: y = into += ...); returns y (appends the op, the
+    timer record)."""
     if wimg is None or not Fn._tc_ok(cin, cout) or cin <= 4:
         raise _Fallback
     hi, lo = planes
-    y = torch.empty((table.n_rows, cout), dtype=torch.float32, device=dev)
+    y = into if into is not None else torch.empty((table.n_rows, cout), dtype=torch.float32, device=dev)
     nbr, mask, order = table.ordered() or (table.nbr, table.mask, None)
     part = table.partition() if order is not None else None
     ws, ws_bytes = Fn._conv_workspace(dev, table.n_rows, table.kvol, cout) if order is None else (None, 0)
@@ -173,7 +174,7 @@ def _op_conv(ops, kind, planes, n_in, table, wimg, cin, cout, mode, dev, req):
     _meta(kind, n_in, table, cin, cout, "mt")
     ops.emit(OP_CONV, (hi.data_ptr(), Fn._ptr(lo), nbr.data_ptr(), wimg.data_ptr(), 0, Fn._ptr(order), y.data_ptr(), Fn._ptr(mask),
                        Fn._ptr(part), Fn._ptr(ws), *bn),
-             (n_in, table.n_rows, table.kvol, cin, cout, mode, cout, 0, ws_bytes), eps, mom)
+             (n_in, table.n_rows, table.kvol, cin, cout, mode, cout, 0 if into is None else 1, ws_bytes), eps, mom)
     return y
 
 
@@ -220,7 +221,7 @@ def _op_bn_backward(ops, dy, x, y, mean, invstd, g, relu, training, has_res, mod
     return dx, dres, dgb[0], dgb[1]
 
 
-def _op_dgrad(ops, dy, kernel, w3, bwd_getter, flip_dgrad, mode):
+def _op_dgrad(ops, dy, kernel, w3, bwd_getter, flip_dgrad, mode, into=None):
     cin, cout = w3.shape[1], w3.shape[2]
     bwd, flip = bwd_getter()
     if flip != flip_dgrad or cin <= 4:
@@ -228,7 +229,9 @@ def _op_dgrad(ops, dy, kernel, w3, bwd_getter, flip_dgrad, mode):
     chunks = Fn.packed_weights(kernel, w3, flip, mode, True)[1]
     if chunks is None or len(chunks) != 1:
         raise _Fallback
-    return _op_conv(ops, "dgrad", dy._us3d_planes[:2], dy.shape[0], bwd, chunks[0][2], cout, cin, mode, dy.device, None)
+    if into is not None and (into.shape != (bwd.n_rows, cin) or not into.is_contiguous()):
+        raise _Fallback
+    return _op_conv(ops, "dgrad", dy._us3d_planes[:2], dy.shape[0], bwd, chunks[0][2], cout, cin, mode, dy.device, None, into)
 
 
 def _op_wgrad(ops, x_planes, n_in, table, dy, cin, cout, mode, kshape):
@@ -330,16 +333,18 @@ class FusedBasicBlockFunction(torch.autograd.Function):
         # norm1 (ReLU) -> conv1
         dy1, _, dg1, db1 = _op_bn_backward(ops, da1, y1, a1, m1, s1, g1c, True, t1, False, mode)
         w31 = _w3(k1, plan.fwd1)
-        dx = _op_dgrad(ops, dy1, k1, w31, plan.bwd1, plan.flip1, mode) if need_dx else None
+        # dx = dX(conv1) + gradient of the shortcut: the second term is accumulated by the gather kernel's epilogue (y += ...), not
+        # by a separate pass over both tensors — identity shortcut: into the residual gradient norm2's backward has written;
+        # convolutional shortcut: its input gradient lands on top of conv1's
+        dx = (_op_dgrad(ops, dy1, k1, w31, plan.bwd1, plan.flip1, mode, into=dres if kd is None else None)) if need_dx else None
         dk1 = _op_wgrad(ops, xp, x.shape[0], plan.fwd1, dy1, w31.shape[1], w31.shape[2], mode, k1.shape)
         dkd = dgd = dbd = None
         if kd is not None:
             dyd, _, dgd, dbd = _op_bn_backward(ops, dres, yd, None, md, sd, gdc, False, td, False, mode)
             w3d = _w3(kd, plan.fwdd)
             dkd = _op_wgrad(ops, xp, x.shape[0], plan.fwdd, dyd, w3d.shape[1], w3d.shape[2], mode, kd.shape)
-            dres = _op_dgrad(ops, dyd, kd, w3d, plan.bwdd, plan.flipd, mode) if need_dx else None
-        if dx is not None:
-            ops.emit(OP_ADD, (dx.data_ptr(), dres.data_ptr(), dx.data_ptr()), (dx.numel(),))
+            if need_dx:
+                _op_dgrad(ops, dyd, kd, w3d, plan.bwdd, plan.flipd, mode, into=dx)
         _run(ops)
         return dx, dk1, dg1, db1, dk2, dg2, db2, dkd, dgd, dbd, None
 
