@@ -86,3 +86,21 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f"{f} imports the oracle"
+
+
+def test_launch_list_rejects_unknown_ops_without_a_device():
+    """us3d_run_ops validates the list before anything is launched: an unknown op kind is an argument error (no GPU needed), an
+    empty list is a no-op."""
+    import ctypes
+
+    from unscene3d_b200 import _lib
+
+    lib = _lib.lib
+    assert lib.us3d_run_ops(None, 0, None) == 0
+    op = _lib.Op()
+    op.kind = 99
+    rc = lib.us3d_run_ops(ctypes.byref(op), 1, None)
+    assert rc != 0 and b"unknown op kind 99" in lib.us3d_last_error()
+    flat = (ctypes.c_longlong * 27)(*([77] + [0] * 26))
+    f = (ctypes.c_double * 2)(0.0, 0.0)
+    assert lib.us3d_run_ops_flat(flat, f, 1, None) != 0 and b"unknown op kind 77" in lib.us3d_last_error()
