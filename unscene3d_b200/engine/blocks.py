@@ -423,8 +423,22 @@ class FusedConvNormReLUFunction(torch.autograd.Function):
     def forward(ctx, x, k, g, b, plan):
         x = Fn._rows(x)
         fwd, bwd_getter, flip, norm = plan
-        y, m, s, t = _conv_norm_stats(x, k, fwd, flip, norm)
-        out, gc = Fn.bn_apply_raw(y, g, b, None, m, s, True)
+        res = None
+        mode = Fn.get_precision()
+        if _lists["on"] and mode != 0 and Fn._bn_fuse["on"]:
+            try:  # the two launches as one list (the 3-channel stem and anything off the tensor-core path fall back)
+                ops = _Ops()
+                y, m, s, t = _stats(ops, "fwd", _planes_of(x, mode), x.shape[0], fwd, k, flip, norm, mode, x.device)
+                out, gc = _op_bn_apply(ops, y, m, s, g, b, None, True, mode)
+                _run(ops)
+                res = (y, m, s, t, out, gc)
+            except _Fallback:
+                _pending_meta.clear()
+        if res is None:
+            y, m, s, t = _conv_norm_stats(x, k, fwd, flip, norm)
+            out, gc = Fn.bn_apply_raw(y, g, b, None, m, s, True)
+        else:
+            y, m, s, t, out, gc = res
         ctx.save_for_backward(x, y, out, m, s, gc, k)
         ctx.plan, ctx.training, ctx.planes = plan, bool(t), _planes(x)
         return out
@@ -434,8 +448,21 @@ class FusedConvNormReLUFunction(torch.autograd.Function):
         x, y, out, m, s, gc, k = ctx.saved_tensors
         fwd, bwd_getter, flip, _ = ctx.plan
         _restore(x, ctx.planes)
-        dy, _, dg, db = Fn.bn_backward_raw(Fn._rows(dout), y, out, m, s, gc, True, ctx.training, False)
+        dout = Fn._rows(dout)
         w3 = _w3(k, fwd)
+        mode = Fn.get_precision()
+        if _lists["on"] and mode != 0:
+            try:
+                ops = _Ops()
+                xp = _planes_of(x, mode)
+                dy, _, dg, db = _op_bn_backward(ops, dout, y, out, m, s, gc, True, ctx.training, False, mode)
+                dx = _op_dgrad(ops, dy, k, w3, bwd_getter, flip, mode) if ctx.needs_input_grad[0] else None
+                dk = _op_wgrad(ops, xp, x.shape[0], fwd, dy, w3.shape[1], w3.shape[2], mode, k.shape)
+                _run(ops)
+                return dx, dk, dg, db, None
+            except _Fallback:
+                _pending_meta.clear()
+        dy, _, dg, db = Fn.bn_backward_raw(dout, y, out, m, s, gc, True, ctx.training, False)
         dx = Fn.conv_input_gradient(dy, k, w3, bwd_getter, flip) if ctx.needs_input_grad[0] else None
         dk = Fn.spconv_wgrad(x, fwd, dy, w3.shape[1], w3.shape[2]).view(k.shape)
         return dx, dk, dg, db, None
