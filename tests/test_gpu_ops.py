@@ -318,7 +318,8 @@ def test_launch_lists_equal_the_call_by_call_route(eng):
     for on in (True, False, None):  # None: the call-by-call route a second time = the run-to-run noise floor of the atomics
         B.set_launch_lists(bool(on))
         try:
-            net = models.Res16UNet14(3, 20, BackboneConfig(), D=3, out_fpn=True)
+            # Res16UNet34C: stages of 2-6 blocks (one launch list per stage), weight images packed lazily DURING list assembly
+            net = models.Res16UNet34C(3, 20, BackboneConfig(), D=3, out_fpn=True)
             net.load_state_dict(seeded_state(net, 0))
             net = net.cuda().train()
             _lib.reset_launch_count()

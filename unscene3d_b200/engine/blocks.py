@@ -92,10 +92,18 @@ class _Ops:
     """A launch list under assembly: flat int64 records [kind, p[16], v[10]] + two floats per op (us3d_run_ops_flat) — Python ints
     appended to a list and converted ONCE (a ctypes structure per op costs as much host time as the call it replaces)."""
 
-    __slots__ = ("a", "f", "n")
+    __slots__ = ("a", "f", "n", "keep")
 
     def __init__(self):
         self.a, self.f, self.n = [], [], 0
+        # Every tensor an op of the list reads or writes stays alive until the list has been LAUNCHED: a temporary dropped during
+        # assembly would hand its memory back to the allocator, and a kernel launched right away into the recycled block (a lazy
+        # weight pack, the zero fill of a new gradient arena, a plane split) would be overwritten by the deferred op later.
+        self.keep = []
+
+    def hold(self, *tensors):
+        self.keep.extend(tensors)
+        return tensors[0]
 
     def emit(self, kind, p, v, f0=0.0, f1=0.0):
         a = self.a
@@ -141,7 +149,7 @@ def _planes_of(t, mode):
     return Fn.bf16_planes(t, mode == 3)
 
 
-def _new_rows(n, c, dev, mode):
+def _new_rows(ops, n, c, dev, mode):
     """fp32 rows + the bf16 planes the pass that fills them will also write (attached like bn_apply_raw does)."""
     y = torch.empty((n, c), dtype=torch.float32, device=dev)
     if not (Fn._want_planes(c) and n > 0):
@@ -149,6 +157,7 @@ def _new_rows(n, c, dev, mode):
     hi = torch.empty((n, c), dtype=torch.bfloat16, device=dev)
     lo = torch.empty((n, c), dtype=torch.bfloat16, device=dev) if mode == 3 else None
     y._us3d_planes = (hi, lo, y._version)
+    ops.hold(y, hi, lo)
     return y, hi, lo
 
 
@@ -159,13 +168,15 @@ def _op_conv(ops, kind, planes, n_in, table, wimg, cin, cout, mode, dev, req, in
         raise _Fallback
     hi, lo = planes
     y = into if into is not None else torch.empty((table.n_rows, cout), dtype=torch.float32, device=dev)
+    ops.hold(y, hi, lo, wimg)
     nbr, mask, order = table.ordered() or (table.nbr, table.mask, None)
     part = table.partition() if order is not None else None
     ws, ws_bytes = Fn._conv_workspace(dev, table.n_rows, table.kvol, cout) if order is None else (None, 0)
+    ops.hold(ws)  # the per-device scratch is REPLACED when a later op needs more: this op keeps the buffer it was given
     bn = [0, 0, 0, 0, 0, 0]
     eps = mom = 0.0
     if req is not None and table.n_rows > 0:
-        stats = torch.empty((2, cout), dtype=torch.float32, device=dev)
+        stats = ops.hold(torch.empty((2, cout), dtype=torch.float32, device=dev))
         sp = stats.data_ptr()
         bn = [Fn._bn_workspace(dev, cout).data_ptr(), sp, sp + 4 * cout, Fn._ptr(req.running_mean), Fn._ptr(req.running_var),
               Fn._ptr(req.num_batches_tracked)]
@@ -198,7 +209,8 @@ def _stats(ops, kind, planes, n_in, table, kernel, flip, norm, mode, dev):
 def _op_bn_apply(ops, x, mean, invstd, gamma, beta, residual, relu, mode):
     n, c = x.shape
     g, b = Fn._detached(gamma), Fn._detached(beta)
-    y, hi, lo = _new_rows(n, c, x.device, mode)
+    y, hi, lo = _new_rows(ops, n, c, x.device, mode)
+    ops.hold(x, mean, invstd, g, b, residual)
     ops.emit(OP_BN_APPLY, (x.data_ptr(), mean.data_ptr(), invstd.data_ptr(), g.data_ptr(), b.data_ptr(), Fn._ptr(residual), y.data_ptr(),
                            hi.data_ptr(), Fn._ptr(lo)),
              (c, n, c, 0 if residual is None else Fn._ld(residual), int(relu), c))
@@ -211,9 +223,10 @@ def _op_bn_backward(ops, dy, x, y, mean, invstd, g, relu, training, has_res, mod
     yy = y if y is not None else x
     if dy.data_ptr() % 16 != 0 or Fn._ld(dy) % 4 != 0 or x.data_ptr() % 16 != 0 or Fn._ld(x) % 4 != 0:
         raise _Fallback
-    dx, hi, lo = _new_rows(n, c, dev, mode)
+    dx, hi, lo = _new_rows(ops, n, c, dev, mode)
     dres = torch.empty((n, c), dtype=torch.float32, device=dev) if has_res else None
     dgb = torch.empty((2, c), dtype=torch.float32, device=dev)
+    ops.hold(dres, dgb, dy, x, yy, mean, invstd, g)
     gp = dgb.data_ptr()
     ops.emit(OP_BN_BACKWARD, (dy.data_ptr(), x.data_ptr(), yy.data_ptr(), mean.data_ptr(), invstd.data_ptr(), g.data_ptr(),
                               Fn._bn_workspace(dev, c).data_ptr(), dx.data_ptr(), Fn._ptr(dres), gp, gp + 4 * c, hi.data_ptr(), Fn._ptr(lo)),
@@ -240,6 +253,7 @@ def _op_wgrad(ops, x_planes, n_in, table, dy, cin, cout, mode, kshape):
     dw = Fn._zero_arena.take(table.kvol * cin * cout, dy.device)
     nbr, mask, order = (table.ordered() if table.kvol <= 8 else None) or (table.nbr, table.mask, None)
     dh, dl = dy._us3d_planes[:2]
+    ops.hold(dw, dh, dl, x_planes[0], x_planes[1])
     _meta("wgrad", n_in, table, cin, cout, "wgrad-tc")
     ops.emit(OP_WGRAD, (x_planes[0].data_ptr(), Fn._ptr(x_planes[1]), dh.data_ptr(), Fn._ptr(dl), nbr.data_ptr(), dw.data_ptr(), Fn._ptr(mask),
                         Fn._ptr(order)),
@@ -271,7 +285,15 @@ class FusedBasicBlockFunction(torch.autograd.Function):
 
     @staticmethod
     def _forward_list(x, k1, g1, b1, k2, g2, b2, kd, gd, bd, plan, mode):
-        dev, n_in, ops = x.device, x.shape[0], _Ops()
+        ops = _Ops()
+        res = FusedBasicBlockFunction._forward_ops(ops, x, k1, g1, b1, k2, g2, b2, kd, gd, bd, plan, mode)
+        _run(ops)
+        return res
+
+    @staticmethod
+    def _forward_ops(ops, x, k1, g1, b1, k2, g2, b2, kd, gd, bd, plan, mode):
+        """Appends the block's forward launches to `ops` (nothing is launched here); returns what forward saves."""
+        dev, n_in = x.device, x.shape[0]
         xp = _planes_of(x, mode)
         y1, m1, s1, t1 = _stats(ops, "fwd", xp, n_in, plan.fwd1, k1, plan.flip1, plan.norm1, mode, dev)
         a1, g1c = _op_bn_apply(ops, y1, m1, s1, g1, b1, None, True, mode)
@@ -284,7 +306,6 @@ class FusedBasicBlockFunction(torch.autograd.Function):
         else:
             res = x
         out, g2c = _op_bn_apply(ops, y2, m2, s2, g2, b2, res, True, mode)
-        _run(ops)
         return y1, a1, y2, out, yd, m1, s1, m2, s2, md, sd, g1c, g2c, gdc, t1, t2, td
 
     @staticmethod
@@ -319,11 +340,16 @@ class FusedBasicBlockFunction(torch.autograd.Function):
 
     @staticmethod
     def _backward_list(ctx, dout, mode):
-        x, y1, a1, y2, out, yd, m1, s1, m2, s2, md, sd, g1c, g2c, gdc, k1, k2, kd = ctx.saved_tensors
-        plan = ctx.plan
-        t1, t2, td = ctx.training
-        need_dx = ctx.needs_input_grad[0]
         ops = _Ops()
+        grads = FusedBasicBlockFunction._backward_ops(ops, ctx.saved_tensors, ctx.plan, ctx.training, dout, ctx.needs_input_grad[0], mode)
+        _run(ops)
+        return grads + (None,)
+
+    @staticmethod
+    def _backward_ops(ops, saved, plan, training, dout, need_dx, mode):
+        """Appends the block's backward launches to `ops`; returns (dx, dk1, dg1, db1, dk2, dg2, db2, dkd, dgd, dbd)."""
+        x, y1, a1, y2, out, yd, m1, s1, m2, s2, md, sd, g1c, g2c, gdc, k1, k2, kd = saved
+        t1, t2, td = training
         xp, a1p = _planes_of(x, mode), _planes_of(a1, mode)
         # norm2 (+ residual, ReLU) -> conv2
         dy2, dres, dg2, db2 = _op_bn_backward(ops, dout, y2, out, m2, s2, g2c, True, t2, True, mode)
@@ -345,14 +371,16 @@ class FusedBasicBlockFunction(torch.autograd.Function):
             dkd = _op_wgrad(ops, xp, x.shape[0], plan.fwdd, dyd, w3d.shape[1], w3d.shape[2], mode, kd.shape)
             if need_dx:
                 _op_dgrad(ops, dyd, kd, w3d, plan.bwdd, plan.flipd, mode, into=dx)
-        _run(ops)
-        return dx, dk1, dg1, db1, dk2, dg2, db2, dkd, dgd, dbd, None
+        return dx, dk1, dg1, db1, dk2, dg2, db2, dkd, dgd, dbd
 
     @staticmethod
     def _backward_calls(ctx, dout):
-        x, y1, a1, y2, out, yd, m1, s1, m2, s2, md, sd, g1c, g2c, gdc, k1, k2, kd = ctx.saved_tensors
-        plan = ctx.plan
-        t1, t2, td = ctx.training
+        return FusedBasicBlockFunction._backward_calls_of(ctx.saved_tensors, ctx.plan, ctx.training, dout, ctx.needs_input_grad[0]) + (None,)
+
+    @staticmethod
+    def _backward_calls_of(saved, plan, training, dout, need_dx):
+        x, y1, a1, y2, out, yd, m1, s1, m2, s2, md, sd, g1c, g2c, gdc, k1, k2, kd = saved
+        t1, t2, td = training
         # norm2 (+ residual, ReLU)
         dy2, dres, dg2, db2 = Fn.bn_backward_raw(dout, y2, out, m2, s2, g2c, True, t2, True)
         w32 = _w3(k2, plan.fwd2)
@@ -361,30 +389,28 @@ class FusedBasicBlockFunction(torch.autograd.Function):
         # norm1 (ReLU)
         dy1, _, dg1, db1 = Fn.bn_backward_raw(da1, y1, a1, m1, s1, g1c, True, t1, False)
         w31 = _w3(k1, plan.fwd1)
-        dx = Fn.conv_input_gradient(dy1, k1, w31, plan.bwd1, plan.flip1) if ctx.needs_input_grad[0] else None
+        dx = Fn.conv_input_gradient(dy1, k1, w31, plan.bwd1, plan.flip1) if need_dx else None
         dk1 = Fn.spconv_wgrad(x, plan.fwd1, dy1, w31.shape[1], w31.shape[2]).view(k1.shape)
         dkd = dgd = dbd = None
         if kd is not None:
             dyd, _, dgd, dbd = Fn.bn_backward_raw(dres, yd, None, md, sd, gdc, False, td, False)
             w3d = _w3(kd, plan.fwdd)
             dkd = Fn.spconv_wgrad(x, plan.fwdd, dyd, w3d.shape[1], w3d.shape[2]).view(kd.shape)
-            dres = Fn.conv_input_gradient(dyd, kd, w3d, plan.bwdd, plan.flipd) if ctx.needs_input_grad[0] else None
+            dres = Fn.conv_input_gradient(dyd, kd, w3d, plan.bwdd, plan.flipd) if need_dx else None
         if dx is not None:
             check(lib.us3d_add(dx.data_ptr(), dres.data_ptr(), dx.data_ptr(), dx.numel(), _stream()))
-        return dx, dk1, dg1, db1, dk2, dg2, db2, dkd, dgd, dbd, None
+        return dx, dk1, dg1, db1, dk2, dg2, db2, dkd, dgd, dbd
 
 
-def fused_basic_block(block, x):
-    """Runs a BasicBlock (conv1/norm1/conv2/norm2[/downsample = Sequential(conv, norm)]) as one autograd node; returns the
-    output SparseTensor, or None when the block is not of that shape (the caller then takes the module-by-module route)."""
-    from .tensor import MinkowskiBatchNorm, SparseTensor, _ConvBase
+def _block_plan(block, cm, key, cin):
+    """(plan, the 9 parameters of FusedBasicBlockFunction, output key) of a BasicBlock applied to a [*, cin] tensor on map `key`,
+    or None when the block is not of the fusable shape."""
+    from .tensor import MinkowskiBatchNorm, _ConvBase
 
-    if not _enabled["on"]:
-        return None
     c1, n1, c2, n2 = (getattr(block, a, None) for a in ("conv1", "norm1", "conv2", "norm2"))
     if not (isinstance(c1, _ConvBase) and isinstance(c2, _ConvBase) and isinstance(n1, MinkowskiBatchNorm) and isinstance(n2, MinkowskiBatchNorm)):
         return None
-    if hasattr(block, "conv3") or c1.bias is not None or c2.bias is not None or not x.F.is_cuda or x.F.dtype != torch.float32:
+    if hasattr(block, "conv3") or c1.bias is not None or c2.bias is not None:
         return None
     ds = block.downsample
     cd = nd = None
@@ -396,7 +422,6 @@ def fused_basic_block(block, x):
     for n in (n1, n2, nd):
         if n is not None and (n.bn.weight is None or (n.bn.training and n.bn.track_running_stats and n.bn.momentum is None)):
             return None
-    cm, key = x.coordinate_manager, x.coordinate_map_key
     plan = _Plan()
     key1, plan.fwd1, plan.bwd1, plan.flip1 = c1.tables(cm, key)
     key2, plan.fwd2, plan.bwd2, plan.flip2 = c2.tables(cm, key1)
@@ -407,12 +432,121 @@ def fused_basic_block(block, x):
         keyd, plan.fwdd, plan.bwdd, plan.flipd = cd.tables(cm, key)
         if keyd != key2:
             return None
-    elif key2 != key or c2.kernel.shape[-1] != x.F.shape[1]:
+    elif key2 != key or c2.kernel.shape[-1] != cin:
         return None
-    out = FusedBasicBlockFunction.apply(x.F, c1.kernel, n1.bn.weight, n1.bn.bias, c2.kernel, n2.bn.weight, n2.bn.bias,
-                                        None if cd is None else cd.kernel, None if nd is None else nd.bn.weight,
-                                        None if nd is None else nd.bn.bias, plan)
+    params = (c1.kernel, n1.bn.weight, n1.bn.bias, c2.kernel, n2.bn.weight, n2.bn.bias, None if cd is None else cd.kernel,
+              None if nd is None else nd.bn.weight, None if nd is None else nd.bn.bias)
+    return plan, params, key2
+
+
+def fused_basic_block(block, x):
+    """Runs a BasicBlock (conv1/norm1/conv2/norm2[/downsample = Sequential(conv, norm)]) as one autograd node; returns the
+    output SparseTensor, or None when the block is not of that shape (the caller then takes the module-by-module route)."""
+    from .tensor import SparseTensor
+
+    if not _enabled["on"] or not x.F.is_cuda or x.F.dtype != torch.float32:
+        return None
+    cm = x.coordinate_manager
+    bp = _block_plan(block, cm, x.coordinate_map_key, x.F.shape[1])
+    if bp is None:
+        return None
+    plan, params, key2 = bp
+    out = FusedBasicBlockFunction.apply(x.F, *params, plan)
     return SparseTensor(out, coordinate_map_key=key2, coordinate_manager=cm)
+
+
+_N_SAVED = 18  # tensors FusedBasicBlockFunction saves per block
+
+
+class FusedStageFunction(torch.autograd.Function):
+    """The consecutive BasicBlocks of a stage (models/res16unet.py:224-297: block1 .. block8 are Sequentials of 2-6 blocks) as ONE
+    autograd node with ONE launch list each way: the same launches as block by block, 8 nodes and 16 C calls per step instead of
+    23 and 46.  Falls back block by block (call-by-call route) when a list cannot be assembled."""
+
+    @staticmethod
+    def forward(ctx, x, plans, *params):
+        x = Fn._rows(x)
+        mode = Fn.get_precision()
+        nb = len(plans)
+        results = None
+        if _lists["on"] and mode != 0 and Fn._bn_fuse["on"]:
+            try:
+                ops, cur, results = _Ops(), x, []
+                for i in range(nb):
+                    r = FusedBasicBlockFunction._forward_ops(ops, cur, *params[9 * i:9 * i + 9], plans[i], mode)
+                    results.append((cur,) + r)
+                    cur = r[3]
+                _run(ops)
+            except _Fallback:
+                _pending_meta.clear()
+                results = None
+        if results is None:
+            cur, results = x, []
+            for i in range(nb):
+                r = FusedBasicBlockFunction._forward_calls(cur, *params[9 * i:9 * i + 9], plans[i])
+                results.append((cur,) + r)
+                cur = r[3]
+        saved, trainings, planes = [], [], []
+        for i, (xi, y1, a1, y2, out, yd, m1, s1, m2, s2, md, sd, g1c, g2c, gdc, t1, t2, td) in enumerate(results):
+            k1, k2, kd = params[9 * i], params[9 * i + 3], params[9 * i + 6]
+            saved += [xi, y1, a1, y2, out, yd, m1, s1, m2, s2, md, sd, g1c, g2c, gdc, k1, k2, kd]
+            trainings.append((bool(t1), bool(t2), bool(td)))
+            planes.append((_planes(xi), _planes(a1)))
+        ctx.save_for_backward(*saved)
+        ctx.plans, ctx.trainings, ctx.planes = plans, trainings, planes
+        return results[-1][4]
+
+    @staticmethod
+    def backward(ctx, dout):
+        saved, plans = ctx.saved_tensors, ctx.plans
+        nb = len(plans)
+        per = [saved[_N_SAVED * i:_N_SAVED * (i + 1)] for i in range(nb)]
+        for i in range(nb):
+            _restore(per[i][0], ctx.planes[i][0])
+            _restore(per[i][2], ctx.planes[i][1])
+        dout = Fn._rows(dout)
+        mode = Fn.get_precision()
+        grads = None
+        if _lists["on"] and mode != 0:
+            try:
+                ops, cur, grads = _Ops(), dout, [None] * nb
+                for i in reversed(range(nb)):
+                    g = FusedBasicBlockFunction._backward_ops(ops, per[i], plans[i], ctx.trainings[i], cur, i > 0 or ctx.needs_input_grad[0], mode)
+                    grads[i], cur = g, g[0]
+                _run(ops)
+            except _Fallback:
+                _pending_meta.clear()
+                grads = None
+        if grads is None:
+            cur, grads = dout, [None] * nb
+            for i in reversed(range(nb)):
+                g = FusedBasicBlockFunction._backward_calls_of(per[i], plans[i], ctx.trainings[i], cur, i > 0 or ctx.needs_input_grad[0])
+                grads[i], cur = g, g[0]
+        flat = []
+        for g in grads:
+            flat += list(g[1:])
+        return (grads[0][0], None) + tuple(flat)
+
+
+def fused_stage(blocks, x):
+    """Runs a Sequential of BasicBlocks as one autograd node (FusedStageFunction); None when any of them is not of the fusable
+    shape (the caller then runs the Sequential, whose blocks still fuse one by one where they can)."""
+    from .tensor import SparseTensor
+
+    if not (_enabled["on"] and _lists["on"]) or not x.F.is_cuda or x.F.dtype != torch.float32 or len(blocks) < 2:
+        return None
+    cm, key, cin = x.coordinate_manager, x.coordinate_map_key, x.F.shape[1]
+    plans, params = [], []
+    for block in blocks:
+        bp = _block_plan(block, cm, key, cin)
+        if bp is None:
+            return None
+        plan, p, key = bp
+        plans.append(plan)
+        params += list(p)
+        cin = p[3].shape[-1]
+    out = FusedStageFunction.apply(x.F, plans, *params)
+    return SparseTensor(out, coordinate_map_key=key, coordinate_manager=cm)
 
 
 class FusedConvNormReLUFunction(torch.autograd.Function):

@@ -85,6 +85,12 @@ def _cuda_transition_core(conv_layer, norm, x):
     return fused_conv_norm_relu(conv_layer, norm, x)
 
 
+def _cuda_stage_core(blocks, x):
+    from unscene3d_b200.engine.blocks import fused_stage
+
+    return fused_stage(blocks, x)
+
+
 class Res16UNetBase(ResNetBase):
     BLOCK = None
     PLANES = (32, 64, 128, 256, 256, 256, 256, 256)
@@ -153,12 +159,21 @@ class Res16UNetBase(ResNetBase):
         fused = core(conv_layer, norm, x)
         return fused if fused is not None else self.relu(norm(conv_layer(x)))
 
+    # blockN = Sequential of residual blocks: one autograd node and one launch list per stage where the engine offers it
+    # (unscene3d_b200.engine.blocks.fused_stage), else the Sequential itself (whose blocks fuse one by one, see _ResidualBase)
+    stage_core = None
+
+    def _stage(self, blocks, x):
+        core = type(self).stage_core or _cuda_stage_core
+        fused = core(blocks, x)
+        return fused if fused is not None else blocks(x)
+
     def _encode(self, x):
         """Returns the five encoder outputs, fine to coarse: stem, block1..block4."""
         outs = [self._conv_norm_relu(self.conv0p1s1, self.bn0, x)]
         for i, s in self._ENC:
             t = self._conv_norm_relu(getattr(self, f"conv{i}p{s}s2"), getattr(self, f"bn{i}"), outs[-1])
-            outs.append(getattr(self, f"block{i}")(t))
+            outs.append(self._stage(getattr(self, f"block{i}"), t))
         return outs
 
     def _decode(self, enc):
@@ -166,7 +181,7 @@ class Res16UNetBase(ResNetBase):
         out, ups = enc[-1], []
         for (j, s), skip in zip(self._DEC, reversed(enc[:-1])):
             t = self._conv_norm_relu(getattr(self, f"convtr{j}p{s}s2"), getattr(self, f"bntr{j}"), out)
-            out = getattr(self, f"block{j + 1}")(me.cat(t, skip))
+            out = self._stage(getattr(self, f"block{j + 1}"), me.cat(t, skip))
             ups.append(out)
         return ups
 
