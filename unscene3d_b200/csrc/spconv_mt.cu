@@ -8,12 +8,14 @@
 // in flight per CTA: one weight slab (offset k, 64-channel chunk) is loaded ONCE into a B ring slot and
 // multiplied against the gathered A tiles of all T tiles, each accumulating into its own TMEM accumulator.
 //
-//   warps 0-3  A producers: 16-byte cp.async (LDGSTS) from the bf16 planes (hi, + lo for the three-term
-//              split) straight into K-major SWIZZLE_128B slots, zero-fill for absent neighbours;
-//              cp.async.wait_group (lag) -> fence.proxy.async -> mbarrier arrive
-//   warp 4     B loader: cp.async.bulk of the pre-packed, pre-swizzled weight slab
-//   warp 5     MMA issuer: tcgen05.mma M=128, N=Cout, K=16 (x3 for the split); tcgen05.commit frees slots
-//   warps 6-9  epilogue: tcgen05.ld -> (+bias, +=) -> fp32 rows
+//   warps 0-7    A producers: 16-byte cp.async (LDGSTS, PTX ignore-src predicate for absent neighbours, one 32 x 32 -> 64 bit
+//                multiply-add per row address) from the bf16 planes (hi, + lo for the three-term split) straight into K-major
+//                SWIZZLE_128B slots; completion by cp.async.mbarrier.arrive.noinc
+//   warp 8       B loader: cp.async.bulk of the pre-packed, pre-swizzled weight slab
+//   warps 9,15-17 MMA issuers, one per tile of the group: tcgen05.mma M=128, N=Cout (2 Cout for the fused operand), K=16;
+//                tcgen05.commit frees slots
+//   warps 10-13, 18-21  two epilogue sets (set e: tiles e, e + 2): tcgen05.ld -> (+bias, +=) -> fp32 rows, BatchNorm column sums
+//   warp 14      neighbour-index ring
 //
 // Round 2:
 //   * warp 10 streams the neighbour indices of the next NIDX (super-tile, offset) pairs into a shared-memory ring with

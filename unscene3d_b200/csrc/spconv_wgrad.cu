@@ -13,12 +13,14 @@
 // each offset of the group (A ring), each offset accumulating into its own TMEM accumulator — the dY stream,
 // which a one-offset-per-CTA layout re-reads 27 times, is read ceil(27 / KG) times.
 //
-//   warps 0-3  producers: 16-byte cp.async into the swizzled slabs (zero-fill for absent neighbours / rows past
-//              the split); one A ring slot = one plane of one (row block, offset) = 16 KB.  Completion is
-//              signalled by cp.async.mbarrier.arrive.noinc (the producers never wait for their own copies); the
-//              MMA warp crosses the generic -> async proxy with fence.proxy.async after its wait
-//   warp 4     MMA issuer (warp-uniform control flow, one elected lane issues)
-//   warps 0-3  epilogue at the end: tcgen05.ld -> red.global.add into dW
+//   warps 0-7  producers: 16-byte cp.async (ignore-src predicate) into the swizzled slabs (zero-fill for absent neighbours / rows
+//              past the split); one A ring slot = one plane of one (row block, offset) = 16 KB; neighbour indices are fetched one
+//              row block ahead.  Completion is signalled by cp.async.mbarrier.arrive.noinc (the producers never wait for their
+//              own copies); the MMA warps cross the generic -> async proxy with fence.proxy.async after their wait
+//   warps 8-9  MMA issuers (warp-uniform control flow, one elected lane issues): offset kq of the group belongs to warp kq % 2,
+//              with its own TMEM accumulators and its own A ring — tcgen05.mma issue blocks for about the instruction's execution
+//              time, so one issuer alone leaves the tensor pipe idle while it waits and books (profiles/r2_wgrad_roles.md)
+//   warps 0-7  epilogue at the end: tcgen05.ld -> red.global.add into dW
 #include "common.cuh"
 #include "tc_common.cuh"
 
