@@ -104,3 +104,44 @@ def test_launch_list_rejects_unknown_ops_without_a_device():
     flat = (ctypes.c_longlong * 27)(*([77] + [0] * 26))
     f = (ctypes.c_double * 2)(0.0, 0.0)
     assert lib.us3d_run_ops_flat(flat, f, 1, None) != 0 and b"unknown op kind 77" in lib.us3d_last_error()
+
+
+def test_launch_list_records_and_gradient_arena_host_logic():
+    """Host logic behind the launch lists (no device): every op is one row of 27 int64 (kind, 16 pointers, 10 integers) + 2 floats —
+    the layout us3d_run_ops_flat reads —, held tensors stay referenced until the list is dropped; the zero-filled arena of the weight
+    gradients hands out disjoint, 256-byte aligned, all-zero slices and starts a new buffer when one is exhausted."""
+    import torch
+
+    from unscene3d_b200 import _lib
+    from unscene3d_b200.engine import blocks as B
+    from unscene3d_b200.engine import functional as Fn
+
+    ops = B._Ops()
+    ops.emit(_lib.OP_BN_APPLY, (11, 12, 13), (1, 2))
+    ops.emit(_lib.OP_CONV, tuple(range(100, 116)), tuple(range(10)), 1e-5, 0.02)
+    assert ops.n == 2 and len(ops.a) == 2 * 27 and len(ops.f) == 4
+    assert ops.a[:27] == [_lib.OP_BN_APPLY, 11, 12, 13] + [0] * 13 + [1, 2] + [0] * 8
+    assert ops.a[27] == _lib.OP_CONV and ops.a[28:44] == list(range(100, 116)) and ops.a[44:54] == list(range(10))
+    assert ops.f[2:] == [1e-5, 0.02]
+    t = torch.zeros(3)
+    assert ops.hold(t, None) is t and ops.keep[0] is t
+    assert ctypes_sizeof_op() == 4 + 4 + 16 * 8 + 10 * 8 + 2 * 4  # int kind (+ padding), p[16], v[10], f[2]
+
+    arena = Fn._ZeroArena()
+    dev = torch.device("cpu")
+    a = arena.take(1000, dev)
+    b = arena.take(70, dev)
+    assert a.numel() == 1000 and b.numel() == 70 and float(a.abs().sum()) == 0.0 and float(b.abs().sum()) == 0.0
+    assert b.data_ptr() - a.data_ptr() == 1024 * 4  # slices start on 64-float (256-byte) granules of the buffer
+    a.fill_(1.0)
+    assert float(b.abs().sum()) == 0.0
+    big = arena.take((16 << 20) + 5, dev)  # larger than what is left: a fresh zero buffer, the earlier slices stay valid
+    assert big.numel() == (16 << 20) + 5 and float(big[:1000].abs().sum()) == 0.0 and float(a.sum()) == 1000.0
+
+
+def ctypes_sizeof_op():
+    import ctypes
+
+    from unscene3d_b200 import _lib
+
+    return ctypes.sizeof(_lib.Op)
