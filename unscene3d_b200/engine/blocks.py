@@ -456,6 +456,16 @@ def fused_basic_block(block, x):
 
 
 _N_SAVED = 18  # tensors FusedBasicBlockFunction saves per block
+_BIG_MAP_BYTES = 192 << 20
+
+
+def _big_map(t):
+    """A list allocates every tensor of its ops before the first of them runs and keeps them until it is launched, so a deferred
+    STAGE has the temporaries of all its blocks alive at once.  On maps whose row tensors are hundreds of MB that costs more than the
+    saved host time (measured: the 4 x 200k-voxel Mask3D step 103 -> 122-142 ms with stage-wide lists at the finest level, where a
+    tensor is 300-400 MB and the step is device-bound anyway; the 200k-voxel backbone step 14.3 -> 13.9 ms): there the stage is
+    launched block by block."""
+    return t.shape[0] * t.shape[1] * 4 > _BIG_MAP_BYTES
 
 
 class FusedStageFunction(torch.autograd.Function):
@@ -472,11 +482,16 @@ class FusedStageFunction(torch.autograd.Function):
         if _lists["on"] and mode != 0 and Fn._bn_fuse["on"]:
             try:
                 ops, cur, results = _Ops(), x, []
+                big = _big_map(x)
                 for i in range(nb):
                     r = FusedBasicBlockFunction._forward_ops(ops, cur, *params[9 * i:9 * i + 9], plans[i], mode)
                     results.append((cur,) + r)
                     cur = r[3]
-                _run(ops)
+                    if big:  # one list per block: see _big_map
+                        _run(ops)
+                        ops = _Ops()
+                if ops.n:
+                    _run(ops)
             except _Fallback:
                 _pending_meta.clear()
                 results = None
@@ -510,10 +525,15 @@ class FusedStageFunction(torch.autograd.Function):
         if _lists["on"] and mode != 0:
             try:
                 ops, cur, grads = _Ops(), dout, [None] * nb
+                big = _big_map(dout)
                 for i in reversed(range(nb)):
                     g = FusedBasicBlockFunction._backward_ops(ops, per[i], plans[i], ctx.trainings[i], cur, i > 0 or ctx.needs_input_grad[0], mode)
                     grads[i], cur = g, g[0]
-                _run(ops)
+                    if big:
+                        _run(ops)
+                        ops = _Ops()
+                if ops.n:
+                    _run(ops)
             except _Fallback:
                 _pending_meta.clear()
                 grads = None
