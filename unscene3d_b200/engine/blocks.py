@@ -478,10 +478,10 @@ class FusedStageFunction(torch.autograd.Function):
         x = Fn._rows(x)
         mode = Fn.get_precision()
         nb = len(plans)
-        results = None
+        results, done = [], 0  # done: blocks whose launches have been issued (their BatchNorm buffers are updated: never redo them)
         if _lists["on"] and mode != 0 and Fn._bn_fuse["on"]:
             try:
-                ops, cur, results = _Ops(), x, []
+                ops, cur = _Ops(), x
                 big = _big_map(x)
                 for i in range(nb):
                     r = FusedBasicBlockFunction._forward_ops(ops, cur, *params[9 * i:9 * i + 9], plans[i], mode)
@@ -489,18 +489,18 @@ class FusedStageFunction(torch.autograd.Function):
                     cur = r[3]
                     if big:  # one list per block: see _big_map
                         _run(ops)
-                        ops = _Ops()
+                        ops, done = _Ops(), i + 1
                 if ops.n:
                     _run(ops)
+                done = nb
             except _Fallback:
                 _pending_meta.clear()
-                results = None
-        if results is None:
-            cur, results = x, []
-            for i in range(nb):
-                r = FusedBasicBlockFunction._forward_calls(cur, *params[9 * i:9 * i + 9], plans[i])
-                results.append((cur,) + r)
-                cur = r[3]
+        del results[done:]  # blocks assembled but not launched
+        cur = results[-1][4] if results else x
+        for i in range(done, nb):
+            r = FusedBasicBlockFunction._forward_calls(cur, *params[9 * i:9 * i + 9], plans[i])
+            results.append((cur,) + r)
+            cur = r[3]
         saved, trainings, planes = [], [], []
         for i, (xi, y1, a1, y2, out, yd, m1, s1, m2, s2, md, sd, g1c, g2c, gdc, t1, t2, td) in enumerate(results):
             k1, k2, kd = params[9 * i], params[9 * i + 3], params[9 * i + 6]
@@ -521,27 +521,26 @@ class FusedStageFunction(torch.autograd.Function):
             _restore(per[i][2], ctx.planes[i][1])
         dout = Fn._rows(dout)
         mode = Fn.get_precision()
-        grads = None
+        grads, todo = [None] * nb, nb  # todo: blocks [0, todo) still have to run (the list route works from the last block down)
         if _lists["on"] and mode != 0:
             try:
-                ops, cur, grads = _Ops(), dout, [None] * nb
+                ops, cur = _Ops(), dout
                 big = _big_map(dout)
                 for i in reversed(range(nb)):
                     g = FusedBasicBlockFunction._backward_ops(ops, per[i], plans[i], ctx.trainings[i], cur, i > 0 or ctx.needs_input_grad[0], mode)
                     grads[i], cur = g, g[0]
                     if big:
                         _run(ops)
-                        ops = _Ops()
+                        ops, todo = _Ops(), i
                 if ops.n:
                     _run(ops)
+                todo = 0
             except _Fallback:
                 _pending_meta.clear()
-                grads = None
-        if grads is None:
-            cur, grads = dout, [None] * nb
-            for i in reversed(range(nb)):
-                g = FusedBasicBlockFunction._backward_calls_of(per[i], plans[i], ctx.trainings[i], cur, i > 0 or ctx.needs_input_grad[0])
-                grads[i], cur = g, g[0]
+        cur = grads[todo][0] if todo < nb else dout
+        for i in reversed(range(todo)):
+            g = FusedBasicBlockFunction._backward_calls_of(per[i], plans[i], ctx.trainings[i], cur, i > 0 or ctx.needs_input_grad[0])
+            grads[i], cur = g, g[0]
         flat = []
         for g in grads:
             flat += list(g[1:])
